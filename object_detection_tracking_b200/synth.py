@@ -1,0 +1,103 @@
+"""Seeded synthetic weights / frames for the detector, in the reference's variable naming.
+
+No model weights ship with the reference (download links only, README.md:83,105) and
+this environment has no network, so parity and the bench run on seeded random
+weights.  Names follow the Tensorpack-npz convention the reference loads
+(`obj_detect_tracking.py:417-443`; scopes from `nn.py:886-1005`,
+`models.py:984-1101`) so a real `.npz` drops in unchanged:
+
+  conv0/W, conv0/bn/{gamma,beta,mean/EMA,variance/EMA}
+  group{0..3}/block{i}/{conv1,conv2,conv3,convshortcut}/W (+ bn/..)
+  fpn/lateral_1x1_c{2..5}/{W,b}, fpn/posthoc_3x3_p{2..5}/{W,b}
+  rpn/conv0/{W,b}, rpn/class/{W,b}, rpn/box/{W,b}
+  fastrcnn/fc6/{W,b}, fastrcnn/fc7/{W,b}, fastrcnn/outputs/{class,box}/{W,b}
+
+Conv kernels are HWIO (`nn.py:350,367`), dense kernels [in,out] (`nn.py:753`).
+The distributions are chosen so activations stay O(1) through 33 residual blocks
+and the RPN / class logits have spread (otherwise every proposal collapses and
+parity would be vacuous).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _conv_w(rng, k, cin, cout, gain=2.0):
+    std = np.sqrt(gain / (k * k * cin))
+    return (rng.standard_normal((k, k, cin, cout)) * std).astype(np.float32)
+
+
+def _bn(rng, w, name, c, gamma_lo=0.8, gamma_hi=1.2):
+    w[name + "/bn/gamma"] = rng.uniform(gamma_lo, gamma_hi, c).astype(np.float32)
+    w[name + "/bn/beta"] = (rng.standard_normal(c) * 0.05).astype(np.float32)
+    w[name + "/bn/mean/EMA"] = (rng.standard_normal(c) * 0.05).astype(np.float32)
+    w[name + "/bn/variance/EMA"] = rng.uniform(0.8, 1.2, c).astype(np.float32)
+
+
+def synth_weights(cfg, seed: int = 1234) -> dict:
+    rng = np.random.default_rng(seed)
+    w = {}
+    w["conv0/W"] = _conv_w(rng, 7, 3, 64)
+    _bn(rng, w, "conv0", 64)
+    cin = 64
+    for g, (feat, count) in enumerate(zip((64, 128, 256, 512), cfg.resnet_num_block)):
+        for i in range(count):
+            p = "group%d/block%d" % (g, i)
+            w[p + "/conv1/W"] = _conv_w(rng, 1, cin, feat)
+            _bn(rng, w, p + "/conv1", feat)
+            w[p + "/conv2/W"] = _conv_w(rng, 3, feat, feat)
+            _bn(rng, w, p + "/conv2", feat)
+            w[p + "/conv3/W"] = _conv_w(rng, 1, feat, feat * 4)
+            # residual-branch last BN: small gamma keeps the running sum bounded
+            _bn(rng, w, p + "/conv3", feat * 4, 0.1, 0.3)
+            if cin != feat * 4:
+                w[p + "/convshortcut/W"] = _conv_w(rng, 1, cin, feat * 4, gain=1.0)
+                _bn(rng, w, p + "/convshortcut", feat * 4)
+            cin = feat * 4
+    nc = cfg.fpn_num_channel
+    for i, c in enumerate((256, 512, 1024, 2048)):
+        w["fpn/lateral_1x1_c%d/W" % (i + 2)] = _conv_w(rng, 1, c, nc, gain=0.25)
+        w["fpn/lateral_1x1_c%d/b" % (i + 2)] = (rng.standard_normal(nc) * 0.02).astype(np.float32)
+        w["fpn/posthoc_3x3_p%d/W" % (i + 2)] = _conv_w(rng, 3, nc, nc, gain=(0.12, 0.3, 0.8, 2.5)[i])
+        w["fpn/posthoc_3x3_p%d/b" % (i + 2)] = (rng.standard_normal(nc) * 0.02).astype(np.float32)
+    na = len(cfg.anchor_ratios)
+    w["rpn/conv0/W"] = _conv_w(rng, 3, nc, nc, gain=1.0)
+    w["rpn/conv0/b"] = (rng.standard_normal(nc) * 0.02).astype(np.float32)
+    w["rpn/class/W"] = (rng.standard_normal((1, 1, nc, na)) * 0.12).astype(np.float32)
+    w["rpn/class/b"] = (rng.standard_normal(na) * 0.1).astype(np.float32)
+    w["rpn/box/W"] = (rng.standard_normal((1, 1, nc, 4 * na)) * 0.03).astype(np.float32)
+    w["rpn/box/b"] = (rng.standard_normal(4 * na) * 0.02).astype(np.float32)
+    dim = cfg.fpn_frcnn_fc_head_dim
+    fin = nc * 7 * 7
+    w["fastrcnn/fc6/W"] = (rng.standard_normal((fin, dim)) * np.sqrt(2.0 / fin)).astype(np.float32)
+    w["fastrcnn/fc6/b"] = (rng.standard_normal(dim) * 0.02).astype(np.float32)
+    w["fastrcnn/fc7/W"] = (rng.standard_normal((dim, dim)) * np.sqrt(2.0 / dim)).astype(np.float32)
+    w["fastrcnn/fc7/b"] = (rng.standard_normal(dim) * 0.02).astype(np.float32)
+    ncls = cfg.num_class
+    w["fastrcnn/outputs/class/W"] = (rng.standard_normal((dim, ncls)) * 0.15).astype(np.float32)
+    w["fastrcnn/outputs/class/b"] = (rng.standard_normal(ncls) * 0.1).astype(np.float32)
+    nbox = ncls if not cfg.use_frcnn_class_agnostic else 1
+    w["fastrcnn/outputs/box/W"] = (rng.standard_normal((dim, nbox * 4)) * 0.03).astype(np.float32)
+    w["fastrcnn/outputs/box/b"] = (rng.standard_normal(nbox * 4) * 0.02).astype(np.float32)
+    return w
+
+
+def synth_frame(h: int, w: int, seed: int = 0, n_rects: int = 4) -> np.ndarray:
+    """uint8 [h, w, 3] BGR frame: low-pass noise + a few flat rectangles + white noise
+    (SURVEY.md section 8d), so RPN logits have spatial structure."""
+    rng = np.random.default_rng(seed)
+    gh, gw = max(2, h // 16), max(2, w // 16)
+    coarse = rng.uniform(0, 255, (gh, gw, 3)).astype(np.float32)
+    # separable bilinear up-sampling of the coarse grid (no cv2 dependency)
+    ys = np.linspace(0, gh - 1, h, dtype=np.float32)
+    xs = np.linspace(0, gw - 1, w, dtype=np.float32)
+    y0 = np.floor(ys).astype(np.int64); y1 = np.minimum(y0 + 1, gh - 1); fy = (ys - y0)[:, None, None]
+    x0 = np.floor(xs).astype(np.int64); x1 = np.minimum(x0 + 1, gw - 1); fx = (xs - x0)[None, :, None]
+    rows = coarse[y0] * (1 - fy) + coarse[y1] * fy
+    img = rows[:, x0] * (1 - fx) + rows[:, x1] * fx
+    for _ in range(n_rects):
+        rh, rw = int(rng.integers(h // 8, h // 2)), int(rng.integers(w // 10, w // 3))
+        ry, rx = int(rng.integers(0, h - rh)), int(rng.integers(0, w - rw))
+        img[ry:ry + rh, rx:rx + rw] = rng.uniform(0, 255, 3).astype(np.float32)
+    img += rng.uniform(-10, 10, img.shape).astype(np.float32)
+    return np.clip(img, 0, 255).astype(np.uint8)
