@@ -1,0 +1,103 @@
+/* libb200det -- C ABI of the B200-native detect -> embed -> associate hot path.
+ *
+ * Drop-in boundary for JunweiLiang/Object_Detection_Tracking: the entry points below are what the
+ * reference's Python call surface binds for this path (the reference has no native code of its own;
+ * its hot path is `sess.run` on a TF graph).  Citations are file:line in the reference repository.
+ *
+ *   models.get_model(config, gpuid, ...)                       models.py:97-119      -> b2_create + b2_load_weights
+ *   model.get_feed_dict_forward(img) + sess.run([final_boxes,
+ *       final_labels, final_probs, fpn_box_feat], feed_dict)   obj_detect_tracking.py:610-635,
+ *                                                              models.py:1629-1636   -> b2_detect_host / b2_detect
+ *   model.get_feed_dict_forward_multi(imgs) + sess.run         models.py:3301-3310,
+ *                                                              obj_detect_tracking_multi_queuer.py:474-480 -> same, batch > 1
+ *   initialize(load=True, ...) (.npz / ckpt name->array load)  obj_detect_tracking.py:392-448 -> b2_load_weights
+ *   NearestNeighborDistanceMetric.distance(features, targets)  deep_sort/nn_matching.py:156-177 -> b2_cosine_cost
+ *
+ * Conventions: every function returns 0 on success, <0 on error (message via b2_last_error()); no
+ * exceptions cross the ABI; plain pointers and sizes only.  A b2_ctx is bound to one device and is
+ * single-threaded (the reference calls sess.run from exactly one thread).  The library never
+ * allocates caller-visible output memory: callers pass capacity-sized buffers and receive counts.
+ */
+#ifndef B200DET_H_
+#define B200DET_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2_ctx b2_ctx;
+
+/* Mirrors the fields of the reference's argparse namespace that shape the inference graph
+ * (obj_detect_tracking.py:236-389). */
+typedef struct b2_config {
+  int32_t batch;              /* im_batch_size; frames per b2_detect call */
+  int32_t height, width;      /* frame size after resizeImage (nn.py:1540-1560), e.g. 720 x 1280 */
+  int32_t input_dtype;        /* 0 = float32 HWC BGR (the reference placeholder), 1 = uint8 HWC BGR */
+  int32_t num_class;          /* incl. background (15 ActEV, 81 COCO) */
+  int32_t resnet_blocks[4];   /* (3,4,23,3) R101, (3,4,6,3) R50 */
+  int32_t use_dilations;      /* --version 3: res5 dilation 2 */
+  int32_t class_agnostic;     /* use_frcnn_class_agnostic (versions 4-6) */
+  int32_t rpn_topk;           /* rpn_test_post_nms_topk */
+  int32_t result_per_im;      /* 100 */
+  int32_t fpn_num_channel;    /* 256 */
+  int32_t fc_head_dim;        /* 1024 */
+  int32_t precision;          /* 0 = fp16 operands / fp32 accumulate; 1 = split fp16 pair (~fp32 products) */
+  int32_t conv_impl;          /* 0 = tcgen05 tensor-core kernel, 1 = CUDA-core cross-check kernel */
+  int32_t use_cuda_graph;     /* replay the frame as one CUDA graph */
+  float max_size;             /* rounded up to a multiple of 32 by the caller */
+  float rpn_min_size, rpn_nms_thres, fastrcnn_nms_iou_thres, result_score_thres;
+  float anchor_strides[5], anchor_sizes[5], anchor_ratios[3];
+  float bbox_reg_weights[4];
+} b2_config;
+
+const char* b2_last_error(void);
+int b2_version(void);
+
+int b2_create(b2_ctx** out, int device, const b2_config* cfg);
+void b2_destroy(b2_ctx* ctx);
+
+/* Named fp32 host arrays in the reference's Tensorpack-npz naming ("conv0/W",
+ * "group1/block0/conv2/bn/mean/EMA", "fpn/lateral_1x1_c2/b", "fastrcnn/fc6/W", ...).
+ * BatchNorm is folded, kernels are packed K-major and split into fp16 planes on the device. */
+int b2_load_weights(b2_ctx* ctx, const char* const* names, const float* const* data, const int64_t* numel, int n);
+
+/* One pass of the hot path over `batch` frames resident on the device.  All pointers are device
+ * pointers; outputs: boxes [B,100,4] x1y1x2y2, probs [B,100], labels [B,100] (1-based), valid [B],
+ * box_feat [B*100,C,7,7] fp32 (feat_mode 0) or [B*100,C] mean-pooled (feat_mode 1); any may be NULL.
+ * Asynchronous on the context stream unless `sync` != 0. */
+int b2_detect(b2_ctx* ctx, const void* frames_dev, float* boxes, float* probs, int32_t* labels, int32_t* valid,
+              float* box_feat, int feat_mode, int sync);
+/* Same with host buffers (pinned for full speed): H2D of the frames, the pass, D2H of the results. */
+int b2_detect_host(b2_ctx* ctx, const void* frames_host, float* boxes, float* probs, int32_t* labels,
+                   int32_t* valid, float* box_feat, int feat_mode);
+
+/* Stage-addressable access for parity tests.  Activations are returned as fp32. */
+int b2_stage_shape(b2_ctx* ctx, const char* name, int64_t shape[4], int32_t* dtype /*0 f32, 1 i32*/);
+int b2_get_stage(b2_ctx* ctx, const char* name, void* dst_host, int64_t capacity_bytes);
+int b2_set_stage(b2_ctx* ctx, const char* name, const void* src_host, int64_t bytes);
+/* Run a subset of the pass: bit mask of B2_PHASE_*. */
+enum {
+  B2_PHASE_BACKBONE = 1, B2_PHASE_FPN = 2, B2_PHASE_RPN_HEAD = 4, B2_PHASE_PROPOSALS = 8,
+  B2_PHASE_ROI = 16, B2_PHASE_HEAD_FC = 32, B2_PHASE_POST = 64, B2_PHASE_BOX_FEAT = 128, B2_PHASE_ALL = 255
+};
+int b2_run_phases(b2_ctx* ctx, int phase_mask);
+/* Device time of the last b2_run_phases/b2_detect per phase (ms), measured with CUDA events. */
+int b2_phase_times(b2_ctx* ctx, float ms[8]);
+int b2_kernel_launches(b2_ctx* ctx);   /* kernels launched by one full pass */
+
+/* DeepSORT appearance cost: gallery [S,D] rows grouped per track by seg_offsets[T+1], dets [N,D];
+ * cost[T,N] = min over the track's rows of (1 - cos).  Host pointers. */
+int b2_cosine_cost(int device, const float* gallery, const int32_t* seg_offsets, int T, const float* dets, int N,
+                   int D, int precision, float* cost);
+
+/* Single-op entry used by the kernel parity tests (host pointers, NHWC activations, HWIO kernel). */
+int b2_op_conv2d(int device, const float* x, const float* w, const float* bias, const float* res, int B, int H, int W,
+                 int Cin, int R, int S, int Cout, int stride, int dil, int pad_t, int pad_b, int pad_l, int pad_r,
+                 int relu, int res_shift, int impl, int split, int a_mode, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* B200DET_H_ */

@@ -1,0 +1,166 @@
+"""Drop-in model objects for the reference's detect call surface.
+
+The reference drivers never touch TF ops: they call `models.get_model(...)`, read five tensor
+attributes and call `sess.run(fetches, feed_dict=model.get_feed_dict_forward(img))`
+(obj_detect_tracking.py:505,610-635; obj_detect_tracking_multi_queuer.py:474-480).  The frozen-graph
+classes show that boundary is meant to be swappable ("has the same interface as Mask_RCNN_FPN",
+models.py:196-263).  This module provides the same surface on top of libb200det:
+
+    model = get_model(config, gpuid=0, controller="/cpu:0", is_multi=False)     # models.py:97-119
+    model.image, model.final_boxes, model.final_labels, model.final_probs, model.fpn_box_feat,
+    model.final_valid_indices (batch mode)
+    model.get_feed_dict_forward(img) / model.get_feed_dict_forward_multi(imgs)  # models.py:1629,3301
+    sess = Session(); sess.run([model.final_boxes, ...], feed_dict=fd)
+
+Outputs follow the reference conventions: fresh, writable numpy arrays owned by the caller; boxes are
+x1,y1,x2,y2 in resized-image pixels; labels are 1-based (int64 single image, float32 batch).
+There is no CPU fallback: without the CUDA library or a B200 the calls raise.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .config import normalize_config
+from .engine import Detector
+
+
+class TensorHandle:
+    """Stands in for a tf.Tensor / placeholder: only identity and a name matter to the drivers."""
+
+    def __init__(self, model, name):
+        self.model = model
+        self.name = name
+
+    def __repr__(self):
+        return "<b200det tensor %s>" % self.name
+
+
+class Mask_RCNN_FPN:
+    """Single-image model object (reference: models.py:266-1813, inference surface only)."""
+
+    is_multi = False
+
+    def __init__(self, config, gpuid=0, precision="split", input_dtype="float32"):
+        self.config = normalize_config(config)
+        self.gpuid = gpuid
+        self.precision = precision
+        self.input_dtype = input_dtype
+        self.num_class = self.config.num_class
+        self.image = TensorHandle(self, "image:0")
+        self.final_boxes = TensorHandle(self, "final_boxes:0")          # exported names: models.py:138-146
+        self.final_labels = TensorHandle(self, "final_labels:0")
+        self.final_probs = TensorHandle(self, "final_probs:0")
+        self.fpn_box_feat = TensorHandle(self, "fpn_box_feat:0")
+        self.final_valid_indices = TensorHandle(self, "final_valid_indices:0")
+        self._weights = None
+        self._detectors = {}
+
+    # -- weights (reference: initialize(), obj_detect_tracking.py:392-448) ----------------------------
+    def set_weights(self, weights: dict):
+        self._weights = {k: np.asarray(v, dtype=np.float32) for k, v in weights.items()}
+        for d in self._detectors.values():
+            d.load_weights(self._weights)
+
+    def load_npz(self, path: str):
+        """Tensorpack-style .npz: names with or without the ':0' suffix (obj_detect_tracking.py:417-443)."""
+        with np.load(path) as z:
+            self.set_weights({(k[:-2] if k.endswith(":0") else k): z[k] for k in z.files})
+
+    # -- feed dicts -----------------------------------------------------------------------------------
+    def get_feed_dict_forward(self, imgdata):
+        """models.py:1629-1636: {image placeholder: float32 HWC BGR frame}."""
+        return {self.image: imgdata}
+
+    def get_feed_dict_forward_multi(self, imgdatas):
+        """models.py:3301-3310: list of equally sized frames -> [B,H,W,3]."""
+        return {self.image: np.stack(imgdatas, axis=0)}
+
+    # -- execution --------------------------------------------------------------------------------------
+    def _detector(self, B, H, W) -> Detector:
+        key = (B, H, W)
+        det = self._detectors.get(key)
+        if det is None:
+            if self._weights is None:
+                raise RuntimeError("model has no weights: call set_weights()/load_npz() first")
+            det = Detector(self.config, B, H, W, device=self.gpuid, input_dtype=self.input_dtype,
+                           precision=self.precision)
+            det.load_weights(self._weights)
+            self._detectors[key] = det
+        return det
+
+    def _run(self, fetches, feed_dict):
+        img = feed_dict[self.image]
+        img = np.asarray(img)
+        single = img.ndim == 3
+        frames = img[None] if single else img
+        B, H, W, _ = frames.shape
+        det = self._detector(B, H, W)
+        want_feat = any(f is self.fpn_box_feat for f in fetches)
+        out = det.detect_host(frames, want_feat=want_feat)
+        valid = out["valid"]
+        res = []
+        for f in fetches:
+            if single:
+                r = int(valid[0])
+                if f is self.final_boxes:
+                    res.append(out["boxes"][0, :r].copy())
+                elif f is self.final_labels:
+                    res.append(out["labels"][0, :r].astype(np.int64))          # models.py:932: int64, class+1
+                elif f is self.final_probs:
+                    res.append(out["probs"][0, :r].copy())
+                elif f is self.fpn_box_feat:
+                    res.append(out["feat"][:r].copy())
+                elif f is self.final_valid_indices:
+                    res.append(valid.copy())
+                else:
+                    raise KeyError("unknown fetch %r" % (f,))
+            else:
+                if f is self.final_boxes:
+                    res.append(out["boxes"].copy())
+                elif f is self.final_labels:
+                    res.append(out["labels"].astype(np.float32))              # models.py:2973: float32 in batch mode
+                elif f is self.final_probs:
+                    res.append(out["probs"].copy())
+                elif f is self.final_valid_indices:
+                    res.append(valid.copy())
+                elif f is self.fpn_box_feat:
+                    R = det.R
+                    res.append(np.concatenate([out["feat"][b * R:b * R + int(valid[b])] for b in range(B)], axis=0))
+                else:
+                    raise KeyError("unknown fetch %r" % (f,))
+        return res
+
+
+class Mask_RCNN_FPN_multi(Mask_RCNN_FPN):
+    """Fixed-batch model object (reference: models.py:1969-3487)."""
+
+    is_multi = True
+
+
+class Session:
+    """`sess.run(fetches, feed_dict=...)` for fetches that all belong to one model object."""
+
+    def run(self, fetches, feed_dict=None):
+        single = not isinstance(fetches, (list, tuple))
+        flist = [fetches] if single else list(fetches)
+        model = flist[0].model
+        out = model._run(flist, feed_dict or {})
+        return out[0] if single else out
+
+    def close(self):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def get_model(config, gpuid=0, task=0, controller="/cpu:0", is_multi=False, **kw):
+    """models.get_model (models.py:97-119).  `controller`/`task` are TF device-placement arguments with
+    no meaning here; kept for signature compatibility."""
+    if getattr(config, "is_efficientdet", False):
+        raise NotImplementedError("EfficientDet path (efficientdet_wrapper.py) is not built yet")
+    cls = Mask_RCNN_FPN_multi if is_multi else Mask_RCNN_FPN
+    return cls(config, gpuid=gpuid, **kw)

@@ -1,0 +1,528 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM), operands staged by TMA.
+//
+//   D[M = B*Ho*Wo pixels, N = Cout] = A[M, K = R*S*Cin] * W[N, K]^T   (+bias, +residual, ReLU)
+//
+// * A is never materialised: each K-block (one filter tap x 64 input channels) of a 128-pixel tile
+//   is fetched straight from the NHWC activation tensor by ONE TMA im2col load
+//   (cp.async.bulk.tensor.4d...im2col): padding, stride, dilation and the wrap of a pixel run across
+//   image rows / batch images are all resolved by the tensor map (zero fill outside the image).
+// * W is pre-packed [Cout][R][S][Cin] (K-major); a 2D tiled TMA load brings block_n x 64 per K-block.
+// * Both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes directly.
+// * One elected thread issues tcgen05.mma (M=128, N=block_n, K=16); accumulators live in TMEM
+//   (double buffered: the epilogue of tile i overlaps the main loop of tile i+1).
+// * Warp roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
+//   warps4-7 = epilogue (TMEM -> registers -> bias/residual/ReLU -> HBM).
+// * Persistent: grid = min(#tiles, #SMs), static round-robin tile schedule.
+// * SPLIT precision: every operand is an fp16 pair (hi, lo') with x = hi + lo'/2048.  Three MMAs per
+//   K-step -- acc0 += Ahi*Bhi ; acc1 += Ahi*Blo' + Alo'*Bhi -- and D = acc0 + acc1/2048 recover
+//   ~fp32 products on the fp16 tensor pipe (needed for the 1e-3 box parity of the north star).
+//
+// Reference ops replaced: nn.conv2d (nn.py:337-381) + BatchNorm inference (nn.py:1771-1774, folded into
+// weights/bias) + ReLU (nn.py:606-613) + residual add (nn.py:519-521) + FPN upsample-add
+// (nn.py:989-996) + dense (nn.py:730-774).
+#include <vector>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace b2 {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                 // fp16 elements = one 128-byte swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 256;
+constexpr int kTmemCols = 512;
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 200 * 1024;
+
+struct ConvTcParams {
+  int M, Ho, Wo, HoWo;
+  int stride, dil, lower_h, lower_w;
+  int S, cin_blocks, num_kb;
+  int block_n, num_n_blocks, num_tiles;
+  int a_mode;   // 0 = A is a plain [M][Cin] matrix (2D tiled TMA), 1 = im2col TMA
+  uint32_t idesc;
+  uint32_t b_bytes, stage_bytes;
+  int num_stages;
+  __half* out_hi;
+  __half* out_lo;
+  float* out_f32;
+  int ldc, out_H, out_W, off_h, off_w;
+  const float* bias;
+  const __half* res_hi;
+  const __half* res_lo;
+  int ldr, res_H, res_W, res_shift;
+  int relu;
+};
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// 16 consecutive output channels of one pixel: bias, residual, ReLU, store (fp16 hi/lo planes or fp32).
+template <bool SPLIT>
+__device__ __forceinline__ void epilogue_chunk16(const ConvTcParams& p, const uint32_t (&a0)[16],
+                                                 const uint32_t (&a1)[16], size_t opix, size_t rpix, int n,
+                                                 bool valid) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    v[j] = __uint_as_float(a0[j]);
+    if (SPLIT) v[j] = fmaf(__uint_as_float(a1[j]), kLoInv, v[j]);
+  }
+  if (!valid) return;
+  const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float4 b = __ldg(b4 + j);
+    v[4 * j + 0] += b.x;
+    v[4 * j + 1] += b.y;
+    v[4 * j + 2] += b.z;
+    v[4 * j + 3] += b.w;
+  }
+  if (p.res_hi != nullptr) {
+    const uint4* r4 = reinterpret_cast<const uint4*>(p.res_hi + rpix * p.ldr + n);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      uint4 r = __ldg(r4 + j);
+      const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 f = __half22float2(h[t]);
+        v[8 * j + 2 * t] += f.x;
+        v[8 * j + 2 * t + 1] += f.y;
+      }
+    }
+    if (SPLIT && p.res_lo != nullptr) {
+      const uint4* l4 = reinterpret_cast<const uint4*>(p.res_lo + rpix * p.ldr + n);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        uint4 r = __ldg(l4 + j);
+        const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float2 f = __half22float2(h[t]);
+          v[8 * j + 2 * t] = fmaf(f.x, kLoInv, v[8 * j + 2 * t]);
+          v[8 * j + 2 * t + 1] = fmaf(f.y, kLoInv, v[8 * j + 2 * t + 1]);
+        }
+      }
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
+  if (p.out_f32 != nullptr) {
+    float4* o = reinterpret_cast<float4*>(p.out_f32 + opix * p.ldc + n);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    return;
+  }
+  uint32_t hi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) hi[j] = pack_half2(v[2 * j], v[2 * j + 1]);
+  uint4* oh = reinterpret_cast<uint4*>(p.out_hi + opix * p.ldc + n);
+  oh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  oh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+  if (SPLIT && p.out_lo != nullptr) {
+    uint32_t lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float2 h = __half22float2(*reinterpret_cast<__half2*>(&hi[j]));
+      lo[j] = pack_half2((v[2 * j] - h.x) * kLoScale, (v[2 * j + 1] - h.y) * kLoScale);
+    }
+    uint4* ol = reinterpret_cast<uint4*>(p.out_lo + opix * p.ldc + n);
+    ol[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    ol[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+  }
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               const __grid_constant__ ConvTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms need 1024-byte aligned tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + static_cast<size_t>(p.num_stages) * p.stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* tmem_full = bars + 2 * kMaxStages;
+  uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi);
+    tma_prefetch_desc(&tmB_hi);
+    if (SPLIT) {
+      tma_prefetch_desc(&tmA_lo);
+      tma_prefetch_desc(&tmB_lo);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.num_stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);   // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_holder, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const uint32_t a_lo_off = kABytes;
+  const uint32_t b_hi_off = SPLIT ? 2 * kABytes : kABytes;
+  const uint32_t b_lo_off = b_hi_off + p.b_bytes;
+  // accumulator stage s: acc0 at column s*256, acc1 (split) at s*256 + 128
+  const uint32_t acc_stage_cols = 256;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_blocks;
+        const int n_blk = tile - m_blk * p.num_n_blocks;
+        const int m0 = m_blk * kBlockM;
+        const int n0 = n_blk * p.block_n;
+        int img = 0, ch = 0, cw = 0;
+        if (p.a_mode == 1) {
+          img = m0 / p.HoWo;
+          const int rem = m0 - img * p.HoWo;
+          const int pp = rem / p.Wo;
+          const int qq = rem - pp * p.Wo;
+          ch = p.lower_h + pp * p.stride;
+          cw = p.lower_w + qq * p.stride;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = tiles + static_cast<size_t>(stage) * p.stage_bytes;
+          mbar_expect_tx(&full_bar[stage], p.stage_bytes);
+          const int tap = kb / p.cin_blocks;
+          const int cb = kb - tap * p.cin_blocks;
+          if (p.a_mode == 1) {
+            const int r = tap / p.S;
+            const int s = tap - r * p.S;
+            const uint16_t ow = static_cast<uint16_t>(s * p.dil);
+            const uint16_t oh = static_cast<uint16_t>(r * p.dil);
+            tma_load_im2col_4d(st, &tmA_hi, &full_bar[stage], cb * kBlockK, cw, ch, img, ow, oh);
+            if (SPLIT) tma_load_im2col_4d(st + a_lo_off, &tmA_lo, &full_bar[stage], cb * kBlockK, cw, ch, img, ow, oh);
+          } else {
+            tma_load_2d(st, &tmA_hi, &full_bar[stage], cb * kBlockK, m0);
+            if (SPLIT) tma_load_2d(st + a_lo_off, &tmA_lo, &full_bar[stage], cb * kBlockK, m0);
+          }
+          tma_load_2d(st + b_hi_off, &tmB_hi, &full_bar[stage], kb * kBlockK, n0);
+          if (SPLIT) tma_load_2d(st + b_lo_off, &tmB_lo, &full_bar[stage], kb * kBlockK, n0);
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + as * acc_stage_cols;
+        const uint32_t acc1 = acc0 + 128;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(tiles + static_cast<size_t>(stage) * p.stage_bytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint32_t koff = k * kUmmaK * 2;   // bytes along K inside the 128B swizzle row
+            const uint64_t a_hi = make_smem_desc_sw128(st + koff);
+            const uint64_t b_hi = make_smem_desc_sw128(st + b_hi_off + koff);
+            const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
+            umma_f16(acc0, a_hi, b_hi, p.idesc, first);
+            if (SPLIT) {
+              const uint64_t a_lo = make_smem_desc_sw128(st + a_lo_off + koff);
+              const uint64_t b_lo = make_smem_desc_sw128(st + b_lo_off + koff);
+              umma_f16(acc1, a_hi, b_lo, p.idesc, first);
+              umma_f16(acc1, a_lo, b_hi, p.idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[as]);        // accumulator complete -> epilogue
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = ew * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.num_n_blocks;
+      const int n_blk = tile - m_blk * p.num_n_blocks;
+      const int m = m_blk * kBlockM + row;
+      const int n0 = n_blk * p.block_n;
+      const bool valid = m < p.M;
+      size_t opix = 0, rpix = 0;
+      if (valid) {
+        const int img = m / p.HoWo;
+        const int rem = m - img * p.HoWo;
+        const int pp = rem / p.Wo + p.off_h;
+        const int qq = rem - (rem / p.Wo) * p.Wo + p.off_w;
+        opix = (static_cast<size_t>(img) * p.out_H + pp) * p.out_W + qq;
+        rpix = (static_cast<size_t>(img) * p.res_H + (pp >> p.res_shift)) * p.res_W + (qq >> p.res_shift);
+      }
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * acc_stage_cols;
+      for (int c = 0; c < p.block_n; c += 16) {
+        uint32_t a0[16], a1[16];
+        tmem_ld_32x32b_x16(tacc + c, a0);
+        if (SPLIT) tmem_ld_32x32b_x16(tacc + 128 + c, a1);
+        tmem_ld_wait();
+        epilogue_chunk16<SPLIT>(p, a0, a1, opix, rpix, n0 + c, valid);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
+EncodeIm2colFn g_encode_im2col = nullptr;
+int g_driver_version = 0;
+
+void small_tensor_fixup(CUtensorMap* m, size_t bytes) {
+  // Driver <= 13.1 mis-encodes maps of tensors smaller than 128 KiB (bit 21 of the 2nd qword); the
+  // vendored CuTe applies the same fix-up (cute/atom/copy_traits_sm90_tma.hpp).
+  if (g_driver_version <= 13010 && bytes < 131072) reinterpret_cast<uint64_t*>(m)[1] &= ~(1ull << 21);
+}
+
+int encode_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+              uint32_t box_inner, uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: " + std::to_string(static_cast<int>(r)));
+    return -1;
+  }
+  small_tensor_fixup(m, static_cast<size_t>(outer) * row_stride_bytes);
+  return 0;
+}
+
+}  // namespace
+
+struct ConvPlan {
+  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+  ConvTcParams p;
+  bool split;
+  int grid;
+  size_t smem_bytes;
+};
+
+int conv_tc_init() {
+  if (g_encode_tiled && g_encode_im2col) return 0;
+  B2_CUDA(cudaDriverGetVersion(&g_driver_version));
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  B2_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  B2_CHECK(fn != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+  g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  fn = nullptr;
+  B2_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q));
+  B2_CHECK(fn != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeIm2col not available");
+  g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+  B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  return 0;
+}
+
+static int pick_block_n(int cout_pad, bool split) {
+  const int cap = split ? 128 : 256;
+  if (cout_pad <= cap) return cout_pad;
+  for (int bn = cap; bn >= 16; bn -= 16)
+    if (cout_pad % bn == 0) return bn;
+  return 16;
+}
+
+static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, const ConvIO& io, bool split,
+                      int num_sms, int force_a_mode) {
+  B2_CHECK(conv_tc_init() == 0, "conv_tc_init failed");
+  B2_CHECK(d.Cin % kBlockK == 0, "conv_tc: Cin must be a multiple of 64");
+  B2_CHECK(w.Cout_pad % 16 == 0, "conv_tc: Cout_pad must be a multiple of 16");
+  B2_CHECK(w.K == d.R * d.S * d.Cin, "conv_tc: packed weight K mismatch");
+  B2_CHECK(!split || (io.in_lo && w.w_lo), "conv_tc: split precision needs lo planes");
+  ConvTcParams& p = pl->p;
+  const int Ho = d.Ho(), Wo = d.Wo();
+  B2_CHECK(Ho > 0 && Wo > 0, "conv_tc: empty output");
+  p.M = d.B * Ho * Wo;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  p.HoWo = Ho * Wo;
+  p.stride = d.stride;
+  p.dil = d.dil;
+  p.lower_h = -d.pad_t;
+  p.lower_w = -d.pad_l;
+  p.S = d.S;
+  p.cin_blocks = d.Cin / kBlockK;
+  p.num_kb = d.R * d.S * p.cin_blocks;
+  p.block_n = pick_block_n(w.Cout_pad, split);
+  p.num_n_blocks = w.Cout_pad / p.block_n;
+  B2_CHECK(p.num_n_blocks * p.block_n == w.Cout_pad, "conv_tc: Cout_pad not divisible by block_n");
+  const int num_m_blocks = (p.M + kBlockM - 1) / kBlockM;
+  p.num_tiles = num_m_blocks * p.num_n_blocks;
+  p.idesc = make_idesc_f16(kBlockM, p.block_n);
+  p.b_bytes = static_cast<uint32_t>(p.block_n) * kBlockK * 2;
+  p.stage_bytes = (kABytes + p.b_bytes) * (split ? 2 : 1);
+  p.num_stages = kSmemBudget / static_cast<int>(p.stage_bytes);
+  if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+  B2_CHECK(p.num_stages >= 2, "conv_tc: tile too large for shared memory");
+  p.out_hi = io.out_hi;
+  p.out_lo = io.out_lo;
+  p.out_f32 = io.out_f32;
+  p.ldc = d.ldc;
+  p.out_H = d.out_H;
+  p.out_W = d.out_W;
+  p.off_h = d.off_h;
+  p.off_w = d.off_w;
+  B2_CHECK(d.ldc >= w.Cout_pad && d.ldc % 8 == 0, "conv_tc: ldc must cover Cout_pad");
+  B2_CHECK(Ho + d.off_h <= d.out_H && Wo + d.off_w <= d.out_W, "conv_tc: output does not fit buffer");
+  p.bias = w.bias;
+  p.res_hi = io.res_hi;
+  p.res_lo = io.res_lo;
+  p.ldr = d.ldr;
+  p.res_H = d.res_H;
+  p.res_W = d.res_W;
+  p.res_shift = d.res_shift;
+  p.relu = d.relu;
+  pl->split = split;
+  pl->grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  pl->smem_bytes = static_cast<size_t>(p.num_stages) * p.stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+
+  const int in_ld = d.in_ld > 0 ? d.in_ld : d.Cin;
+  const bool plain = (d.R == 1 && d.S == 1 && d.stride == 1 && d.pad_t == 0 && d.pad_b == 0 && d.pad_l == 0 &&
+                      d.pad_r == 0 && d.in_H == d.in_pitch_H && d.in_W == d.in_pitch_W);
+  p.a_mode = plain ? 0 : 1;
+  if (force_a_mode >= 0) {
+    B2_CHECK(force_a_mode == 1 || plain, "conv_tc: tiled A mode needs a plain 1x1 conv");
+    p.a_mode = force_a_mode;
+  }
+  const size_t in_bytes = static_cast<size_t>(d.B) * d.in_pitch_H * d.in_pitch_W * in_ld * 2;
+  for (int plane = 0; plane < (split ? 2 : 1); ++plane) {
+    CUtensorMap* mA = plane == 0 ? &pl->tmA_hi : &pl->tmA_lo;
+    CUtensorMap* mB = plane == 0 ? &pl->tmB_hi : &pl->tmB_lo;
+    const __half* a = plane == 0 ? io.in_hi : io.in_lo;
+    const __half* b = plane == 0 ? w.w_hi : w.w_lo;
+    if (p.a_mode == 0) {
+      if (encode_2d(mA, a, d.Cin, static_cast<uint64_t>(d.B) * d.in_H * d.in_W, static_cast<uint64_t>(in_ld) * 2,
+                    kBlockK, kBlockM))
+        return -1;
+    } else {
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(d.Cin), static_cast<cuuint64_t>(d.in_W),
+                            static_cast<cuuint64_t>(d.in_H), static_cast<cuuint64_t>(d.B)};
+      cuuint64_t strides[3] = {static_cast<cuuint64_t>(in_ld) * 2,
+                               static_cast<cuuint64_t>(d.in_pitch_W) * in_ld * 2,
+                               static_cast<cuuint64_t>(d.in_pitch_H) * d.in_pitch_W * in_ld * 2};
+      // bounding box of filter base positions: lower = -pad, upper = pad_after - (k-1)*dilation  {W, H}
+      int lower[2] = {-d.pad_l, -d.pad_t};
+      int upper[2] = {d.pad_r - (d.S - 1) * d.dil, d.pad_b - (d.R - 1) * d.dil};
+      cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(d.stride), static_cast<cuuint32_t>(d.stride), 1};
+      CUresult r = g_encode_im2col(mA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(a), dims, strides,
+                                   lower, upper, kBlockK, kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeIm2col failed: " + std::to_string(static_cast<int>(r)) + " (Cin=" +
+                  std::to_string(d.Cin) + " W=" + std::to_string(d.in_W) + " H=" + std::to_string(d.in_H) + ")");
+        return -1;
+      }
+      small_tensor_fixup(mA, in_bytes);
+    }
+    if (encode_2d(mB, b, w.K, w.Cout_pad, static_cast<uint64_t>(w.K) * 2, kBlockK, p.block_n)) return -1;
+  }
+  if (!split) {
+    pl->tmA_lo = pl->tmA_hi;
+    pl->tmB_lo = pl->tmB_hi;
+  }
+  return 0;
+}
+
+ConvPlan* conv_tc_plan_create(const ConvDesc& d, const ConvWeights& w, const ConvIO& io, bool split, int num_sms) {
+  ConvPlan* pl = new ConvPlan();
+  if (plan_build(pl, d, w, io, split, num_sms, d.force_a_mode) != 0) {
+    delete pl;
+    return nullptr;
+  }
+  return pl;
+}
+
+void conv_tc_plan_destroy(ConvPlan* p) { delete p; }
+
+int conv_tc_launch(const ConvPlan* pl, cudaStream_t stream) {
+  if (pl->split)
+    conv_tc_kernel<true><<<pl->grid, kThreads, pl->smem_bytes, stream>>>(pl->tmA_hi, pl->tmA_lo, pl->tmB_hi,
+                                                                          pl->tmB_lo, pl->p);
+  else
+    conv_tc_kernel<false><<<pl->grid, kThreads, pl->smem_bytes, stream>>>(pl->tmA_hi, pl->tmA_lo, pl->tmB_hi,
+                                                                           pl->tmB_lo, pl->p);
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b2

@@ -1,0 +1,1010 @@
+// libb200det engine: context, weight folding/packing, the static per-frame launch plan, C ABI.
+//
+// The plan is built once per (batch, H, W): every activation buffer, every TMA tensor map and every
+// kernel parameter block is fixed, so one frame is a fixed sequence of ~150 launches that is captured
+// into a CUDA graph and replayed.  Graph structure follows Mask_RCNN_FPN.build_forward
+// (models.py:488-973); citations at each phase.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/b200det.h"
+#include "common.h"
+#include "kernels.h"
+
+namespace b2 {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* last_error() { return g_err.c_str(); }
+
+namespace {
+
+__global__ void subsample2_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, int B, int H,
+                                  int W, int C, __half* __restrict__ out_hi, __half* __restrict__ out_lo, int Ho,
+                                  int Wo) {
+  const int cvec = C / 8;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * cvec;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(idx % cvec);
+    const size_t pix = idx / cvec;
+    const int b = static_cast<int>(pix / (static_cast<size_t>(Ho) * Wo));
+    const int rem = static_cast<int>(pix % (static_cast<size_t>(Ho) * Wo));
+    const int p = rem / Wo, q = rem % Wo;
+    const size_t src = ((static_cast<size_t>(b) * H + 2 * p) * W + 2 * q) * C + cv * 8;
+    *reinterpret_cast<uint4*>(out_hi + pix * C + cv * 8) = *reinterpret_cast<const uint4*>(in_hi + src);
+    if (out_lo) *reinterpret_cast<uint4*>(out_lo + pix * C + cv * 8) = *reinterpret_cast<const uint4*>(in_lo + src);
+  }
+}
+
+// mean over the 7x7 bins of fpn_box_feat (deep_sort/utils.py:27-28 does this on the host)
+__global__ void pool_feat_kernel(const float* __restrict__ feat, int rows, int C, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * C) return;
+  const float* f = feat + static_cast<size_t>(idx) * 49;
+  float s = 0.f;
+  for (int i = 0; i < 49; ++i) s += f[i];
+  out[idx] = s / 49.f;
+}
+
+struct Planes {
+  __half* hi = nullptr;
+  __half* lo = nullptr;
+  int B = 0, H = 0, W = 0, C = 0;
+  size_t elems() const { return static_cast<size_t>(B) * H * W * C; }
+};
+
+struct Layer {
+  std::string name;        // reference variable scope, e.g. "group1/block0/conv2"
+  ConvDesc d;
+  ConvWeights w;
+  ConvIO io;
+  ConvPlan* plan = nullptr;
+  bool has_bn = false, has_bias = false;
+  int kind = 0;            // 0 conv HWIO, 1 fc6 (NCHW-flatten permute), 2 dense, 3 rpn class+box, 4 head outputs
+};
+
+struct StageRef {
+  int kind;                // 0 planes, 1 f32, 2 i32
+  Planes pl;
+  void* ptr = nullptr;
+  int64_t shape[4] = {1, 1, 1, 1};
+};
+
+enum { NPHASE = 8 };
+
+}  // namespace
+}  // namespace b2
+
+using namespace b2;
+
+struct b2_ctx {
+  b2_config cfg;
+  int device = 0, num_sms = 148;
+  bool split = false;
+  cudaStream_t stream = nullptr;
+  std::vector<void*> allocs;
+  std::vector<std::unique_ptr<Layer>> layers;
+  std::vector<Layer*> phase_layers[NPHASE];   // conv layers per phase, in launch order (phases with only convs)
+  std::map<std::string, StageRef> stages;
+  // geometry
+  int c1h = 0, c1w = 0, ch[4], cw[4], ph[5], pw[5], pfh[5], pfw[5];
+  // buffers
+  void* img = nullptr;
+  size_t img_bytes = 0;
+  float* stem_w = nullptr;
+  float* stem_b = nullptr;
+  Planes c1, pool, cfeat[4], lat[4], pfeat[5], rpn_h[5];
+  float* rpn_out[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  RpnParams rpn;
+  RoiAlignParams roi1, roi2;
+  HeadPostParams post;
+  Planes roi_feat, fc6, fc7;
+  float* head_logits = nullptr;
+  float* box_feat = nullptr;
+  float* box_feat_pooled = nullptr;
+  // launch bookkeeping
+  struct Step {
+    int phase;
+    int kind;   // 0 conv layer, 1 stem, 2 maxpool, 3 subsample p6, 4 proposals, 5 roialign1, 6 post, 7 roialign2
+    Layer* layer;
+  };
+  std::vector<Step> steps;
+  cudaGraphExec_t graph = nullptr;
+  bool weights_loaded = false;
+  cudaEvent_t ev[NPHASE + 1];
+  float phase_ms[NPHASE];
+  int launches = 0;
+
+  template <typename T>
+  T* alloc(size_t n, bool zero = true) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, n * sizeof(T) + 256) != cudaSuccess) return nullptr;
+    if (zero) cudaMemset(p, 0, n * sizeof(T) + 256);
+    allocs.push_back(p);
+    return static_cast<T*>(p);
+  }
+  bool alloc_planes(Planes& p, int B, int H, int W, int C) {
+    p.B = B; p.H = H; p.W = W; p.C = C;
+    p.hi = alloc<__half>(p.elems());
+    p.lo = split ? alloc<__half>(p.elems()) : nullptr;
+    return p.hi != nullptr && (!split || p.lo != nullptr);
+  }
+};
+
+namespace {
+
+void reg_planes(b2_ctx* c, const std::string& name, const Planes& p) {
+  StageRef s;
+  s.kind = 0;
+  s.pl = p;
+  s.shape[0] = p.B; s.shape[1] = p.H; s.shape[2] = p.W; s.shape[3] = p.C;
+  c->stages[name] = s;
+}
+void reg_raw(b2_ctx* c, const std::string& name, void* ptr, int kind, int64_t a, int64_t b, int64_t cc, int64_t d) {
+  StageRef s;
+  s.kind = kind;
+  s.ptr = ptr;
+  s.shape[0] = a; s.shape[1] = b; s.shape[2] = cc; s.shape[3] = d;
+  c->stages[name] = s;
+}
+
+// Adds one conv layer reading `in` (view in_H x in_W of the buffer) and writing `out`.
+Layer* add_conv(b2_ctx* c, int phase, const std::string& name, const Planes& in, int view_h, int view_w, int R,
+                int stride, int dil, int pt, int pb, int pl, int pr, int Cout, bool bn, bool bias, bool relu,
+                const Planes& out, int off_h, int off_w, const Planes* res, int res_shift, float* out_f32 = nullptr,
+                int ldc_f32 = 0, int kind = 0) {
+  std::unique_ptr<Layer> L(new Layer());
+  L->name = name;
+  L->has_bn = bn;
+  L->has_bias = bias;
+  L->kind = kind;
+  ConvDesc& d = L->d;
+  d.B = in.B; d.in_H = view_h; d.in_W = view_w; d.Cin = in.C;
+  d.in_pitch_H = in.H; d.in_pitch_W = in.W; d.in_ld = in.C;
+  d.R = R; d.S = R; d.stride = stride; d.dil = dil;
+  d.pad_t = pt; d.pad_b = pb; d.pad_l = pl; d.pad_r = pr;
+  d.Cout = Cout;
+  d.relu = relu ? 1 : 0;
+  d.off_h = off_h; d.off_w = off_w;
+  if (out_f32) {
+    d.out_H = d.Ho(); d.out_W = d.Wo(); d.ldc = ldc_f32;
+  } else {
+    d.out_H = out.H; d.out_W = out.W; d.ldc = out.C;
+  }
+  if (res) {
+    d.res_H = res->H; d.res_W = res->W; d.ldr = res->C; d.res_shift = res_shift;
+  }
+  L->w.Cout_pad = (Cout + 15) / 16 * 16;
+  L->w.K = R * R * in.C;
+  L->w.w_hi = c->alloc<__half>(static_cast<size_t>(L->w.Cout_pad) * L->w.K);
+  L->w.w_lo = c->split ? c->alloc<__half>(static_cast<size_t>(L->w.Cout_pad) * L->w.K) : nullptr;
+  L->w.bias = c->alloc<float>(L->w.Cout_pad);
+  L->io.in_hi = in.hi; L->io.in_lo = in.lo;
+  L->io.out_hi = out.hi; L->io.out_lo = out.lo; L->io.out_f32 = out_f32;
+  if (res) { L->io.res_hi = res->hi; L->io.res_lo = res->lo; }
+  Layer* raw = L.get();
+  c->layers.push_back(std::move(L));
+  c->steps.push_back({phase, 0, raw});
+  return raw;
+}
+
+int log2i(int v) { int r = 0; while ((1 << r) < v) ++r; return r; }
+
+// generate_anchors.py:42-109 restated for one (stride, size): the 3 ratio anchors of a cell.
+void cell_anchors(float stride, float size, const float* ratios, float out[3][4]) {
+  const double base = stride;
+  const double w0 = base, h0 = base, xc = 0.5 * (w0 - 1), yc = 0.5 * (h0 - 1);
+  const double area = w0 * h0;
+  const double scale = size / stride;
+  for (int i = 0; i < 3; ++i) {
+    const double ws = nearbyint(sqrt(area / ratios[i]));
+    const double hs = nearbyint(ws * ratios[i]);
+    // _mkanchors then _scale_enum (single scale)
+    const double x1 = xc - 0.5 * (ws - 1), x2 = xc + 0.5 * (ws - 1);
+    const double y1 = yc - 0.5 * (hs - 1), y2 = yc + 0.5 * (hs - 1);
+    const double w = x2 - x1 + 1, h = y2 - y1 + 1;
+    const double cx = x1 + 0.5 * (w - 1), cy = y1 + 0.5 * (h - 1);
+    const double W = w * scale, H = h * scale;
+    out[i][0] = static_cast<float>(cx - 0.5 * (W - 1));
+    out[i][1] = static_cast<float>(cy - 0.5 * (H - 1));
+    out[i][2] = static_cast<float>(cx + 0.5 * (W - 1));
+    out[i][3] = static_cast<float>(cy + 0.5 * (H - 1));
+  }
+}
+
+int build_plan(b2_ctx* c) {
+  const b2_config& cfg = c->cfg;
+  const int B = cfg.batch, H = cfg.height, W = cfg.width;
+  B2_CHECK(B >= 1 && H >= 32 && W >= 32, "b2_create: bad frame geometry");
+  B2_CHECK(cfg.fpn_num_channel == 256, "b2_create: fpn_num_channel must be 256");
+  B2_CHECK(cfg.rpn_topk >= 1 && cfg.rpn_topk <= 1024, "b2_create: rpn_topk must be in [1,1024]");
+  // ---- geometry (nn.py:843-944, tf_pad_reverse=True) ----
+  const int PH = (H + 31) / 32 * 32, PW = (W + 31) / 32 * 32;
+  c->c1h = (PH + 5 - 7) / 2 + 1;
+  c->c1w = (PW + 5 - 7) / 2 + 1;
+  int h = (c->c1h + 1 - 3) / 2 + 1, w = (c->c1w + 1 - 3) / 2 + 1;
+  for (int g = 0; g < 4; ++g) {
+    if (g > 0) { h = (h + 1 - 3) / 2 + 1; w = (w + 1 - 3) / 2 + 1; }
+    c->ch[g] = h; c->cw[g] = w;
+  }
+  for (int i = 0; i < 4; ++i) { c->pfh[i] = c->ch[i]; c->pfw[i] = c->cw[i]; }
+  c->pfh[4] = (c->ch[3] - 1) / 2 + 1;
+  c->pfw[4] = (c->cw[3] - 1) / 2 + 1;
+  for (int i = 0; i < 5; ++i) {
+    c->ph[i] = c->pfh[i]; c->pw[i] = c->pfw[i];
+    if (i < 3) {   // models.py:382-390 crop p2..p4 to ceil(H/stride)
+      const int s = static_cast<int>(cfg.anchor_strides[i]);
+      c->ph[i] = std::min(c->pfh[i], (H + s - 1) / s);
+      c->pw[i] = std::min(c->pfw[i], (W + s - 1) / s);
+    }
+  }
+  for (int i = 0; i < 3; ++i)
+    B2_CHECK(c->ch[i] == 2 * c->ch[i + 1] && c->cw[i] == 2 * c->cw[i + 1], "b2_create: FPN levels must nest 2x");
+
+  // ---- input + stem + pool (phase 0) ----
+  c->img_bytes = static_cast<size_t>(B) * H * W * 3 * (cfg.input_dtype == 1 ? 1 : 4);
+  c->img = c->alloc<uint8_t>(c->img_bytes);
+  c->stem_w = c->alloc<float>(147 * 64);
+  c->stem_b = c->alloc<float>(64);
+  B2_CHECK(c->alloc_planes(c->c1, B, c->c1h, c->c1w, 64), "alloc c1");
+  B2_CHECK(c->alloc_planes(c->pool, B, c->ch[0], c->cw[0], 64), "alloc pool");
+  c->steps.push_back({0, 1, nullptr});
+  c->steps.push_back({0, 2, nullptr});
+  reg_planes(c, "c1", c->c1);
+  reg_planes(c, "pool", c->pool);
+
+  // ---- ResNet groups (nn.py:459-588) ----
+  Planes cur = c->pool;
+  for (int g = 0; g < 4; ++g) {
+    const int feat = 64 << g, count = cfg.resnet_blocks[g];
+    const int gh = c->ch[g], gw = c->cw[g];
+    Planes pingpong[2];
+    B2_CHECK(c->alloc_planes(pingpong[0], B, gh, gw, feat * 4), "alloc group out");
+    B2_CHECK(c->alloc_planes(pingpong[1], B, gh, gw, feat * 4), "alloc group out");
+    Planes t1_first, t1, t2, t2_first, sc;
+    B2_CHECK(c->alloc_planes(t1_first, B, cur.H, cur.W, feat), "alloc t1");
+    B2_CHECK(c->alloc_planes(t1, B, gh, gw, feat), "alloc t1");
+    B2_CHECK(c->alloc_planes(t2, B, gh, gw, feat), "alloc t2");
+    B2_CHECK(c->alloc_planes(t2_first, B, gh, gw, feat), "alloc t2");
+    B2_CHECK(c->alloc_planes(sc, B, gh, gw, feat * 4), "alloc shortcut");
+    for (int i = 0; i < count; ++i) {
+      const std::string p = "group" + std::to_string(g) + "/block" + std::to_string(i);
+      const int stride = (g > 0 && i == 0) ? 2 : 1;
+      const bool in_last3 = i >= count - 3;
+      const int dil = (g == 3 && cfg.use_dilations && in_last3) ? 2 : 1;
+      const Planes& x = cur;
+      const Planes& a1 = (i == 0) ? t1_first : t1;
+      add_conv(c, 0, p + "/conv1", x, x.H, x.W, 1, 1, 1, 0, 0, 0, 0, feat, true, false, true, a1, 0, 0, nullptr, 0);
+      const Planes* a2 = &t2;
+      if (stride == 2) {
+        // pad [1,0] + 3x3 stride-2 VALID (nn.py:487-492); with dilation the output is padded [1,0] again
+        // (nn.py:493-497): written at offset (1,1) of a buffer whose first row/col stay zero.
+        a2 = &t2_first;
+        const int off = dil != 1 ? 1 : 0;
+        add_conv(c, 0, p + "/conv2", a1, a1.H, a1.W, 3, 2, dil, 1, 0, 1, 0, feat, true, false, true, *a2, off, off,
+                 nullptr, 0);
+      } else {
+        add_conv(c, 0, p + "/conv2", a1, a1.H, a1.W, 3, 1, dil, dil, dil, dil, dil, feat, true, false, true, *a2, 0,
+                 0, nullptr, 0);
+      }
+      const Planes* resid = &x;
+      if (x.C != feat * 4) {
+        // resnet_shortcut (nn.py:551-566): stride 2 => drop last row/col, 1x1 stride-2 VALID
+        if (stride == 2)
+          add_conv(c, 0, p + "/convshortcut", x, x.H, x.W, 1, 2, 1, 0, -1, 0, -1, feat * 4, true, false, false, sc, 0,
+                   0, nullptr, 0);
+        else
+          add_conv(c, 0, p + "/convshortcut", x, x.H, x.W, 1, 1, 1, 0, 0, 0, 0, feat * 4, true, false, false, sc, 0,
+                   0, nullptr, 0);
+        resid = &sc;
+      }
+      const Planes& out = pingpong[i & 1];
+      add_conv(c, 0, p + "/conv3", *a2, a2->H, a2->W, 1, 1, 1, 0, 0, 0, 0, feat * 4, true, false, true, out, 0, 0,
+               resid, 0);
+      cur = out;
+    }
+    c->cfeat[g] = cur;
+    reg_planes(c, "c" + std::to_string(g + 2), cur);
+  }
+
+  // ---- FPN (nn.py:947-1014), phase 1 ----
+  const int nc = cfg.fpn_num_channel;
+  for (int i = 3; i >= 0; --i) {
+    B2_CHECK(c->alloc_planes(c->lat[i], B, c->ch[i], c->cw[i], nc), "alloc lateral");
+    const std::string nm = "fpn/lateral_1x1_c" + std::to_string(i + 2);
+    add_conv(c, 1, nm, c->cfeat[i], c->ch[i], c->cw[i], 1, 1, 1, 0, 0, 0, 0, nc, false, true, false, c->lat[i], 0, 0,
+             i < 3 ? &c->lat[i + 1] : nullptr, 1);
+  }
+  for (int i = 0; i < 4; ++i) {
+    B2_CHECK(c->alloc_planes(c->pfeat[i], B, c->pfh[i], c->pfw[i], nc), "alloc p");
+    const std::string nm = "fpn/posthoc_3x3_p" + std::to_string(i + 2);
+    add_conv(c, 1, nm, c->lat[i], c->ch[i], c->cw[i], 3, 1, 1, 1, 1, 1, 1, nc, false, true, false, c->pfeat[i], 0, 0,
+             nullptr, 0);
+    reg_planes(c, "p" + std::to_string(i + 2), c->pfeat[i]);
+  }
+  B2_CHECK(c->alloc_planes(c->pfeat[4], B, c->pfh[4], c->pfw[4], nc), "alloc p6");
+  c->steps.push_back({1, 3, nullptr});
+  reg_planes(c, "p6", c->pfeat[4]);
+
+  // ---- RPN head (models.py:979-1009), phase 2; class+box 1x1 fused into one N=15 GEMM ----
+  for (int i = 0; i < 5; ++i) {
+    B2_CHECK(c->alloc_planes(c->rpn_h[i], B, c->ph[i], c->pw[i], nc), "alloc rpn hidden");
+    Layer* L0 = add_conv(c, 2, "rpn/conv0", c->pfeat[i], c->ph[i], c->pw[i], 3, 1, 1, 1, 1, 1, 1, nc, false, true,
+                         true, c->rpn_h[i], 0, 0, nullptr, 0);
+    (void)L0;
+    c->rpn_out[i] = c->alloc<float>(static_cast<size_t>(B) * c->ph[i] * c->pw[i] * 16 + 16 * 128);
+    add_conv(c, 2, "rpn/classbox", c->rpn_h[i], c->ph[i], c->pw[i], 1, 1, 1, 0, 0, 0, 0, 15, false, true, false,
+             Planes(), 0, 0, nullptr, 0, c->rpn_out[i], 16, 3);
+    reg_raw(c, "rpn_l" + std::to_string(i), c->rpn_out[i], 1, B, c->ph[i], c->pw[i], 16);
+  }
+
+  // ---- proposals (phase 3) ----
+  RpnParams& rp = c->rpn;
+  memset(&rp, 0, sizeof(rp));
+  const int K = cfg.rpn_topk;
+  for (int i = 0; i < 5; ++i) {
+    rp.logits[i] = c->rpn_out[i];
+    rp.h[i] = c->ph[i];
+    rp.w[i] = c->pw[i];
+    rp.stride[i] = cfg.anchor_strides[i];
+    cell_anchors(cfg.anchor_strides[i], cfg.anchor_sizes[i], cfg.anchor_ratios, rp.cell[i]);
+  }
+  rp.B = B; rp.topk = K;
+  rp.img_h = static_cast<float>(H); rp.img_w = static_cast<float>(W);
+  rp.decode_clip = logf(cfg.max_size / 16.0f);
+  {
+    const double dc = log(static_cast<double>(cfg.max_size) / 16.0);   // np.log in float64, cast at use
+    rp.decode_clip = static_cast<float>(dc);
+  }
+  rp.min_size = cfg.rpn_min_size;
+  rp.nms_thr = cfg.rpn_nms_thres;
+  rp.lvl_boxes = c->alloc<float>(static_cast<size_t>(B) * 5 * K * 4);
+  rp.lvl_scores = c->alloc<float>(static_cast<size_t>(B) * 5 * K);
+  rp.lvl_count = c->alloc<int>(B * 5);
+  rp.prop_boxes = c->alloc<float>(static_cast<size_t>(B) * K * 4);
+  rp.prop_scores = c->alloc<float>(static_cast<size_t>(B) * K);
+  rp.prop_count = c->alloc<int>(B);
+  c->steps.push_back({3, 4, nullptr});
+  reg_raw(c, "lvl_boxes", rp.lvl_boxes, 1, B, 5, K, 4);
+  reg_raw(c, "lvl_scores", rp.lvl_scores, 1, B, 5, K, 1);
+  reg_raw(c, "lvl_count", rp.lvl_count, 2, B, 5, 1, 1);
+  reg_raw(c, "proposal_boxes", rp.prop_boxes, 1, B, K, 4, 1);
+  reg_raw(c, "proposal_scores", rp.prop_scores, 1, B, K, 1, 1);
+  reg_raw(c, "proposal_count", rp.prop_count, 2, B, 1, 1, 1);
+
+  // ---- ROIAlign of the proposals (phase 4) ----
+  const int M = B * K;
+  const int Mpad = (M + 127) / 128 * 128;
+  B2_CHECK(c->alloc_planes(c->roi_feat, 1, 1, Mpad, 49 * nc), "alloc roi feat");
+  RoiAlignParams& r1 = c->roi1;
+  memset(&r1, 0, sizeof(r1));
+  for (int i = 0; i < 4; ++i) {
+    r1.feat_hi[i] = c->pfeat[i].hi;
+    r1.feat_lo[i] = c->pfeat[i].lo;
+    r1.H[i] = c->ph[i]; r1.W[i] = c->pw[i];
+    r1.pitch_H[i] = c->pfh[i]; r1.pitch_W[i] = c->pfw[i];
+    r1.inv_stride[i] = 1.0f / cfg.anchor_strides[i];
+  }
+  r1.C = nc; r1.B = B; r1.rois_per_image = K;
+  r1.boxes = rp.prop_boxes; r1.count = rp.prop_count;
+  r1.out_hi = c->roi_feat.hi; r1.out_lo = c->roi_feat.lo; r1.out_nchw = nullptr;
+  c->steps.push_back({4, 5, nullptr});
+  reg_planes(c, "roi_feat", c->roi_feat);
+
+  // ---- box head (models.py:1030-1108), phase 5: fc6, fc7, class+box outputs fused (N = 5*num_class) ----
+  const int dim = cfg.fc_head_dim;
+  B2_CHECK(dim % 64 == 0, "b2_create: fc_head_dim must be a multiple of 64");
+  B2_CHECK(c->alloc_planes(c->fc6, 1, 1, Mpad, dim), "alloc fc6");
+  B2_CHECK(c->alloc_planes(c->fc7, 1, 1, Mpad, dim), "alloc fc7");
+  const int nout = cfg.num_class + (cfg.class_agnostic ? 4 : cfg.num_class * 4);
+  const int ldo = (nout + 15) / 16 * 16;
+  c->head_logits = c->alloc<float>(static_cast<size_t>(Mpad) * ldo);
+  Planes rf = c->roi_feat; rf.W = M;
+  Planes f6 = c->fc6; f6.W = M;
+  Planes f7 = c->fc7; f7.W = M;
+  add_conv(c, 5, "fastrcnn/fc6", rf, 1, M, 1, 1, 1, 0, 0, 0, 0, dim, false, true, true, f6, 0, 0, nullptr, 0, nullptr,
+           0, 1);
+  add_conv(c, 5, "fastrcnn/fc7", f6, 1, M, 1, 1, 1, 0, 0, 0, 0, dim, false, true, true, f7, 0, 0, nullptr, 0, nullptr,
+           0, 2);
+  add_conv(c, 5, "fastrcnn/outputs", f7, 1, M, 1, 1, 1, 0, 0, 0, 0, nout, false, true, false, Planes(), 0, 0, nullptr,
+           0, c->head_logits, ldo, 4);
+  reg_planes(c, "fc6", f6);
+  reg_planes(c, "fc7", f7);
+  reg_raw(c, "head_logits", c->head_logits, 1, B, K, ldo, 1);
+
+  // ---- post-processing (phase 6) ----
+  HeadPostParams& hp = c->post;
+  memset(&hp, 0, sizeof(hp));
+  const int nc1 = cfg.num_class - 1, R = cfg.result_per_im;
+  hp.logits = c->head_logits; hp.ld = ldo; hp.num_class = cfg.num_class; hp.B = B; hp.rois_per_image = K;
+  hp.class_agnostic = cfg.class_agnostic;
+  hp.rois = rp.prop_boxes; hp.roi_count = rp.prop_count;
+  for (int i = 0; i < 4; ++i) hp.reg_w[i] = cfg.bbox_reg_weights[i];
+  hp.decode_clip = static_cast<float>(log(1333.0 / 16.0));   // decode_bbox_target default (nn.py:1518)
+  hp.img_h = static_cast<float>(H); hp.img_w = static_cast<float>(W);
+  hp.score_thresh = cfg.result_score_thres; hp.nms_thr = cfg.fastrcnn_nms_iou_thres;
+  hp.max_per_class = R; hp.max_total = R;
+  hp.probs = c->alloc<float>(static_cast<size_t>(M) * cfg.num_class);
+  hp.dec_boxes = c->alloc<float>(static_cast<size_t>(M) * nc1 * 4);
+  hp.cls_keep = c->alloc<int>(static_cast<size_t>(B) * nc1 * R);
+  hp.cls_count = c->alloc<int>(B * nc1);
+  hp.final_boxes = c->alloc<float>(static_cast<size_t>(B) * R * 4);
+  hp.final_probs = c->alloc<float>(static_cast<size_t>(B) * R);
+  hp.final_labels = c->alloc<int>(static_cast<size_t>(B) * R);
+  hp.final_count = c->alloc<int>(B);
+  c->steps.push_back({6, 6, nullptr});
+  reg_raw(c, "probs", hp.probs, 1, B, K, cfg.num_class, 1);
+  reg_raw(c, "dec_boxes", hp.dec_boxes, 1, B, K, nc1, 4);
+  reg_raw(c, "final_boxes", hp.final_boxes, 1, B, R, 4, 1);
+  reg_raw(c, "final_probs", hp.final_probs, 1, B, R, 1, 1);
+  reg_raw(c, "final_labels", hp.final_labels, 2, B, R, 1, 1);
+  reg_raw(c, "final_count", hp.final_count, 2, B, 1, 1, 1);
+
+  // ---- fpn_box_feat: ROIAlign of the final boxes (models.py:972-973), phase 7 ----
+  c->box_feat = c->alloc<float>(static_cast<size_t>(B) * R * nc * 49);
+  c->box_feat_pooled = c->alloc<float>(static_cast<size_t>(B) * R * nc);
+  RoiAlignParams& r2 = c->roi2;
+  r2 = r1;
+  r2.rois_per_image = R;
+  r2.boxes = hp.final_boxes; r2.count = hp.final_count;
+  r2.out_hi = nullptr; r2.out_lo = nullptr; r2.out_nchw = c->box_feat;
+  c->steps.push_back({7, 7, nullptr});
+  reg_raw(c, "fpn_box_feat", c->box_feat, 1, static_cast<int64_t>(B) * R, nc, 7, 7);
+
+  // ---- tensor-core plans ----
+  if (cfg.conv_impl == 0) {
+    for (auto& L : c->layers) {
+      L->plan = conv_tc_plan_create(L->d, L->w, L->io, c->split, c->num_sms);
+      if (!L->plan) {
+        set_error(std::string("plan for ") + L->name + ": " + last_error());
+        return -1;
+      }
+    }
+  }
+  return 0;
+}
+
+int run_step(b2_ctx* c, const b2_ctx::Step& s) {
+  const b2_config& cfg = c->cfg;
+  cudaStream_t st = c->stream;
+  switch (s.kind) {
+    case 0:
+      if (cfg.conv_impl == 0) return conv_tc_launch(s.layer->plan, st);
+      return conv_simt_launch(s.layer->d, s.layer->w, s.layer->io, c->split, st);
+    case 1:
+      return stem_launch(c->img, cfg.input_dtype == 1, cfg.batch, cfg.height, cfg.width, c->stem_w, c->stem_b,
+                         c->c1.hi, c->c1.lo, c->c1h, c->c1w, st);
+    case 2:
+      return maxpool_launch(c->c1.hi, c->c1.lo, cfg.batch, c->c1h, c->c1w, 64, c->pool.hi, c->pool.lo, c->ch[0],
+                            c->cw[0], st);
+    case 3: {
+      const Planes& p5 = c->pfeat[3];
+      const Planes& p6 = c->pfeat[4];
+      const size_t total = static_cast<size_t>(p6.B) * p6.H * p6.W * (p6.C / 8);
+      subsample2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(p5.hi, p5.lo, p5.B, p5.H, p5.W,
+                                                                                     p5.C, p6.hi, p6.lo, p6.H, p6.W);
+      B2_CUDA(cudaGetLastError());
+      return 0;
+    }
+    case 4:
+      return rpn_proposals_launch(c->rpn, st);
+    case 5:
+      return roialign_launch(c->roi1, st);
+    case 6:
+      return head_post_launch(c->post, st);
+    case 7: {
+      if (roialign_launch(c->roi2, st)) return -1;
+      const int rows = cfg.batch * cfg.result_per_im;
+      pool_feat_kernel<<<(rows * cfg.fpn_num_channel + 255) / 256, 256, 0, st>>>(c->box_feat, rows,
+                                                                                 cfg.fpn_num_channel,
+                                                                                 c->box_feat_pooled);
+      B2_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
+  return -1;
+}
+
+int step_launches(const b2_ctx::Step& s) {
+  switch (s.kind) {
+    case 4: return 2;
+    case 6: return 3;
+    case 7: return 2;
+    default: return 1;
+  }
+}
+
+int enqueue(b2_ctx* c, int mask, bool with_events) {
+  if (with_events) B2_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  int last = -1;
+  for (const auto& s : c->steps) {
+    if (!(mask & (1 << s.phase))) continue;
+    if (with_events && last >= 0 && s.phase != last) B2_CUDA(cudaEventRecord(c->ev[last + 1], c->stream));
+    if (run_step(c, s)) return -1;
+    last = s.phase;
+  }
+  if (with_events && last >= 0) B2_CUDA(cudaEventRecord(c->ev[last + 1], c->stream));
+  return 0;
+}
+
+// ---- weight loading -------------------------------------------------------------------------
+struct WeightSet {
+  std::map<std::string, std::pair<const float*, int64_t>> m;
+  const float* get(const std::string& n, int64_t expect) const {
+    auto it = m.find(n);
+    if (it == m.end()) { set_error("missing weight: " + n); return nullptr; }
+    if (it->second.second != expect) {
+      set_error("weight " + n + ": expected " + std::to_string(expect) + " values, got " +
+                std::to_string(it->second.second));
+      return nullptr;
+    }
+    return it->second.first;
+  }
+  bool has(const std::string& n) const { return m.count(n) != 0; }
+};
+
+// BatchNorm inference folded into a per-output-channel scale/shift (nn.py:1771-1774, eps 1e-5)
+int bn_fold(const WeightSet& ws, const std::string& scope, int C, std::vector<double>& scale,
+            std::vector<double>& shift) {
+  const float* g = ws.get(scope + "/bn/gamma", C);
+  const float* b = ws.get(scope + "/bn/beta", C);
+  const float* m = ws.get(scope + "/bn/mean/EMA", C);
+  const float* v = ws.get(scope + "/bn/variance/EMA", C);
+  if (!g || !b || !m || !v) return -1;
+  scale.resize(C);
+  shift.resize(C);
+  for (int i = 0; i < C; ++i) {
+    const double inv = static_cast<double>(g[i]) / sqrt(static_cast<double>(v[i]) + 1e-5);
+    scale[i] = inv;
+    shift[i] = static_cast<double>(b[i]) - static_cast<double>(m[i]) * inv;
+  }
+  return 0;
+}
+
+int upload_layer(b2_ctx* c, Layer* L, const std::vector<float>& packed, const std::vector<float>& bias) {
+  const size_t n = packed.size();
+  float* tmp = nullptr;
+  B2_CUDA(cudaMalloc(&tmp, n * sizeof(float)));
+  B2_CUDA(cudaMemcpyAsync(tmp, packed.data(), n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  if (f32_to_planes(tmp, L->w.w_hi, L->w.w_lo, n, c->stream)) return -1;
+  B2_CUDA(cudaMemcpyAsync(L->w.bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  B2_CUDA(cudaFree(tmp));
+  return 0;
+}
+
+int load_layer(b2_ctx* c, Layer* L, const WeightSet& ws) {
+  const int Cin = L->d.Cin, R = L->d.R, S = L->d.S, Cout = L->d.Cout, K = L->w.K, Cp = L->w.Cout_pad;
+  std::vector<float> packed(static_cast<size_t>(Cp) * K, 0.f), bias(Cp, 0.f);
+  std::vector<double> scale(Cout, 1.0), shift(Cout, 0.0);
+  if (L->kind == 0) {
+    const float* w = ws.get(L->name + "/W", static_cast<int64_t>(R) * S * Cin * Cout);   // HWIO
+    if (!w) return -1;
+    if (L->has_bn && bn_fold(ws, L->name, Cout, scale, shift)) return -1;
+    if (L->has_bias) {
+      const float* b = ws.get(L->name + "/b", Cout);
+      if (!b) return -1;
+      for (int o = 0; o < Cout; ++o) shift[o] = b[o];
+    }
+    for (int t = 0; t < R * S; ++t)
+      for (int ci = 0; ci < Cin; ++ci) {
+        const float* src = w + (static_cast<size_t>(t) * Cin + ci) * Cout;
+        for (int o = 0; o < Cout; ++o)
+          packed[static_cast<size_t>(o) * K + static_cast<size_t>(t) * Cin + ci] = static_cast<float>(src[o] * scale[o]);
+      }
+  } else if (L->kind == 1) {
+    // fc6: reference flattens NCHW (index c*49 + y*7 + x, models.py:1056 + nn.py:738-740);
+    // our ROI features are [y][x][c], so permute the rows of W [in, out].
+    const int C = c->cfg.fpn_num_channel;
+    const float* w = ws.get(L->name + "/W", static_cast<int64_t>(Cin) * Cout);
+    const float* b = ws.get(L->name + "/b", Cout);
+    if (!w || !b) return -1;
+    for (int ch = 0; ch < C; ++ch)
+      for (int s = 0; s < 49; ++s) {
+        const float* src = w + (static_cast<size_t>(ch) * 49 + s) * Cout;
+        const size_t k = static_cast<size_t>(s) * C + ch;
+        for (int o = 0; o < Cout; ++o) packed[static_cast<size_t>(o) * K + k] = src[o];
+      }
+    for (int o = 0; o < Cout; ++o) shift[o] = b[o];
+  } else if (L->kind == 2) {
+    const float* w = ws.get(L->name + "/W", static_cast<int64_t>(Cin) * Cout);
+    const float* b = ws.get(L->name + "/b", Cout);
+    if (!w || !b) return -1;
+    for (int k = 0; k < Cin; ++k)
+      for (int o = 0; o < Cout; ++o) packed[static_cast<size_t>(o) * K + k] = w[static_cast<size_t>(k) * Cout + o];
+    for (int o = 0; o < Cout; ++o) shift[o] = b[o];
+  } else if (L->kind == 3 || L->kind == 4) {
+    // two reference layers fused along N: rpn/{class,box} or fastrcnn/outputs/{class,box}
+    const std::string base = L->kind == 3 ? "rpn" : "fastrcnn/outputs";
+    const int n0 = L->kind == 3 ? 3 : c->cfg.num_class;
+    const int n1 = Cout - n0;
+    const float* w0 = ws.get(base + "/class/W", static_cast<int64_t>(Cin) * n0);
+    const float* b0 = ws.get(base + "/class/b", n0);
+    const float* w1 = ws.get(base + "/box/W", static_cast<int64_t>(Cin) * n1);
+    const float* b1 = ws.get(base + "/box/b", n1);
+    if (!w0 || !b0 || !w1 || !b1) return -1;
+    for (int k = 0; k < Cin; ++k) {
+      for (int o = 0; o < n0; ++o) packed[static_cast<size_t>(o) * K + k] = w0[static_cast<size_t>(k) * n0 + o];
+      for (int o = 0; o < n1; ++o) packed[static_cast<size_t>(n0 + o) * K + k] = w1[static_cast<size_t>(k) * n1 + o];
+    }
+    for (int o = 0; o < n0; ++o) shift[o] = b0[o];
+    for (int o = 0; o < n1; ++o) shift[n0 + o] = b1[o];
+  }
+  for (int o = 0; o < Cout; ++o) bias[o] = static_cast<float>(shift[o]);
+  return upload_layer(c, L, packed, bias);
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* b2_last_error(void) { return b2::last_error(); }
+int b2_version(void) { return 1; }
+
+int b2_create(b2_ctx** out, int device, const b2_config* cfg) {
+  B2_CHECK(out && cfg, "b2_create: null argument");
+  *out = nullptr;
+  B2_CUDA(cudaSetDevice(device));
+  std::unique_ptr<b2_ctx> c(new b2_ctx());
+  c->cfg = *cfg;
+  c->device = device;
+  c->split = cfg->precision == 1;
+  cudaDeviceProp prop;
+  B2_CUDA(cudaGetDeviceProperties(&prop, device));
+  B2_CHECK(prop.major == 10, "b2_create: this library is built for sm_100a (B200) only");
+  c->num_sms = prop.multiProcessorCount;
+  B2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int i = 0; i <= NPHASE; ++i) B2_CUDA(cudaEventCreate(&c->ev[i]));
+  memset(c->phase_ms, 0, sizeof(c->phase_ms));
+  if (build_plan(c.get())) {
+    b2_destroy(c.release());
+    return -1;
+  }
+  c->launches = 0;
+  for (const auto& s : c->steps) c->launches += step_launches(s);
+  B2_CUDA(cudaDeviceSynchronize());
+  *out = c.release();
+  return 0;
+}
+
+void b2_destroy(b2_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  if (c->graph) cudaGraphExecDestroy(c->graph);
+  for (auto& L : c->layers)
+    if (L->plan) conv_tc_plan_destroy(L->plan);
+  for (void* p : c->allocs) cudaFree(p);
+  for (int i = 0; i <= NPHASE; ++i)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int b2_load_weights(b2_ctx* c, const char* const* names, const float* const* data, const int64_t* numel, int n) {
+  B2_CHECK(c && names && data && numel, "b2_load_weights: null argument");
+  B2_CUDA(cudaSetDevice(c->device));
+  WeightSet ws;
+  for (int i = 0; i < n; ++i) ws.m[names[i]] = std::make_pair(data[i], numel[i]);
+  // stem: HWIO [7,7,3,64] == [147][64]; BN folded
+  {
+    const float* w = ws.get("conv0/W", 147 * 64);
+    std::vector<double> scale, shift;
+    if (!w || bn_fold(ws, "conv0", 64, scale, shift)) return -1;
+    std::vector<float> pw(147 * 64), pb(64);
+    for (int k = 0; k < 147; ++k)
+      for (int o = 0; o < 64; ++o) pw[k * 64 + o] = static_cast<float>(w[k * 64 + o] * scale[o]);
+    for (int o = 0; o < 64; ++o) pb[o] = static_cast<float>(shift[o]);
+    B2_CUDA(cudaMemcpy(c->stem_w, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMemcpy(c->stem_b, pb.data(), pb.size() * 4, cudaMemcpyHostToDevice));
+  }
+  // shared RPN weights: packed once, every level's layer gets its own copy of the (small) operand
+  for (auto& L : c->layers)
+    if (load_layer(c, L.get(), ws)) return -1;
+  c->weights_loaded = true;
+  return 0;
+}
+
+int b2_run_phases(b2_ctx* c, int mask) {
+  B2_CHECK(c, "b2_run_phases: null ctx");
+  B2_CUDA(cudaSetDevice(c->device));
+  B2_CHECK(c->weights_loaded, "b2_run_phases: weights not loaded");
+  if (enqueue(c, mask, true)) return -1;
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  int last = -1;
+  for (int ph = 0; ph < NPHASE; ++ph) {
+    c->phase_ms[ph] = 0.f;
+    if (!(mask & (1 << ph))) continue;
+    bool any = false;
+    for (const auto& s : c->steps) any = any || s.phase == ph;
+    if (!any) continue;
+    cudaEventElapsedTime(&c->phase_ms[ph], c->ev[last < 0 ? 0 : last + 1], c->ev[ph + 1]);
+    last = ph;
+  }
+  return 0;
+}
+
+int b2_phase_times(b2_ctx* c, float ms[8]) {
+  B2_CHECK(c && ms, "b2_phase_times: null argument");
+  for (int i = 0; i < NPHASE; ++i) ms[i] = c->phase_ms[i];
+  return 0;
+}
+
+int b2_kernel_launches(b2_ctx* c) { return c ? c->launches : -1; }
+
+static int ensure_graph(b2_ctx* c) {
+  if (c->graph || !c->cfg.use_cuda_graph) return 0;
+  cudaGraph_t g = nullptr;
+  // one eager pass first: lazy one-time attribute setup must not happen inside the capture
+  if (enqueue(c, B2_PHASE_ALL, false)) return -1;
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  B2_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = enqueue(c, B2_PHASE_ALL, false);
+  cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+  if (rc) return -1;
+  B2_CUDA(e);
+  B2_CUDA(cudaGraphInstantiate(&c->graph, g, 0));
+  B2_CUDA(cudaGraphDestroy(g));
+  return 0;
+}
+
+static int run_all(b2_ctx* c) {
+  if (c->cfg.use_cuda_graph) {
+    if (ensure_graph(c)) return -1;
+    B2_CUDA(cudaGraphLaunch(c->graph, c->stream));
+    return 0;
+  }
+  return enqueue(c, B2_PHASE_ALL, false);
+}
+
+static int copy_outputs(b2_ctx* c, float* boxes, float* probs, int32_t* labels, int32_t* valid, float* box_feat,
+                        int feat_mode, cudaMemcpyKind kind) {
+  const int B = c->cfg.batch, R = c->cfg.result_per_im, C = c->cfg.fpn_num_channel;
+  cudaStream_t st = c->stream;
+  if (boxes) B2_CUDA(cudaMemcpyAsync(boxes, c->post.final_boxes, sizeof(float) * B * R * 4, kind, st));
+  if (probs) B2_CUDA(cudaMemcpyAsync(probs, c->post.final_probs, sizeof(float) * B * R, kind, st));
+  if (labels) B2_CUDA(cudaMemcpyAsync(labels, c->post.final_labels, sizeof(int32_t) * B * R, kind, st));
+  if (valid) B2_CUDA(cudaMemcpyAsync(valid, c->post.final_count, sizeof(int32_t) * B, kind, st));
+  if (box_feat) {
+    if (feat_mode == 1)
+      B2_CUDA(cudaMemcpyAsync(box_feat, c->box_feat_pooled, sizeof(float) * B * R * C, kind, st));
+    else
+      B2_CUDA(cudaMemcpyAsync(box_feat, c->box_feat, sizeof(float) * B * R * C * 49, kind, st));
+  }
+  return 0;
+}
+
+int b2_detect(b2_ctx* c, const void* frames_dev, float* boxes, float* probs, int32_t* labels, int32_t* valid,
+              float* box_feat, int feat_mode, int sync) {
+  B2_CHECK(c, "b2_detect: null ctx");
+  B2_CUDA(cudaSetDevice(c->device));
+  B2_CHECK(c->weights_loaded, "b2_detect: weights not loaded");
+  if (frames_dev && frames_dev != c->img)
+    B2_CUDA(cudaMemcpyAsync(c->img, frames_dev, c->img_bytes, cudaMemcpyDeviceToDevice, c->stream));
+  if (run_all(c)) return -1;
+  if (copy_outputs(c, boxes, probs, labels, valid, box_feat, feat_mode, cudaMemcpyDeviceToDevice)) return -1;
+  if (sync) B2_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int b2_detect_host(b2_ctx* c, const void* frames_host, float* boxes, float* probs, int32_t* labels, int32_t* valid,
+                   float* box_feat, int feat_mode) {
+  B2_CHECK(c && frames_host, "b2_detect_host: null argument");
+  B2_CUDA(cudaSetDevice(c->device));
+  B2_CHECK(c->weights_loaded, "b2_detect_host: weights not loaded");
+  B2_CUDA(cudaMemcpyAsync(c->img, frames_host, c->img_bytes, cudaMemcpyHostToDevice, c->stream));
+  if (run_all(c)) return -1;
+  if (copy_outputs(c, boxes, probs, labels, valid, box_feat, feat_mode, cudaMemcpyDeviceToHost)) return -1;
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int b2_stage_shape(b2_ctx* c, const char* name, int64_t shape[4], int32_t* dtype) {
+  B2_CHECK(c && name && shape, "b2_stage_shape: null argument");
+  auto it = c->stages.find(name);
+  B2_CHECK(it != c->stages.end(), std::string("unknown stage: ") + name);
+  for (int i = 0; i < 4; ++i) shape[i] = it->second.shape[i];
+  if (dtype) *dtype = it->second.kind == 2 ? 1 : 0;
+  return 0;
+}
+
+int b2_get_stage(b2_ctx* c, const char* name, void* dst, int64_t capacity) {
+  B2_CHECK(c && name && dst, "b2_get_stage: null argument");
+  B2_CUDA(cudaSetDevice(c->device));
+  auto it = c->stages.find(name);
+  B2_CHECK(it != c->stages.end(), std::string("unknown stage: ") + name);
+  const StageRef& s = it->second;
+  const int64_t n = s.shape[0] * s.shape[1] * s.shape[2] * s.shape[3];
+  B2_CHECK(capacity >= n * 4, "b2_get_stage: buffer too small");
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  if (s.kind == 0) {
+    float* tmp = nullptr;
+    B2_CUDA(cudaMalloc(&tmp, n * 4));
+    if (planes_to_f32(s.pl.hi, s.pl.lo, tmp, n, c->stream)) return -1;
+    B2_CUDA(cudaMemcpyAsync(dst, tmp, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    B2_CUDA(cudaFree(tmp));
+  } else {
+    B2_CUDA(cudaMemcpy(dst, s.ptr, n * 4, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+int b2_set_stage(b2_ctx* c, const char* name, const void* src, int64_t bytes) {
+  B2_CHECK(c && name && src, "b2_set_stage: null argument");
+  B2_CUDA(cudaSetDevice(c->device));
+  if (strcmp(name, "image") == 0) {
+    B2_CHECK(bytes == static_cast<int64_t>(c->img_bytes), "b2_set_stage(image): size mismatch");
+    B2_CUDA(cudaMemcpy(c->img, src, bytes, cudaMemcpyHostToDevice));
+    return 0;
+  }
+  auto it = c->stages.find(name);
+  B2_CHECK(it != c->stages.end(), std::string("unknown stage: ") + name);
+  const StageRef& s = it->second;
+  const int64_t n = s.shape[0] * s.shape[1] * s.shape[2] * s.shape[3];
+  B2_CHECK(bytes == n * 4, "b2_set_stage: size mismatch");
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  if (s.kind == 0) {
+    float* tmp = nullptr;
+    B2_CUDA(cudaMalloc(&tmp, n * 4));
+    B2_CUDA(cudaMemcpy(tmp, src, n * 4, cudaMemcpyHostToDevice));
+    if (f32_to_planes(tmp, s.pl.hi, s.pl.lo, n, c->stream)) return -1;
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    B2_CUDA(cudaFree(tmp));
+  } else {
+    B2_CUDA(cudaMemcpy(s.ptr, src, n * 4, cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+// ---- DeepSORT appearance cost ---------------------------------------------------------------
+int b2_cosine_cost(int device, const float* gallery, const int32_t* seg_offsets, int T, const float* dets, int N,
+                   int D, int precision, float* cost) {
+  B2_CHECK(gallery && seg_offsets && dets && cost, "b2_cosine_cost: null argument");
+  if (T <= 0 || N <= 0) return 0;
+  B2_CUDA(cudaSetDevice(device));
+  const int S = seg_offsets[T];
+  B2_CHECK(S > 0 && D > 0, "b2_cosine_cost: empty gallery");
+  const bool split = precision == 1;
+  const int Dp = (D + 63) / 64 * 64, Np = (N + 15) / 16 * 16, Sp = (S + 127) / 128 * 128;
+  cudaStream_t st = nullptr;
+  float *d_g = nullptr, *d_d = nullptr, *d_dots = nullptr, *d_cost = nullptr, *d_bias = nullptr;
+  int* d_off = nullptr;
+  __half *g_hi = nullptr, *g_lo = nullptr, *q_hi = nullptr, *q_lo = nullptr;
+  B2_CUDA(cudaMalloc(&d_g, sizeof(float) * S * D));
+  B2_CUDA(cudaMalloc(&d_d, sizeof(float) * N * D));
+  B2_CUDA(cudaMalloc(&d_dots, sizeof(float) * Sp * Np));
+  B2_CUDA(cudaMalloc(&d_cost, sizeof(float) * T * N));
+  B2_CUDA(cudaMalloc(&d_bias, sizeof(float) * Np));
+  B2_CUDA(cudaMalloc(&d_off, sizeof(int) * (T + 1)));
+  B2_CUDA(cudaMalloc(&g_hi, sizeof(__half) * Sp * Dp));
+  B2_CUDA(cudaMalloc(&g_lo, sizeof(__half) * Sp * Dp));
+  B2_CUDA(cudaMalloc(&q_hi, sizeof(__half) * Np * Dp));
+  B2_CUDA(cudaMalloc(&q_lo, sizeof(__half) * Np * Dp));
+  B2_CUDA(cudaMemset(g_hi, 0, sizeof(__half) * Sp * Dp));
+  B2_CUDA(cudaMemset(g_lo, 0, sizeof(__half) * Sp * Dp));
+  B2_CUDA(cudaMemset(q_hi, 0, sizeof(__half) * Np * Dp));
+  B2_CUDA(cudaMemset(q_lo, 0, sizeof(__half) * Np * Dp));
+  B2_CUDA(cudaMemset(d_bias, 0, sizeof(float) * Np));
+  B2_CUDA(cudaMemcpy(d_g, gallery, sizeof(float) * S * D, cudaMemcpyHostToDevice));
+  B2_CUDA(cudaMemcpy(d_d, dets, sizeof(float) * N * D, cudaMemcpyHostToDevice));
+  B2_CUDA(cudaMemcpy(d_off, seg_offsets, sizeof(int) * (T + 1), cudaMemcpyHostToDevice));
+  if (cosine_normalize_rows(d_g, S, D, g_hi, g_lo, Dp, st)) return -1;
+  if (cosine_normalize_rows(d_d, N, D, q_hi, q_lo, Dp, st)) return -1;
+  ConvDesc d;
+  d.B = 1; d.in_H = 1; d.in_W = S; d.Cin = Dp; d.in_pitch_H = 1; d.in_pitch_W = S; d.in_ld = Dp;
+  d.Cout = N; d.out_H = 1; d.out_W = S; d.ldc = Np;
+  ConvWeights w;
+  w.w_hi = q_hi; w.w_lo = split ? q_lo : nullptr; w.bias = d_bias; w.Cout_pad = Np; w.K = Dp;
+  ConvIO io;
+  io.in_hi = g_hi; io.in_lo = split ? g_lo : nullptr; io.out_f32 = d_dots;
+  cudaDeviceProp prop;
+  B2_CUDA(cudaGetDeviceProperties(&prop, device));
+  ConvPlan* plan = conv_tc_plan_create(d, w, io, split, prop.multiProcessorCount);
+  B2_CHECK(plan != nullptr, std::string("b2_cosine_cost: ") + last_error());
+  int rc = conv_tc_launch(plan, st);
+  if (!rc) rc = cosine_segmin(d_dots, Np, d_off, T, N, d_cost, st);
+  cudaError_t e = cudaMemcpy(cost, d_cost, sizeof(float) * T * N, cudaMemcpyDeviceToHost);
+  conv_tc_plan_destroy(plan);
+  cudaFree(d_g); cudaFree(d_d); cudaFree(d_dots); cudaFree(d_cost); cudaFree(d_bias); cudaFree(d_off);
+  cudaFree(g_hi); cudaFree(g_lo); cudaFree(q_hi); cudaFree(q_lo);
+  if (rc) return -1;
+  B2_CUDA(e);
+  return 0;
+}
+
+// ---- single conv op for kernel parity tests ---------------------------------------------------
+int b2_op_conv2d(int device, const float* x, const float* w, const float* bias, const float* res, int B, int H, int W,
+                 int Cin, int R, int S, int Cout, int stride, int dil, int pad_t, int pad_b, int pad_l, int pad_r,
+                 int relu, int res_shift, int impl, int split, int a_mode, float* out) {
+  B2_CHECK(x && w && out, "b2_op_conv2d: null argument");
+  B2_CUDA(cudaSetDevice(device));
+  ConvDesc d;
+  d.B = B; d.in_H = H; d.in_W = W; d.Cin = Cin; d.in_pitch_H = H; d.in_pitch_W = W; d.in_ld = Cin;
+  d.R = R; d.S = S; d.stride = stride; d.dil = dil;
+  d.pad_t = pad_t; d.pad_b = pad_b; d.pad_l = pad_l; d.pad_r = pad_r;
+  d.Cout = Cout; d.relu = relu; d.force_a_mode = a_mode;
+  const int Ho = d.Ho(), Wo = d.Wo();
+  B2_CHECK(Ho > 0 && Wo > 0, "b2_op_conv2d: empty output");
+  const int Cp = (Cout + 15) / 16 * 16;
+  d.out_H = Ho; d.out_W = Wo; d.ldc = Cp;
+  const int rH = res_shift ? (Ho + 1) / 2 : Ho, rW = res_shift ? (Wo + 1) / 2 : Wo;
+  d.res_H = rH; d.res_W = rW; d.ldr = Cp; d.res_shift = res_shift;
+  const size_t nx = static_cast<size_t>(B) * H * W * Cin, K = static_cast<size_t>(R) * S * Cin;
+  const size_t nw = static_cast<size_t>(Cp) * K, no = static_cast<size_t>(B) * Ho * Wo * Cp;
+  const size_t nr = static_cast<size_t>(B) * rH * rW * Cp;
+  // pack HWIO -> [Cout_pad][R*S*Cin]
+  std::vector<float> pw(nw, 0.f), pb(Cp, 0.f);
+  for (size_t k = 0; k < K; ++k)
+    for (int o = 0; o < Cout; ++o) pw[static_cast<size_t>(o) * K + k] = w[k * Cout + o];
+  if (bias) for (int o = 0; o < Cout; ++o) pb[o] = bias[o];
+  std::vector<float> pr;
+  if (res) {
+    pr.assign(nr, 0.f);
+    for (size_t p = 0; p < static_cast<size_t>(B) * rH * rW; ++p)
+      for (int o = 0; o < Cout; ++o) pr[p * Cp + o] = res[p * Cout + o];
+  }
+  float *dx = nullptr, *dw = nullptr, *dr = nullptr, *dof = nullptr;
+  ConvWeights cw; ConvIO io;
+  __half *xh, *xl, *oh, *ol, *rh = nullptr, *rl = nullptr;
+  B2_CUDA(cudaMalloc(&dx, nx * 4));
+  B2_CUDA(cudaMalloc(&dw, nw * 4));
+  B2_CUDA(cudaMalloc(&dof, no * 4));
+  B2_CUDA(cudaMalloc(&xh, nx * 2 + 256)); B2_CUDA(cudaMalloc(&xl, nx * 2 + 256));
+  B2_CUDA(cudaMalloc(&cw.w_hi, nw * 2 + 256)); B2_CUDA(cudaMalloc(&cw.w_lo, nw * 2 + 256));
+  B2_CUDA(cudaMalloc(&oh, no * 2 + 256)); B2_CUDA(cudaMalloc(&ol, no * 2 + 256));
+  B2_CUDA(cudaMalloc(&cw.bias, Cp * 4));
+  B2_CUDA(cudaMemset(oh, 0, no * 2)); B2_CUDA(cudaMemset(ol, 0, no * 2));
+  B2_CUDA(cudaMemcpy(dx, x, nx * 4, cudaMemcpyHostToDevice));
+  B2_CUDA(cudaMemcpy(dw, pw.data(), nw * 4, cudaMemcpyHostToDevice));
+  B2_CUDA(cudaMemcpy(cw.bias, pb.data(), Cp * 4, cudaMemcpyHostToDevice));
+  cudaStream_t st = nullptr;
+  if (f32_to_planes(dx, xh, xl, nx, st) || f32_to_planes(dw, cw.w_hi, cw.w_lo, nw, st)) return -1;
+  if (res) {
+    B2_CUDA(cudaMalloc(&dr, nr * 4));
+    B2_CUDA(cudaMalloc(&rh, nr * 2 + 256)); B2_CUDA(cudaMalloc(&rl, nr * 2 + 256));
+    B2_CUDA(cudaMemcpy(dr, pr.data(), nr * 4, cudaMemcpyHostToDevice));
+    if (f32_to_planes(dr, rh, rl, nr, st)) return -1;
+  }
+  cw.Cout_pad = Cp; cw.K = static_cast<int>(K);
+  if (!split) { /* keep lo planes allocated but unused */ }
+  io.in_hi = xh; io.in_lo = split ? xl : nullptr;
+  io.out_hi = oh; io.out_lo = split ? ol : nullptr;
+  io.res_hi = rh; io.res_lo = split ? rl : nullptr;
+  ConvWeights cw_use = cw;
+  if (!split) cw_use.w_lo = nullptr;
+  int rc = 0;
+  if (impl == 0) {
+    cudaDeviceProp prop;
+    B2_CUDA(cudaGetDeviceProperties(&prop, device));
+    ConvPlan* plan = conv_tc_plan_create(d, cw_use, io, split != 0, prop.multiProcessorCount);
+    B2_CHECK(plan != nullptr, std::string("b2_op_conv2d: ") + last_error());
+    rc = conv_tc_launch(plan, st);
+    cudaError_t e = cudaDeviceSynchronize();
+    conv_tc_plan_destroy(plan);
+    if (!rc) B2_CUDA(e);
+  } else {
+    rc = conv_simt_launch(d, cw_use, io, split != 0, st);
+    if (!rc) B2_CUDA(cudaDeviceSynchronize());
+  }
+  if (rc) return -1;
+  if (planes_to_f32(oh, split ? ol : nullptr, dof, no, st)) return -1;
+  std::vector<float> ho(no);
+  B2_CUDA(cudaMemcpy(ho.data(), dof, no * 4, cudaMemcpyDeviceToHost));
+  for (size_t p = 0; p < static_cast<size_t>(B) * Ho * Wo; ++p)
+    for (int o = 0; o < Cout; ++o) out[p * Cout + o] = ho[p * Cp + o];
+  cudaFree(dx); cudaFree(dw); cudaFree(dof); cudaFree(xh); cudaFree(xl); cudaFree(cw.w_hi); cudaFree(cw.w_lo);
+  cudaFree(oh); cudaFree(ol); cudaFree(cw.bias);
+  if (res) { cudaFree(dr); cudaFree(rh); cudaFree(rl); }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,75 @@
+// Parameter blocks and launchers of the non-GEMM kernels (proposals, ROIAlign, detection post-process,
+// appearance cost).  All launches are asynchronous on the given stream; nothing syncs with the host.
+#pragma once
+#include "common.h"
+
+namespace b2 {
+
+// stem.cu
+int f32_to_planes(const float* src, __half* hi, __half* lo, size_t n, cudaStream_t s);
+int planes_to_f32(const __half* hi, const __half* lo, float* dst, size_t n, cudaStream_t s);
+int stem_launch(const void* img, int is_u8, int B, int H, int W, const float* wgt, const float* bias, __half* out_hi,
+                __half* out_lo, int Ho, int Wo, cudaStream_t s);
+int maxpool_launch(const __half* in_hi, const __half* in_lo, int B, int H, int W, int C, __half* out_hi,
+                   __half* out_lo, int Ho, int Wo, cudaStream_t s);
+
+// rpn.cu
+struct RpnParams {
+  const float* logits[5];   // per level [B * h*w][16]: cols 0..2 objectness, 3..14 deltas (anchor-major)
+  int h[5], w[5];
+  float stride[5];
+  float cell[5][3][4];      // cell anchors x1,y1,x2,y2 (generate_anchors.py semantics, before the +1)
+  int B, topk;
+  float img_h, img_w, decode_clip, min_size, nms_thr;
+  float* lvl_boxes;         // [B][5][topk][4]
+  float* lvl_scores;        // [B][5][topk]
+  int* lvl_count;           // [B][5]
+  float* prop_boxes;        // [B][topk][4]
+  float* prop_scores;       // [B][topk]
+  int* prop_count;          // [B]
+};
+int rpn_proposals_launch(const RpnParams& p, cudaStream_t s);
+
+// roialign.cu
+struct RoiAlignParams {
+  const __half* feat_hi[4];   // p2..p5, NHWC
+  const __half* feat_lo[4];   // nullptr in fp16 precision
+  int H[4], W[4];             // cropped view the ROIAlign sees (models.py:382-390)
+  int pitch_H[4], pitch_W[4]; // buffer dims
+  float inv_stride[4];
+  int C;                      // 256
+  int B, rois_per_image;      // boxes [B][rois_per_image][4], count[B]
+  const float* boxes;
+  const int* count;
+  __half* out_hi;             // [B*rois][7][7][C]   (fc6 operand order), or
+  __half* out_lo;
+  float* out_nchw;            // [B*rois][C][7][7]   fp32 (fpn_box_feat contract)
+};
+int roialign_launch(const RoiAlignParams& p, cudaStream_t s);
+
+// head.cu
+struct HeadPostParams {
+  const float* logits;        // [B*rois][ld]: cols 0..nc-1 class logits, nc + c*4 .. box logits of class c
+  int ld, num_class, B, rois_per_image;
+  int class_agnostic;         // box logits shared by all classes (use_frcnn_class_agnostic)
+  const float* rois;          // [B][rois][4]
+  const int* roi_count;       // [B]
+  float reg_w[4];
+  float decode_clip, img_h, img_w, score_thresh, nms_thr;
+  int max_per_class, max_total;
+  float* probs;               // [B][rois][num_class]
+  float* dec_boxes;           // [B][rois][num_class-1][4]
+  int* cls_keep;              // [B][num_class-1][max_per_class] roi indices
+  int* cls_count;             // [B][num_class-1]
+  float* final_boxes;         // [B][max_total][4]
+  float* final_probs;         // [B][max_total]
+  int* final_labels;          // [B][max_total]
+  int* final_count;           // [B]
+};
+int head_post_launch(const HeadPostParams& p, cudaStream_t s);
+
+// cosine.cu
+int cosine_normalize_rows(const float* src, int rows, int D, __half* hi, __half* lo, int ld, cudaStream_t s);
+int cosine_segmin(const float* dots, int ld, const int* seg_offsets, int T, int N, float* cost, cudaStream_t s);
+
+}  // namespace b2

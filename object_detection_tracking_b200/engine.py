@@ -1,0 +1,158 @@
+"""Python owner of a b2_ctx: the thin host layer above the C ABI (ctypes only; torch/numpy arrays are
+just buffers).  One Detector = one device = one fixed (batch, H, W) launch plan."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p
+
+import numpy as np
+
+from . import _lib
+from .config import normalize_config
+
+
+class Detector:
+    def __init__(self, cfg, batch: int, height: int, width: int, device: int = 0, input_dtype: str = "float32",
+                 precision: str = "split", conv_impl: str = "tcgen05", use_cuda_graph: bool = True):
+        self.lib = _lib.load()
+        self.cfg = normalize_config(cfg)
+        self.batch, self.height, self.width = int(batch), int(height), int(width)
+        self.device = int(device)
+        self.input_dtype = input_dtype
+        self.precision = precision
+        self._c = _lib.make_config(self.cfg, batch, height, width, input_dtype, precision, conv_impl, use_cuda_graph)
+        self._ctx = c_void_p(0)
+        _lib.check(self.lib.b2_create(ctypes.byref(self._ctx), self.device, ctypes.byref(self._c)), "b2_create")
+        self.R = int(self.cfg.result_per_im)
+        self.C = int(self.cfg.fpn_num_channel)
+        self._pinned = None
+
+    # -- lifetime ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self.lib.b2_destroy(self._ctx)
+            self._ctx = c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- weights ----------------------------------------------------------------------------------
+    def load_weights(self, weights: dict):
+        """`weights`: name -> float32 ndarray in the reference's Tensorpack-npz naming."""
+        names = sorted(weights.keys())
+        arrs = [np.ascontiguousarray(weights[k], dtype=np.float32) for k in names]
+        n = len(names)
+        c_names = (c_char_p * n)(*[k.encode() for k in names])
+        c_data = (c_void_p * n)(*[a.ctypes.data for a in arrs])
+        c_numel = (c_int64 * n)(*[a.size for a in arrs])
+        _lib.check(self.lib.b2_load_weights(self._ctx, c_names, c_data, c_numel, n), "b2_load_weights")
+
+    # -- the hot call -----------------------------------------------------------------------------
+    def _np_dtype(self):
+        return np.uint8 if self.input_dtype == "uint8" else np.float32
+
+    def alloc_outputs(self, feat_mode: int = 0, pinned: bool = False):
+        B, R, C = self.batch, self.R, self.C
+        shapes = dict(boxes=((B, R, 4), np.float32), probs=((B, R), np.float32), labels=((B, R), np.int32),
+                      valid=((B,), np.int32),
+                      feat=(((B * R, C) if feat_mode == 1 else (B * R, C, 7, 7)), np.float32))
+        if pinned:
+            import torch
+            tmap = {np.float32: torch.float32, np.int32: torch.int32}
+            return {k: torch.empty(s, dtype=tmap[d]).pin_memory() for k, (s, d) in shapes.items()}
+        return {k: np.empty(s, dtype=d) for k, (s, d) in shapes.items()}
+
+    def detect_host(self, frames, out: dict | None = None, feat_mode: int = 0, want_feat: bool = True):
+        """frames: [B,H,W,3] host array (numpy or pinned torch) of the configured dtype.  Returns dict of
+        host arrays (boxes [B,100,4], probs, labels, valid, feat)."""
+        if isinstance(frames, np.ndarray):
+            frames = np.ascontiguousarray(frames, dtype=self._np_dtype())
+            assert frames.shape == (self.batch, self.height, self.width, 3), frames.shape
+        if out is None:
+            out = self.alloc_outputs(feat_mode)
+        _lib.check(self.lib.b2_detect_host(self._ctx, _lib.ptr(frames), _lib.ptr(out["boxes"]), _lib.ptr(out["probs"]),
+                                           _lib.ptr(out["labels"]), _lib.ptr(out["valid"]),
+                                           _lib.ptr(out["feat"]) if want_feat else c_void_p(0), feat_mode),
+                   "b2_detect_host")
+        return out
+
+    def detect_device(self, frames_dev, out_dev: dict | None = None, feat_mode: int = 0, sync: bool = True):
+        """frames_dev / out_dev: torch CUDA tensors (or None to leave results in the context)."""
+        o = out_dev or {}
+        _lib.check(self.lib.b2_detect(self._ctx, _lib.ptr(frames_dev), _lib.ptr(o.get("boxes")),
+                                      _lib.ptr(o.get("probs")), _lib.ptr(o.get("labels")), _lib.ptr(o.get("valid")),
+                                      _lib.ptr(o.get("feat")), feat_mode, int(sync)), "b2_detect")
+        return out_dev
+
+    # -- stage access (parity tests) ----------------------------------------------------------------
+    def stage_shape(self, name: str):
+        shape = (c_int64 * 4)()
+        dt = c_int32(0)
+        _lib.check(self.lib.b2_stage_shape(self._ctx, name.encode(), shape, ctypes.byref(dt)), "b2_stage_shape")
+        return tuple(int(v) for v in shape), (np.int32 if dt.value == 1 else np.float32)
+
+    def get_stage(self, name: str) -> np.ndarray:
+        shape, dt = self.stage_shape(name)
+        a = np.empty(shape, dtype=dt)
+        _lib.check(self.lib.b2_get_stage(self._ctx, name.encode(), _lib.ptr(a), a.nbytes), "b2_get_stage")
+        return a
+
+    def set_stage(self, name: str, value: np.ndarray):
+        if name == "image":
+            a = np.ascontiguousarray(value, dtype=self._np_dtype())
+        else:
+            _, dt = self.stage_shape(name)
+            a = np.ascontiguousarray(value, dtype=dt)
+        _lib.check(self.lib.b2_set_stage(self._ctx, name.encode(), _lib.ptr(a), a.nbytes), "b2_set_stage")
+
+    def run_phases(self, mask: int = 255):
+        _lib.check(self.lib.b2_run_phases(self._ctx, int(mask)), "b2_run_phases")
+
+    def phase_times(self) -> dict:
+        ms = (c_float * 8)()
+        _lib.check(self.lib.b2_phase_times(self._ctx, ms), "b2_phase_times")
+        return {n: float(ms[i]) for i, n in enumerate(_lib.PHASE_NAMES)}
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.b2_kernel_launches(self._ctx))
+
+
+def cosine_cost(gallery: np.ndarray, seg_offsets: np.ndarray, dets: np.ndarray, device: int = 0,
+                precision: str = "split") -> np.ndarray:
+    """[T, N] appearance cost = per-track min over gallery rows of (1 - cosine) on the GPU."""
+    lib = _lib.load()
+    gallery = np.ascontiguousarray(gallery, dtype=np.float32)
+    dets = np.ascontiguousarray(dets, dtype=np.float32)
+    seg = np.ascontiguousarray(seg_offsets, dtype=np.int32)
+    T = seg.shape[0] - 1
+    N, D = dets.shape
+    cost = np.zeros((T, N), dtype=np.float32)
+    if T == 0 or N == 0:
+        return cost
+    _lib.check(lib.b2_cosine_cost(device, _lib.ptr(gallery), _lib.ptr(seg), T, _lib.ptr(dets), N, D,
+                                  {"fp16": 0, "split": 1}[precision], _lib.ptr(cost)), "b2_cosine_cost")
+    return cost
+
+
+def op_conv2d(x, w, bias=None, res=None, stride=1, dil=1, pad=(0, 0, 0, 0), relu=False, res_shift=0,
+              impl="tcgen05", split=True, a_mode=-1, device=0) -> np.ndarray:
+    """Single convolution through the C ABI (NHWC activations, HWIO kernel) -- used by the kernel tests."""
+    lib = _lib.load()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    B, H, W, Cin = x.shape
+    R, S, _, Cout = w.shape
+    pt, pb, pl, pr = pad
+    Ho = (H + pt + pb - ((R - 1) * dil + 1)) // stride + 1
+    Wo = (W + pl + pr - ((S - 1) * dil + 1)) // stride + 1
+    out = np.zeros((B, Ho, Wo, Cout), dtype=np.float32)
+    b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+    r = None if res is None else np.ascontiguousarray(res, dtype=np.float32)
+    _lib.check(lib.b2_op_conv2d(device, _lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(r), B, H, W, Cin, R, S, Cout,
+                                stride, dil, pt, pb, pl, pr, int(relu), int(res_shift),
+                                {"tcgen05": 0, "simt": 1}[impl], int(split), int(a_mode), _lib.ptr(out)),
+               "b2_op_conv2d")
+    return out

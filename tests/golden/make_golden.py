@@ -1,0 +1,86 @@
+"""Generates the committed golden fixtures by running the REFERENCE's own importable code
+(/root/reference: generate_anchors.py, deep_sort/*).  Run once in the authoring container:
+    python tests/golden/make_golden.py
+The fixtures travel with the repo; /root/reference does not exist on the GPU box."""
+import os
+import sys
+
+import numpy as np
+import scipy.linalg  # noqa: F401  (import before the np.float shim)
+import scipy.optimize  # noqa: F401
+
+np.float = float   # deep_sort/detection.py:30 uses the removed alias
+np.int = int
+sys.path.insert(0, "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+from generate_anchors import generate_anchors  # noqa: E402
+from deep_sort import nn_matching  # noqa: E402
+from deep_sort.detection import Detection  # noqa: E402
+from deep_sort.tracker import Tracker  # noqa: E402
+
+
+def anchors():
+    out = {}
+    for stride, size in zip((4, 8, 16, 32, 64), (32, 64, 128, 256, 512)):
+        out["s%d" % stride] = generate_anchors(stride, scales=np.array([size], dtype=np.float64) / stride,
+                                               ratios=np.array((0.5, 1, 2), dtype=np.float64))
+    out["default"] = generate_anchors()
+    np.savez(os.path.join(HERE, "anchors.npz"), **out)
+
+
+def cosine():
+    rng = np.random.default_rng(7)
+    T, N, D, budget = 23, 37, 256, 5
+    seg = [0]
+    gal = []
+    for t in range(T):
+        n = int(rng.integers(1, budget + 1))
+        gal.append(np.abs(rng.standard_normal((n, D))).astype(np.float32) + 0.1)
+        seg.append(seg[-1] + n)
+    dets = (np.abs(rng.standard_normal((N, D))) + 0.1).astype(np.float32)
+    m = nn_matching.NearestNeighborDistanceMetric("cosine", 0.5, budget)
+    m.samples = {t: list(gal[t]) for t in range(T)}
+    cost = m.distance(dets, list(range(T)))
+    np.savez(os.path.join(HERE, "deepsort_cosine.npz"), gallery=np.concatenate(gal), seg=np.asarray(seg, np.int32),
+             dets=dets, cost=cost)
+
+
+def tracker_run():
+    """8 frames of synthetic moving objects through the reference Tracker (this fork's defaults,
+    tracker.py:40) -> per-frame (track_id, tlwh) of confirmed tracks."""
+    rng = np.random.default_rng(11)
+    D, n_obj, n_frames = 256, 6, 10
+    proto = np.abs(rng.standard_normal((n_obj, D))).astype(np.float32) + 0.05
+    pos = rng.uniform(100, 900, (n_obj, 2))
+    vel = rng.uniform(-12, 12, (n_obj, 2))
+    size = rng.uniform(40, 120, (n_obj, 2))
+    frames = []
+    metric = nn_matching.NearestNeighborDistanceMetric("cosine", 0.5, 5)
+    tracker = Tracker(metric)
+    results = []
+    for f in range(n_frames):
+        dets_f = []
+        for o in range(n_obj):
+            if rng.uniform() < 0.15:
+                continue   # missed detection
+            p = pos[o] + vel[o] * f + rng.normal(0, 1.0, 2)
+            feat = proto[o] + np.abs(rng.standard_normal(D)).astype(np.float32) * 0.05
+            dets_f.append(np.concatenate([p, size[o], [0.9], feat]).astype(np.float32))
+        dets_f = np.asarray(dets_f, dtype=np.float32).reshape(-1, 5 + D)
+        frames.append(dets_f)
+        detections = [Detection(r[:4], r[4], r[5:]) for r in dets_f]
+        tracker.predict()
+        tracker.update(detections)
+        for t in tracker.tracks:
+            if t.is_confirmed() and t.time_since_update <= 1:
+                results.append([f, t.track_id] + t.to_tlwh().tolist())
+    np.savez(os.path.join(HERE, "deepsort_tracker.npz"), results=np.asarray(results, dtype=np.float64),
+             **{"frame%d" % i: fr for i, fr in enumerate(frames)})
+
+
+if __name__ == "__main__":
+    anchors()
+    cosine()
+    tracker_run()
+    print("golden fixtures written to", HERE)
