@@ -86,6 +86,11 @@ int b2_run_phases(b2_ctx* ctx, int phase_mask);
 /* Device time of the last b2_run_phases/b2_detect per phase (ms), measured with CUDA events. */
 int b2_phase_times(b2_ctx* ctx, float ms[8]);
 int b2_kernel_launches(b2_ctx* ctx);   /* kernels launched by one full pass */
+/* Per-launch-group profiling for the roofline report: device ms of every step of the plan (averaged
+ * over `reps` eager passes) and a description of each step (algorithmic FLOPs / HBM bytes). */
+int b2_num_steps(b2_ctx* ctx);
+int b2_profile_steps(b2_ctx* ctx, int reps, float* ms_out, int cap, int* n_out);
+int b2_step_info(b2_ctx* ctx, int idx, char* name, int name_cap, double* flops, double* bytes, int* kind);
 
 /* DeepSORT appearance cost: gallery [S,D] rows grouped per track by seg_offsets[T+1], dets [N,D];
  * cost[T,N] = min over the track's rows of (1 - cos).  Host pointers. */

@@ -41,6 +41,9 @@ SYMBOLS = [
     ("b2_run_phases", c_int, [c_void_p, c_int]),
     ("b2_phase_times", c_int, [c_void_p, POINTER(c_float)]),
     ("b2_kernel_launches", c_int, [c_void_p]),
+    ("b2_num_steps", c_int, [c_void_p]),
+    ("b2_profile_steps", c_int, [c_void_p, c_int, POINTER(c_float), c_int, POINTER(c_int)]),
+    ("b2_step_info", c_int, [c_void_p, c_int, ctypes.c_char_p, c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int)]),
     ("b2_cosine_cost", c_int, [c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     ("b2_op_conv2d", c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 18 + [c_void_p]),
 ]

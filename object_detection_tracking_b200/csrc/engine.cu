@@ -5,6 +5,7 @@
 // into a CUDA graph and replayed.  Graph structure follows Mask_RCNN_FPN.build_forward
 // (models.py:488-973); citations at each phase.
 #include <math.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
@@ -739,6 +740,71 @@ int b2_phase_times(b2_ctx* c, float ms[8]) {
 }
 
 int b2_kernel_launches(b2_ctx* c) { return c ? c->launches : -1; }
+
+// Per-step device timing (CUDA events around every launch group, eager mode), averaged over `reps`.
+int b2_profile_steps(b2_ctx* c, int reps, float* ms_out, int cap, int* n_out) {
+  B2_CHECK(c && ms_out && n_out, "b2_profile_steps: null argument");
+  B2_CUDA(cudaSetDevice(c->device));
+  B2_CHECK(c->weights_loaded, "b2_profile_steps: weights not loaded");
+  const int n = static_cast<int>(c->steps.size());
+  B2_CHECK(cap >= n, "b2_profile_steps: buffer too small");
+  std::vector<cudaEvent_t> ev(2 * n);
+  for (auto& e : ev) B2_CUDA(cudaEventCreate(&e));
+  std::vector<double> acc(n, 0.0);
+  for (int r = 0; r < reps; ++r) {
+    for (int i = 0; i < n; ++i) {
+      B2_CUDA(cudaEventRecord(ev[2 * i], c->stream));
+      if (run_step(c, c->steps[i])) return -1;
+      B2_CUDA(cudaEventRecord(ev[2 * i + 1], c->stream));
+    }
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; ++i) {
+      float ms = 0.f;
+      B2_CUDA(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]));
+      acc[i] += ms;
+    }
+  }
+  for (int i = 0; i < n; ++i) ms_out[i] = static_cast<float>(acc[i] / reps);
+  for (auto& e : ev) cudaEventDestroy(e);
+  *n_out = n;
+  return 0;
+}
+
+// Describes step `idx`: name, kind (0 = tensor-core conv/dense), algorithmic FLOPs and HBM bytes
+// (each operand read once, output written once, at the stored precision).
+int b2_step_info(b2_ctx* c, int idx, char* name, int name_cap, double* flops, double* bytes, int* kind) {
+  B2_CHECK(c && name && flops && bytes && kind, "b2_step_info: null argument");
+  B2_CHECK(idx >= 0 && idx < static_cast<int>(c->steps.size()), "b2_step_info: index out of range");
+  const b2_ctx::Step& s = c->steps[idx];
+  static const char* kKindNames[] = {"conv", "stem", "maxpool", "p6_subsample", "rpn_proposals", "roialign_proposals",
+                                     "head_post", "roialign_final"};
+  std::string nm = s.kind == 0 ? s.layer->name : kKindNames[s.kind];
+  *kind = s.kind;
+  *flops = 0;
+  *bytes = 0;
+  const double esz = c->split ? 4.0 : 2.0;
+  if (s.kind == 0) {
+    const ConvDesc& d = s.layer->d;
+    const double M = static_cast<double>(d.B) * d.Ho() * d.Wo();
+    const double K = static_cast<double>(d.R) * d.S * d.Cin;
+    *flops = 2.0 * M * K * d.Cout;
+    const double in_px = static_cast<double>(d.B) * d.in_H * d.in_W;
+    *bytes = in_px * d.Cin * esz + K * d.Cout * esz + M * d.Cout * (s.layer->io.out_f32 ? 4.0 : esz) +
+             (s.layer->io.res_hi ? M * d.Cout * esz / (d.res_shift ? 4.0 : 1.0) : 0.0);
+    nm += " [" + std::to_string(d.in_H) + "x" + std::to_string(d.in_W) + "x" + std::to_string(d.Cin) + " " +
+          std::to_string(d.R) + "x" + std::to_string(d.S) + "/" + std::to_string(d.stride) + " d" +
+          std::to_string(d.dil) + " ->" + std::to_string(d.Cout) + "]";
+  } else if (s.kind == 1) {
+    const double M = static_cast<double>(c->cfg.batch) * c->c1h * c->c1w;
+    *flops = 2.0 * M * 147 * 64;
+    *bytes = static_cast<double>(c->img_bytes) + M * 64 * esz;
+  } else if (s.kind == 2) {
+    *bytes = (static_cast<double>(c->c1.elems()) + c->pool.elems()) * esz;
+  }
+  snprintf(name, name_cap, "%s", nm.c_str());
+  return 0;
+}
+int b2_num_steps(b2_ctx* c) { return c ? static_cast<int>(c->steps.size()) : -1; }
 
 static int ensure_graph(b2_ctx* c) {
   if (c->graph || !c->cfg.use_cuda_graph) return 0;

@@ -119,6 +119,21 @@ class Detector:
     def kernel_launches(self) -> int:
         return int(self.lib.b2_kernel_launches(self._ctx))
 
+    def profile_steps(self, reps: int = 3) -> list:
+        """Per launch group: dict(name, kind, ms, flops, bytes) -- device time from CUDA events."""
+        n = int(self.lib.b2_num_steps(self._ctx))
+        ms = (c_float * n)()
+        nout = ctypes.c_int(0)
+        _lib.check(self.lib.b2_profile_steps(self._ctx, int(reps), ms, n, ctypes.byref(nout)), "b2_profile_steps")
+        out = []
+        buf = ctypes.create_string_buffer(256)
+        for i in range(nout.value):
+            fl, by, kind = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int(0)
+            _lib.check(self.lib.b2_step_info(self._ctx, i, buf, 256, ctypes.byref(fl), ctypes.byref(by),
+                                             ctypes.byref(kind)), "b2_step_info")
+            out.append(dict(name=buf.value.decode(), kind=kind.value, ms=float(ms[i]), flops=fl.value, bytes=by.value))
+        return out
+
 
 def cosine_cost(gallery: np.ndarray, seg_offsets: np.ndarray, dets: np.ndarray, device: int = 0,
                 precision: str = "split") -> np.ndarray:

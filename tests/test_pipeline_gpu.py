@@ -1,0 +1,151 @@
+"""Parity of the CUDA hot path (through the C ABI) with the CPU oracle, stage by stage and end to end.
+
+Tolerances (written per assertion): integer outputs (counts, labels, kept sets) bit-exact; box
+coordinates and scores within 1e-3 absolute in split precision (north_star); feature maps relative."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-12))
+
+
+@pytest.fixture(scope="module")
+def small():
+    from object_detection_tracking_b200.config import make_config
+    from object_detection_tracking_b200.engine import Detector
+    from object_detection_tracking_b200.synth import synth_frame, synth_weights
+    from oracle import frcnn
+    H, W, B = 192, 256, 2
+    cfg = make_config(resnet_num_block=(1, 2, 2, 1), max_size=W, short_edge_size=H)
+    Wt = synth_weights(cfg, 1234)
+    frames = np.stack([synth_frame(H, W, seed=s) for s in (3, 4)]).astype(np.float32)
+    det = Detector(cfg, B, H, W, precision="split", use_cuda_graph=False)
+    det.load_weights(Wt)
+    det.set_stage("image", frames)
+    det.run_phases(255)
+    ref = [frcnn.forward(cfg, Wt, frames[b]) for b in range(B)]
+    yield cfg, Wt, frames, det, ref
+    det.close()
+
+
+def test_backbone_fpn_stages(small):
+    cfg, Wt, frames, det, ref = small
+    for b in range(2):
+        for i in range(4):
+            g = det.get_stage("c%d" % (i + 2))[b].transpose(2, 0, 1)
+            assert rel(g, ref[b]["c2345"][i]) < 2e-5
+        for i in range(5):
+            r = ref[b]["p23456"][i]
+            g = det.get_stage("p%d" % (i + 2))[b].transpose(2, 0, 1)[:, :r.shape[1], :r.shape[2]]
+            assert rel(g, r) < 5e-5
+
+
+def test_rpn_logits_and_proposals(small):
+    cfg, Wt, frames, det, ref = small
+    K = cfg.rpn_test_post_nms_topk
+    for b in range(2):
+        for i in range(5):
+            g = det.get_stage("rpn_l%d" % i)[b]
+            cls, box = ref[b]["rpn"][i]
+            assert rel(g[..., :3], cls) < 1e-4 and rel(g[..., 3:15].reshape(box.shape), box) < 1e-4
+        cnt = det.get_stage("lvl_count")[b].reshape(-1)
+        lb = det.get_stage("lvl_boxes")[b].reshape(5, K, 4)
+        ls = det.get_stage("lvl_scores")[b].reshape(5, K)
+        for i in range(5):
+            rb, rs = ref[b]["level_proposals"][i]
+            assert int(cnt[i]) == len(rs)                                   # kept set size: exact
+            assert np.abs(lb[i, :len(rs)] - rb).max() < 1e-3               # px
+            assert np.abs(ls[i, :len(rs)] - rs).max() < 1e-4
+        pc = int(det.get_stage("proposal_count")[b].reshape(-1)[0])
+        assert pc == len(ref[b]["proposal_scores"])
+        pb = det.get_stage("proposal_boxes")[b].reshape(K, 4)
+        assert np.abs(pb[:pc] - ref[b]["proposal_boxes"]).max() < 1e-3
+
+
+def test_roi_head_and_final_outputs(small):
+    cfg, Wt, frames, det, ref = small
+    K, R, nc = cfg.rpn_test_post_nms_topk, cfg.result_per_im, cfg.num_class
+    for b in range(2):
+        n = len(ref[b]["proposal_scores"])
+        rf = det.get_stage("roi_feat").reshape(-1, 7, 7, 256)[b * K:b * K + n].transpose(0, 3, 1, 2)
+        assert rel(rf, ref[b]["roi_feat"]) < 5e-5
+        hl = det.get_stage("head_logits")[b, :n, :, 0]
+        assert rel(hl[:, :nc], ref[b]["cls_logits"]) < 1e-4
+        assert rel(hl[:, nc + 4:nc + 4 * nc].reshape(n, nc - 1, 4), ref[b]["box_logits"]) < 1e-4
+        fc = int(det.get_stage("final_count")[b].reshape(-1)[0])
+        assert fc == len(ref[b]["final_probs"])                             # R: exact
+        fl = det.get_stage("final_labels")[b].reshape(-1)[:fc]
+        np.testing.assert_array_equal(fl, ref[b]["final_labels"])          # class ids: bit-exact
+        fb = det.get_stage("final_boxes")[b].reshape(R, 4)[:fc]
+        fp = det.get_stage("final_probs")[b].reshape(-1)[:fc]
+        assert np.abs(fb - ref[b]["final_boxes"]).max() < 1e-3              # north_star tolerance, px
+        assert np.abs(fp - ref[b]["final_probs"]).max() < 1e-3
+        bf = det.get_stage("fpn_box_feat")[b * R:b * R + fc]
+        assert rel(bf, ref[b]["fpn_box_feat"]) < 5e-5
+
+
+def test_postprocess_kernels_bit_exact_on_oracle_inputs(small):
+    """Feed the oracle's own fp32 RPN logits to the proposal kernels: selected sets and order must be
+    identical, coordinates equal up to expf ulps."""
+    cfg, Wt, frames, det, ref = small
+    K = cfg.rpn_test_post_nms_topk
+    for i in range(5):
+        shape, _ = det.stage_shape("rpn_l%d" % i)
+        buf = np.zeros(shape, np.float32)
+        for b in range(2):
+            cls, box = ref[b]["rpn"][i]
+            buf[b, :, :, :3] = cls
+            buf[b, :, :, 3:15] = box.reshape(box.shape[0], box.shape[1], 12)
+        det.set_stage("rpn_l%d" % i, buf)
+    det.run_phases(8)    # proposals only
+    for b in range(2):
+        cnt = det.get_stage("lvl_count")[b].reshape(-1)
+        lb = det.get_stage("lvl_boxes")[b].reshape(5, K, 4)
+        ls = det.get_stage("lvl_scores")[b].reshape(5, K)
+        for i in range(5):
+            rb, rs = ref[b]["level_proposals"][i]
+            assert int(cnt[i]) == len(rs)
+            np.testing.assert_array_equal(ls[i, :len(rs)], rs)              # same logits selected, same order
+            assert np.abs(lb[i, :len(rs)] - rb).max() < 2e-4
+    det.run_phases(255)  # restore the context's own state for later tests
+
+
+def test_fp16_precision_mode_is_close(small):
+    from object_detection_tracking_b200.engine import Detector
+    cfg, Wt, frames, det, ref = small
+    d16 = Detector(cfg, 2, 192, 256, precision="fp16", use_cuda_graph=False)
+    d16.load_weights(Wt)
+    d16.set_stage("image", frames)
+    d16.run_phases(255)
+    for i in range(4):
+        g = d16.get_stage("c%d" % (i + 2))[0].transpose(2, 0, 1)
+        assert rel(g, ref[0]["c2345"][i]) < 2e-2          # fp16 operands: ~1e-3 per layer
+    d16.close()
+
+
+def test_cuda_graph_replay_equals_eager_and_outputs_are_fresh(small):
+    from object_detection_tracking_b200.engine import Detector
+    cfg, Wt, frames, det, ref = small
+    dg = Detector(cfg, 2, 192, 256, precision="split", use_cuda_graph=True)
+    dg.load_weights(Wt)
+    o1 = dg.detect_host(frames)
+    o2 = dg.detect_host(frames)
+    for k in o1:
+        np.testing.assert_array_equal(o1[k], o2[k])
+        assert o1[k] is not o2[k]
+    for b in range(2):
+        r = int(o1["valid"][b])
+        assert r == len(ref[b]["final_probs"])
+        np.testing.assert_array_equal(o1["labels"][b, :r].astype(np.int64), ref[b]["final_labels"])
+        assert np.abs(o1["boxes"][b, :r] - ref[b]["final_boxes"]).max() < 1e-3
+    # u8 frames give the same detections as the float32 copy of the same frames
+    du = Detector(cfg, 2, 192, 256, precision="split", input_dtype="uint8", use_cuda_graph=True)
+    du.load_weights(Wt)
+    o3 = du.detect_host(frames.astype(np.uint8))
+    np.testing.assert_array_equal(o3["labels"], o1["labels"])
+    np.testing.assert_array_equal(o3["boxes"], o1["boxes"])
+    dg.close(); du.close()

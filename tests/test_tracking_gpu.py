@@ -1,0 +1,53 @@
+"""DeepSORT appearance cost on the GPU vs golden vectors produced by the reference's own nn_matching."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cosine_cost_matches_reference_golden(golden_dir):
+    from object_detection_tracking_b200.engine import cosine_cost
+    g = np.load(os.path.join(golden_dir, "deepsort_cosine.npz"))
+    cost = cosine_cost(g["gallery"], g["seg"], g["dets"], precision="split")
+    assert cost.shape == g["cost"].shape
+    assert np.abs(cost - g["cost"]).max() < 2e-6       # fp32 cosine in [0, 2]: a few ulps
+    c16 = cosine_cost(g["gallery"], g["seg"], g["dets"], precision="fp16")
+    assert np.abs(c16 - g["cost"]).max() < 2e-3
+
+
+def test_metric_class_is_drop_in(golden_dir):
+    from object_detection_tracking_b200.tracking import GpuNearestNeighborDistanceMetric
+    from oracle import nn_matching
+    rng = np.random.default_rng(0)
+    m_gpu = GpuNearestNeighborDistanceMetric("cosine", 0.5, budget=5)
+    m_ref = nn_matching.NearestNeighborDistanceMetric("cosine", 0.5, budget=5)
+    for step in range(4):
+        feats = np.abs(rng.standard_normal((9, 256))).astype(np.float32)
+        targets = rng.integers(0, 6, 9)
+        active = sorted(set(targets.tolist()))
+        m_gpu.partial_fit(feats, targets, active)
+        m_ref.partial_fit(feats, targets, active)
+        q = np.abs(rng.standard_normal((11, 256))).astype(np.float32)
+        a = m_gpu.distance(q, active)
+        b = m_ref.distance(q, active)
+        assert a.dtype == np.float64 and a.shape == b.shape
+        assert np.abs(a - b).max() < 2e-6
+    assert m_gpu.distance(np.zeros((0, 256), np.float32), [0]).shape == (1, 0)     # empty detections
+    with pytest.raises(ValueError):
+        GpuNearestNeighborDistanceMetric("euclidean", 0.5)
+
+
+def test_large_gallery_many_tiles():
+    """budget 60 x 100 tracks (multi-queuer defaults): S = 6000 rows, 47 M-tiles."""
+    from object_detection_tracking_b200.engine import cosine_cost
+    from oracle import nn_matching
+    rng = np.random.default_rng(1)
+    T, S_per, N, D = 100, 60, 100, 256
+    gal = np.abs(rng.standard_normal((T * S_per, D))).astype(np.float32)
+    dets = np.abs(rng.standard_normal((N, D))).astype(np.float32)
+    seg = np.arange(0, T * S_per + 1, S_per, dtype=np.int32)
+    cost = cosine_cost(gal, seg, dets)
+    ref = np.stack([nn_matching.nn_cosine_distance(gal[seg[t]:seg[t + 1]], dets) for t in range(T)])
+    assert np.abs(cost - ref).max() < 2e-6

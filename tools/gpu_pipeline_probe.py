@@ -47,14 +47,14 @@ def main():
             cls, box = o["rpn"][i]
             print("b%d rpn%d cls rel %.3e box rel %.3e" % (b, i, rel(g[..., :3], cls), rel(g[..., 3:15].reshape(box.shape), box)))
         cnt = det.get_stage("lvl_count")[b].reshape(-1)
-        lb = det.get_stage("lvl_boxes")[b]; ls = det.get_stage("lvl_scores")[b].reshape(5, -1)
+        lb = det.get_stage("lvl_boxes")[b].reshape(5, -1, 4); ls = det.get_stage("lvl_scores")[b].reshape(5, -1)
         for i in range(5):
             rb, rs = o["level_proposals"][i]
             n = min(int(cnt[i]), len(rs))
             print("b%d lvl%d count gpu %d ref %d  box maxabs %.3e score maxabs %.3e" % (
                 b, i, cnt[i], len(rs), np.abs(lb[i, :n] - rb[:n]).max() if n else 0, np.abs(ls[i, :n] - rs[:n]).max() if n else 0))
         pc = int(det.get_stage("proposal_count")[b].reshape(-1)[0])
-        pb = det.get_stage("proposal_boxes")[b]
+        pb = det.get_stage("proposal_boxes")[b].reshape(-1, 4)
         n = min(pc, len(o["proposal_boxes"]))
         print("b%d proposals gpu %d ref %d box maxabs %.3e" % (b, pc, len(o["proposal_boxes"]), np.abs(pb[:n] - o["proposal_boxes"][:n]).max()))
         K = cfg.rpn_test_post_nms_topk
@@ -65,7 +65,7 @@ def main():
         print("b%d cls_logits rel %.3e box_logits rel %.3e" % (b, rel(hl[:, :nc, 0], o["cls_logits"][:n]),
               rel(hl[:, nc + 4:nc + 4 * nc, 0].reshape(n, nc - 1, 4), o["box_logits"][:n])))
         fc = int(det.get_stage("final_count")[b].reshape(-1)[0])
-        fb = det.get_stage("final_boxes")[b]; fp = det.get_stage("final_probs")[b].reshape(-1); fl = det.get_stage("final_labels")[b].reshape(-1)
+        fb = det.get_stage("final_boxes")[b].reshape(-1, 4); fp = det.get_stage("final_probs")[b].reshape(-1); fl = det.get_stage("final_labels")[b].reshape(-1)
         n = min(fc, len(o["final_probs"]))
         print("b%d final gpu %d ref %d labels_equal %s box maxabs %.3e prob maxabs %.3e" % (
             b, fc, len(o["final_probs"]), bool(np.array_equal(fl[:n], o["final_labels"][:n])),
