@@ -99,9 +99,7 @@ struct b2_ctx {
   // buffers
   void* img = nullptr;
   size_t img_bytes = 0;
-  float* stem_w = nullptr;
-  float* stem_b = nullptr;
-  Planes c1, pool, cfeat[4], lat[4], pfeat[5], rpn_h[5];
+  Planes stem_u, c1, pool, cfeat[4], lat[4], pfeat[5], rpn_h[5];
   float* rpn_out[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   RpnParams rpn;
   RoiAlignParams roi1, roi2;
@@ -160,7 +158,7 @@ void reg_raw(b2_ctx* c, const std::string& name, void* ptr, int kind, int64_t a,
 Layer* add_conv(b2_ctx* c, int phase, const std::string& name, const Planes& in, int view_h, int view_w, int R,
                 int stride, int dil, int pt, int pb, int pl, int pr, int Cout, bool bn, bool bias, bool relu,
                 const Planes& out, int off_h, int off_w, const Planes* res, int res_shift, float* out_f32 = nullptr,
-                int ldc_f32 = 0, int kind = 0) {
+                int ldc_f32 = 0, int kind = 0, int S = 0) {
   std::unique_ptr<Layer> L(new Layer());
   L->name = name;
   L->has_bn = bn;
@@ -169,7 +167,7 @@ Layer* add_conv(b2_ctx* c, int phase, const std::string& name, const Planes& in,
   ConvDesc& d = L->d;
   d.B = in.B; d.in_H = view_h; d.in_W = view_w; d.Cin = in.C;
   d.in_pitch_H = in.H; d.in_pitch_W = in.W; d.in_ld = in.C;
-  d.R = R; d.S = R; d.stride = stride; d.dil = dil;
+  d.R = R; d.S = S > 0 ? S : R; d.stride = stride; d.dil = dil;
   d.pad_t = pt; d.pad_b = pb; d.pad_l = pl; d.pad_r = pr;
   d.Cout = Cout;
   d.relu = relu ? 1 : 0;
@@ -183,7 +181,7 @@ Layer* add_conv(b2_ctx* c, int phase, const std::string& name, const Planes& in,
     d.res_H = res->H; d.res_W = res->W; d.ldr = res->C; d.res_shift = res_shift;
   }
   L->w.Cout_pad = (Cout + 15) / 16 * 16;
-  L->w.K = R * R * in.C;
+  L->w.K = d.R * d.S * in.C;
   L->w.w_hi = c->alloc<__half>(static_cast<size_t>(L->w.Cout_pad) * L->w.K);
   L->w.w_lo = c->split ? c->alloc<__half>(static_cast<size_t>(L->w.Cout_pad) * L->w.K) : nullptr;
   L->w.bias = c->alloc<float>(L->w.Cout_pad);
@@ -252,11 +250,13 @@ int build_plan(b2_ctx* c) {
   // ---- input + stem + pool (phase 0) ----
   c->img_bytes = static_cast<size_t>(B) * H * W * 3 * (cfg.input_dtype == 1 ? 1 : 4);
   c->img = c->alloc<uint8_t>(c->img_bytes);
-  c->stem_w = c->alloc<float>(147 * 64);
-  c->stem_b = c->alloc<float>(64);
+  B2_CHECK(c->alloc_planes(c->stem_u, B, c->c1h + 3, c->c1w, 64), "alloc stem operand");
   B2_CHECK(c->alloc_planes(c->c1, B, c->c1h, c->c1w, 64), "alloc c1");
   B2_CHECK(c->alloc_planes(c->pool, B, c->ch[0], c->cw[0], 64), "alloc pool");
   c->steps.push_back({0, 1, nullptr});
+  // conv0 as a 4x1 VALID conv over the packed operand (see stem.cu), BN + ReLU in the epilogue
+  add_conv(c, 0, "conv0", c->stem_u, c->c1h + 3, c->c1w, 4, 1, 1, 0, 0, 0, 0, 64, true, false, true, c->c1, 0, 0,
+           nullptr, 0, nullptr, 0, 5, 1);
   c->steps.push_back({0, 2, nullptr});
   reg_planes(c, "c1", c->c1);
   reg_planes(c, "pool", c->pool);
@@ -480,8 +480,8 @@ int run_step(b2_ctx* c, const b2_ctx::Step& s) {
       if (cfg.conv_impl == 0) return conv_tc_launch(s.layer->plan, st);
       return conv_simt_launch(s.layer->d, s.layer->w, s.layer->io, c->split, st);
     case 1:
-      return stem_launch(c->img, cfg.input_dtype == 1, cfg.batch, cfg.height, cfg.width, c->stem_w, c->stem_b,
-                         c->c1.hi, c->c1.lo, c->c1h, c->c1w, st);
+      return stem_pack_launch(c->img, cfg.input_dtype == 1, cfg.batch, cfg.height, cfg.width, c->stem_u.hi,
+                              c->stem_u.lo, c->stem_u.H, c->stem_u.W, st);
     case 2:
       return maxpool_launch(c->c1.hi, c->c1.lo, cfg.batch, c->c1h, c->c1w, 64, c->pool.hi, c->pool.lo, c->ch[0],
                             c->cw[0], st);
@@ -600,6 +600,20 @@ int load_layer(b2_ctx* c, Layer* L, const WeightSet& ws) {
         for (int o = 0; o < Cout; ++o)
           packed[static_cast<size_t>(o) * K + static_cast<size_t>(t) * Cin + ci] = static_cast<float>(src[o] * scale[o]);
       }
+  } else if (L->kind == 5) {
+    // stem: reference HWIO [7,7,3,64] re-indexed for the packed operand (stem.cu):
+    // W'[o][r][s*12 + ry*6 + sx*3 + c] = W[2r+ry][2s+sx][c][o]
+    const float* w = ws.get(L->name + "/W", 7 * 7 * 3 * 64);
+    if (!w || bn_fold(ws, L->name, Cout, scale, shift)) return -1;
+    for (int r = 0; r < 4; ++r)
+      for (int ch = 0; ch < 48; ++ch) {
+        const int s4 = ch / 12, r12 = ch % 12, ry = r12 / 6, sx = (r12 % 6) / 3, cc = r12 % 3;
+        const int rr = 2 * r + ry, ss = 2 * s4 + sx;
+        if (rr >= 7 || ss >= 7) continue;
+        const float* src = w + (static_cast<size_t>(rr * 7 + ss) * 3 + cc) * 64;
+        for (int o = 0; o < Cout; ++o)
+          packed[static_cast<size_t>(o) * K + static_cast<size_t>(r) * Cin + ch] = static_cast<float>(src[o] * scale[o]);
+      }
   } else if (L->kind == 1) {
     // fc6: reference flattens NCHW (index c*49 + y*7 + x, models.py:1056 + nn.py:738-740);
     // our ROI features are [y][x][c], so permute the rows of W [in, out].
@@ -695,18 +709,6 @@ int b2_load_weights(b2_ctx* c, const char* const* names, const float* const* dat
   B2_CUDA(cudaSetDevice(c->device));
   WeightSet ws;
   for (int i = 0; i < n; ++i) ws.m[names[i]] = std::make_pair(data[i], numel[i]);
-  // stem: HWIO [7,7,3,64] == [147][64]; BN folded
-  {
-    const float* w = ws.get("conv0/W", 147 * 64);
-    std::vector<double> scale, shift;
-    if (!w || bn_fold(ws, "conv0", 64, scale, shift)) return -1;
-    std::vector<float> pw(147 * 64), pb(64);
-    for (int k = 0; k < 147; ++k)
-      for (int o = 0; o < 64; ++o) pw[k * 64 + o] = static_cast<float>(w[k * 64 + o] * scale[o]);
-    for (int o = 0; o < 64; ++o) pb[o] = static_cast<float>(shift[o]);
-    B2_CUDA(cudaMemcpy(c->stem_w, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice));
-    B2_CUDA(cudaMemcpy(c->stem_b, pb.data(), pb.size() * 4, cudaMemcpyHostToDevice));
-  }
   // shared RPN weights: packed once, every level's layer gets its own copy of the (small) operand
   for (auto& L : c->layers)
     if (load_layer(c, L.get(), ws)) return -1;
@@ -776,7 +778,7 @@ int b2_step_info(b2_ctx* c, int idx, char* name, int name_cap, double* flops, do
   B2_CHECK(c && name && flops && bytes && kind, "b2_step_info: null argument");
   B2_CHECK(idx >= 0 && idx < static_cast<int>(c->steps.size()), "b2_step_info: index out of range");
   const b2_ctx::Step& s = c->steps[idx];
-  static const char* kKindNames[] = {"conv", "stem", "maxpool", "p6_subsample", "rpn_proposals", "roialign_proposals",
+  static const char* kKindNames[] = {"conv", "stem_pack", "maxpool", "p6_subsample", "rpn_proposals", "roialign_proposals",
                                      "head_post", "roialign_final"};
   std::string nm = s.kind == 0 ? s.layer->name : kKindNames[s.kind];
   *kind = s.kind;
@@ -795,9 +797,7 @@ int b2_step_info(b2_ctx* c, int idx, char* name, int name_cap, double* flops, do
           std::to_string(d.R) + "x" + std::to_string(d.S) + "/" + std::to_string(d.stride) + " d" +
           std::to_string(d.dil) + " ->" + std::to_string(d.Cout) + "]";
   } else if (s.kind == 1) {
-    const double M = static_cast<double>(c->cfg.batch) * c->c1h * c->c1w;
-    *flops = 2.0 * M * 147 * 64;
-    *bytes = static_cast<double>(c->img_bytes) + M * 64 * esz;
+    *bytes = static_cast<double>(c->img_bytes) + static_cast<double>(c->stem_u.elems()) * esz;
   } else if (s.kind == 2) {
     *bytes = (static_cast<double>(c->c1.elems()) + c->pool.elems()) * esz;
   }

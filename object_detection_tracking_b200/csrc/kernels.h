@@ -8,8 +8,8 @@ namespace b2 {
 // stem.cu
 int f32_to_planes(const float* src, __half* hi, __half* lo, size_t n, cudaStream_t s);
 int planes_to_f32(const __half* hi, const __half* lo, float* dst, size_t n, cudaStream_t s);
-int stem_launch(const void* img, int is_u8, int B, int H, int W, const float* wgt, const float* bias, __half* out_hi,
-                __half* out_lo, int Ho, int Wo, cudaStream_t s);
+int stem_pack_launch(const void* img, int is_u8, int B, int H, int W, __half* out_hi, __half* out_lo, int Hu, int Wu,
+                     cudaStream_t s);
 int maxpool_launch(const __half* in_hi, const __half* in_lo, int B, int H, int W, int C, __half* out_hi,
                    __half* out_lo, int Ho, int Wo, cudaStream_t s);
 

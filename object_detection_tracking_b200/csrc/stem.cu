@@ -1,4 +1,4 @@
-// Frame ingest kernels: fused preprocess + 7x7/2 stem convolution, 3x3/2 max-pool, and the
+// Frame ingest kernels: fused preprocess + stem operand pack (7x7/2 conv -> tensor-core shape), 3x3/2 max-pool, and the
 // fp32 <-> (hi, lo) fp16 plane conversions.
 //
 // Reference ops replaced: build_preprocess (models.py:337-357), resnet_fpn_backbone stem
@@ -29,73 +29,50 @@ __global__ void planes_to_f32_kernel(const __half* __restrict__ hi, const __half
   }
 }
 
-// Stem: each thread = one output pixel x 16 output channels; weights [147][64] fp32 in shared memory.
-// Input is the raw frame (uint8 or float32, HWC, BGR); normalisation follows models.py:345-355 op by op:
-// x * (1/255), - mean, / std  (mean/std reversed to BGR order).
-constexpr int kStemTaps = 7 * 7 * 3;
-
+// Stem operand pack.  The 7x7 stride-2 conv on 3 channels is not a tensor-core shape, so the frame is
+// re-laid out once per pass so that it becomes a 4x1 stride-1 conv on 64 channels (K = 256) that the
+// tcgen05 implicit-GEMM kernel takes unchanged:
+//   P  = normalised frame, zero padded [3 top/left, 2 + pad-to-32 bottom/right]        (nn.py:871-877)
+//   U[b][y][q][s*12 + ry*6 + sx*3 + c] = P[b][2y + ry][2(q + s) + sx][c]   s in 0..3, ry,sx in 0..1, c in 0..2
+//   conv0[p][q][o] = sum_{r<4} sum_{ch<64} U[p + r][q][ch] * W'[o][r][ch],  W'[o][r][ch] = W[2r+ry][2s+sx][c][o]
+// (taps with 2r+ry == 7 or 2s+sx == 7 and channels 48..63 carry zero weights).  Normalisation follows
+// models.py:345-355 op by op: x * (1/255), - mean, / std (BGR order), exact fp32, then the (hi, lo) split.
 template <typename TIn>
-__global__ void __launch_bounds__(256) stem_kernel(const TIn* __restrict__ img, int B, int H, int W,
-                                                   const float* __restrict__ wgt /*[147][64]*/,
-                                                   const float* __restrict__ bias /*[64]*/, __half* __restrict__ out_hi,
-                                                   __half* __restrict__ out_lo, int Ho, int Wo) {
-  __shared__ __align__(16) float sw[kStemTaps * 64];
-  __shared__ float sb[64];
-  for (int i = threadIdx.x; i < kStemTaps * 64; i += blockDim.x) sw[i] = wgt[i];
-  if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
+__global__ void __launch_bounds__(256) stem_pack_kernel(const TIn* __restrict__ img, int B, int H, int W,
+                                                        __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                                        int Hu, int Wu) {
   const float mean[3] = {0.406f, 0.456f, 0.485f};   // BGR order (models.py:350-352)
   const float stdv[3] = {0.225f, 0.224f, 0.229f};
-  const int cg = threadIdx.x & 3;                   // 16-channel group
-  const size_t npix = static_cast<size_t>(B) * Ho * Wo;
-  for (size_t pix = blockIdx.x * 64ull + (threadIdx.x >> 2); pix < npix; pix += static_cast<size_t>(gridDim.x) * 64) {
-    const int b = static_cast<int>(pix / (static_cast<size_t>(Ho) * Wo));
-    const int rem = static_cast<int>(pix % (static_cast<size_t>(Ho) * Wo));
-    const int p = rem / Wo, q = rem % Wo;
-    float acc[16];
+  const size_t total = static_cast<size_t>(B) * Hu * Wu * 8;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(idx & 7);
+    const size_t pix = idx >> 3;
+    const int b = static_cast<int>(pix / (static_cast<size_t>(Hu) * Wu));
+    const int rem = static_cast<int>(pix % (static_cast<size_t>(Hu) * Wu));
+    const int y = rem / Wu, q = rem % Wu;
+    __align__(16) __half hb[8];
+    __align__(16) __half lb[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-    for (int r = 0; r < 7; ++r) {
-      const int ih = p * 2 - 3 + r;
-      if (ih < 0 || ih >= H) continue;
-      for (int s = 0; s < 7; ++s) {
-        const int iw = q * 2 - 3 + s;
-        if (iw < 0 || iw >= W) continue;
-        const TIn* px = img + ((static_cast<size_t>(b) * H + ih) * W + iw) * 3;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float x = static_cast<float>(px[c]);
+    for (int j = 0; j < 8; ++j) {
+      const int ch = cg * 8 + j;
+      float v = 0.f;
+      if (ch < 48) {
+        const int s = ch / 12, r12 = ch % 12;
+        const int ry = r12 / 6, sx = (r12 % 6) / 3, c = r12 % 3;
+        const int iy = 2 * y + ry - 3, ix = 2 * (q + s) + sx - 3;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+          float x = static_cast<float>(img[((static_cast<size_t>(b) * H + iy) * W + ix) * 3 + c]);
           x = __fmul_rn(x, 1.0f / 255);
           x = __fsub_rn(x, mean[c]);
-          x = __fdiv_rn(x, stdv[c]);
-          const float4* w4 = reinterpret_cast<const float4*>(&sw[((r * 7 + s) * 3 + c) * 64 + cg * 16]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 wv = w4[j];
-            acc[4 * j + 0] = fmaf(x, wv.x, acc[4 * j + 0]);
-            acc[4 * j + 1] = fmaf(x, wv.y, acc[4 * j + 1]);
-            acc[4 * j + 2] = fmaf(x, wv.z, acc[4 * j + 2]);
-            acc[4 * j + 3] = fmaf(x, wv.w, acc[4 * j + 3]);
-          }
+          v = __fdiv_rn(x, stdv[c]);
         }
       }
+      hb[j] = __float2half_rn(v);
+      lb[j] = __float2half_rn((v - __half2float(hb[j])) * kLoScale);
     }
-    __align__(16) __half hbuf[16];
-    __align__(16) __half lbuf[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float v = fmaxf(acc[j] + sb[cg * 16 + j], 0.f);
-      hbuf[j] = __float2half_rn(v);
-      lbuf[j] = __float2half_rn((v - __half2float(hbuf[j])) * kLoScale);
-    }
-    uint4* oh = reinterpret_cast<uint4*>(out_hi + pix * 64 + cg * 16);
-    oh[0] = reinterpret_cast<uint4*>(hbuf)[0];
-    oh[1] = reinterpret_cast<uint4*>(hbuf)[1];
-    if (out_lo) {
-      uint4* ol = reinterpret_cast<uint4*>(out_lo + pix * 64 + cg * 16);
-      ol[0] = reinterpret_cast<uint4*>(lbuf)[0];
-      ol[1] = reinterpret_cast<uint4*>(lbuf)[1];
-    }
+    *reinterpret_cast<uint4*>(out_hi + pix * 64 + cg * 8) = *reinterpret_cast<uint4*>(hb);
+    if (out_lo) *reinterpret_cast<uint4*>(out_lo + pix * 64 + cg * 8) = *reinterpret_cast<uint4*>(lb);
   }
 }
 
@@ -169,14 +146,14 @@ int planes_to_f32(const __half* hi, const __half* lo, float* dst, size_t n, cuda
   return 0;
 }
 
-int stem_launch(const void* img, int is_u8, int B, int H, int W, const float* wgt, const float* bias, __half* out_hi,
-                __half* out_lo, int Ho, int Wo, cudaStream_t s) {
-  const size_t npix = static_cast<size_t>(B) * Ho * Wo;
-  const unsigned grid = grid_for(npix, 64, 148 * 16);
+int stem_pack_launch(const void* img, int is_u8, int B, int H, int W, __half* out_hi, __half* out_lo, int Hu, int Wu,
+                     cudaStream_t s) {
+  const size_t total = static_cast<size_t>(B) * Hu * Wu * 8;
+  const unsigned grid = grid_for(total, 256, 148 * 32);
   if (is_u8)
-    stem_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(img), B, H, W, wgt, bias, out_hi, out_lo, Ho, Wo);
+    stem_pack_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(img), B, H, W, out_hi, out_lo, Hu, Wu);
   else
-    stem_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(img), B, H, W, wgt, bias, out_hi, out_lo, Ho, Wo);
+    stem_pack_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(img), B, H, W, out_hi, out_lo, Hu, Wu);
   B2_CUDA(cudaGetLastError());
   return 0;
 }
