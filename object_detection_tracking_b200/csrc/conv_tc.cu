@@ -20,6 +20,8 @@
 // Reference ops replaced: nn.conv2d (nn.py:337-381) + BatchNorm inference (nn.py:1771-1774, folded into
 // weights/bias) + ReLU (nn.py:606-613) + residual add (nn.py:519-521) + FPN upsample-add
 // (nn.py:989-996) + dense (nn.py:730-774).
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.h"
@@ -56,7 +58,12 @@ struct ConvTcParams {
   const __half* res_lo;
   int ldr, res_H, res_W, res_shift;
   int relu;
+  int epi_mode;      // 0 = direct global loads/stores per thread, 1 = TMA-staged (residual in, result out)
+  uint32_t epi_off;  // byte offset of the epilogue staging buffers inside the tile area
 };
+
+constexpr int kEpiBufs = 4;            // ring of 16-column chunk buffers
+constexpr int kEpiPlaneBytes = kBlockM * 16 * 2;   // 128 rows x 16 fp16 = 4 KB per plane
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
@@ -141,21 +148,98 @@ __device__ __forceinline__ void epilogue_chunk16(const ConvTcParams& p, const ui
   }
 }
 
+// Same math on a chunk whose residual sits in (and whose result goes back to) a 32-byte-swizzled
+// shared-memory buffer [128 rows][16 fp16]: row r, 16-byte half jj lives at r*32 + ((jj ^ ((r>>2)&1)) * 16).
+template <bool SPLIT>
+__device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, const uint32_t (&a0)[16],
+                                                      const uint32_t (&a1)[16], uint8_t* buf, int row, int n,
+                                                      bool has_res) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    v[j] = __uint_as_float(a0[j]);
+    if (SPLIT) v[j] = fmaf(__uint_as_float(a1[j]), kLoInv, v[j]);
+  }
+  const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float4 b = __ldg(b4 + j);
+    v[4 * j + 0] += b.x;
+    v[4 * j + 1] += b.y;
+    v[4 * j + 2] += b.z;
+    v[4 * j + 3] += b.w;
+  }
+  const int sw = (row >> 2) & 1;
+  uint4* hi0 = reinterpret_cast<uint4*>(buf + row * 32 + ((0 ^ sw) << 4));
+  uint4* hi1 = reinterpret_cast<uint4*>(buf + row * 32 + ((1 ^ sw) << 4));
+  uint4* lo0 = reinterpret_cast<uint4*>(buf + kEpiPlaneBytes + row * 32 + ((0 ^ sw) << 4));
+  uint4* lo1 = reinterpret_cast<uint4*>(buf + kEpiPlaneBytes + row * 32 + ((1 ^ sw) << 4));
+  if (has_res) {
+    uint4 r[2] = {*hi0, *hi1};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const __half2* h = reinterpret_cast<const __half2*>(&r[j]);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 f = __half22float2(h[t]);
+        v[8 * j + 2 * t] += f.x;
+        v[8 * j + 2 * t + 1] += f.y;
+      }
+    }
+    if (SPLIT) {
+      uint4 l[2] = {*lo0, *lo1};
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const __half2* h = reinterpret_cast<const __half2*>(&l[j]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float2 f = __half22float2(h[t]);
+          v[8 * j + 2 * t] = fmaf(f.x, kLoInv, v[8 * j + 2 * t]);
+          v[8 * j + 2 * t + 1] = fmaf(f.y, kLoInv, v[8 * j + 2 * t + 1]);
+        }
+      }
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
+  uint32_t hi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) hi[j] = pack_half2(v[2 * j], v[2 * j + 1]);
+  *hi0 = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *hi1 = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+  if (SPLIT) {
+    uint32_t lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float2 h = __half22float2(*reinterpret_cast<__half2*>(&hi[j]));
+      lo[j] = pack_half2((v[2 * j] - h.x) * kLoScale, (v[2 * j + 1] - h.y) * kLoScale);
+    }
+    *lo0 = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *lo1 = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+  }
+}
+
 template <bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
+               const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ CUtensorMap tmR_lo,
                const __grid_constant__ ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte aligned tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + static_cast<size_t>(p.num_stages) * p.stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + p.epi_off + kEpiBufs * 2 * kEpiPlaneBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tmem_full = bars + 2 * kMaxStages;
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  uint64_t* res_full = bars + 2 * kMaxStages + 4;                       // [kEpiBufs]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4 + kEpiBufs);
+  uint8_t* epi = tiles + p.epi_off;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -177,6 +261,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);   // one arrive per epilogue warp
     }
+    for (int i = 0; i < kEpiBufs; ++i) mbar_init(&res_full[i], 1);
     fence_mbar_init();
     fence_proxy_async();
   }
@@ -289,37 +374,108 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int row = ew * 32 + lane;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.num_n_blocks;
-      const int n_blk = tile - m_blk * p.num_n_blocks;
-      const int m = m_blk * kBlockM + row;
-      const int n0 = n_blk * p.block_n;
-      const bool valid = m < p.M;
-      size_t opix = 0, rpix = 0;
-      if (valid) {
-        const int img = m / p.HoWo;
-        const int rem = m - img * p.HoWo;
-        const int pp = rem / p.Wo + p.off_h;
-        const int qq = rem - (rem / p.Wo) * p.Wo + p.off_w;
-        opix = (static_cast<size_t>(img) * p.out_H + pp) * p.out_W + qq;
-        rpix = (static_cast<size_t>(img) * p.res_H + (pp >> p.res_shift)) * p.res_W + (qq >> p.res_shift);
+    if (p.epi_mode == 1) {
+      // ---- TMA-staged: residual chunk arrives in a swizzled smem buffer (TMA load, issued two chunks
+      // ahead, also across tile boundaries), the result overwrites it in place and leaves by TMA store.
+      const bool has_res = p.res_hi != nullptr;
+      const bool elected = threadIdx.x == 128;
+      const int nch = p.block_n >> 4;
+      const uint32_t chunk_bytes = kEpiPlaneBytes * ((SPLIT && p.res_lo != nullptr) ? 2 : 1);
+      const uint32_t buf_bytes = 2 * kEpiPlaneBytes;
+      uint32_t g = 0;          // global chunk counter -> buffer g & 3
+      uint32_t rph = 0;        // phase bits of res_full[]
+      // look-ahead cursor (chunk g + 2), advanced only by the elected thread
+      int la_tile = blockIdx.x, la_c = 0;
+      auto issue_res = [&](uint32_t gi) {
+        if (la_tile >= p.num_tiles) return;
+        const int m_blk = la_tile / p.num_n_blocks;
+        const int n_blk = la_tile - m_blk * p.num_n_blocks;
+        const int col = n_blk * p.block_n + la_c * 16;
+        uint8_t* b = epi + (gi & (kEpiBufs - 1)) * buf_bytes;
+        mbar_expect_tx(&res_full[gi & (kEpiBufs - 1)], chunk_bytes);
+        tma_load_2d(b, &tmR_hi, &res_full[gi & (kEpiBufs - 1)], col, m_blk * kBlockM);
+        if (SPLIT && p.res_lo != nullptr)
+          tma_load_2d(b + kEpiPlaneBytes, &tmR_lo, &res_full[gi & (kEpiBufs - 1)], col, m_blk * kBlockM);
+        if (++la_c == nch) {
+          la_c = 0;
+          la_tile += gridDim.x;
+        }
+      };
+      if (elected && has_res) {
+        issue_res(0);
+        issue_res(1);
       }
-      mbar_wait(&tmem_full[as], aphase);
-      tc_fence_after();
-      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * acc_stage_cols;
-      for (int c = 0; c < p.block_n; c += 16) {
-        uint32_t a0[16], a1[16];
-        tmem_ld_32x32b_x16(tacc + c, a0);
-        if (SPLIT) tmem_ld_32x32b_x16(tacc + 128 + c, a1);
-        tmem_ld_wait();
-        epilogue_chunk16<SPLIT>(p, a0, a1, opix, rpix, n0 + c, valid);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_blocks;
+        const int n_blk = tile - m_blk * p.num_n_blocks;
+        const int n0 = n_blk * p.block_n;
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * acc_stage_cols;
+        for (int c = 0; c < nch; ++c, ++g) {
+          const uint32_t j = g & (kEpiBufs - 1);
+          uint8_t* buf = epi + j * buf_bytes;
+          uint32_t a0[16], a1[16];
+          tmem_ld_32x32b_x16(tacc + c * 16, a0);
+          if (SPLIT) tmem_ld_32x32b_x16(tacc + 128 + c * 16, a1);
+          if (has_res) {
+            mbar_wait(&res_full[j], (rph >> j) & 1u);
+            rph ^= 1u << j;
+          }
+          tmem_ld_wait();
+          epilogue_chunk16_smem<SPLIT>(p, a0, a1, buf, row, n0 + c * 16, has_res);
+          fence_proxy_async();
+          if (elected && g >= 1) bulk_wait_read<1>();     // store(g-2) done reading -> buffer (g+2)&3 is free
+          named_bar_sync(1, 128);
+          if (elected) {
+            tma_store_2d(&tmO_hi, buf, n0 + c * 16, m_blk * kBlockM);
+            if (SPLIT && p.out_lo != nullptr) tma_store_2d(&tmO_lo, buf + kEpiPlaneBytes, n0 + c * 16, m_blk * kBlockM);
+            bulk_commit();
+            if (has_res) issue_res(g + 2);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
-      if (++as == 2) {
-        as = 0;
-        aphase ^= 1;
+      if (elected) bulk_wait_read<0>();
+    } else {
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_blocks;
+        const int n_blk = tile - m_blk * p.num_n_blocks;
+        const int m = m_blk * kBlockM + row;
+        const int n0 = n_blk * p.block_n;
+        const bool valid = m < p.M;
+        size_t opix = 0, rpix = 0;
+        if (valid) {
+          const int img = m / p.HoWo;
+          const int rem = m - img * p.HoWo;
+          const int pp = rem / p.Wo + p.off_h;
+          const int qq = rem - (rem / p.Wo) * p.Wo + p.off_w;
+          opix = (static_cast<size_t>(img) * p.out_H + pp) * p.out_W + qq;
+          rpix = (static_cast<size_t>(img) * p.res_H + (pp >> p.res_shift)) * p.res_W + (qq >> p.res_shift);
+        }
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * acc_stage_cols;
+        for (int c = 0; c < p.block_n; c += 16) {
+          uint32_t a0[16], a1[16];
+          tmem_ld_32x32b_x16(tacc + c, a0);
+          if (SPLIT) tmem_ld_32x32b_x16(tacc + 128 + c, a1);
+          tmem_ld_wait();
+          epilogue_chunk16<SPLIT>(p, a0, a1, opix, rpix, n0 + c, valid);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
       }
     }
   }
@@ -350,13 +506,13 @@ void small_tensor_fixup(CUtensorMap* m, size_t bytes) {
 }
 
 int encode_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
-              uint32_t box_inner, uint32_t box_outer) {
+              uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed: " + std::to_string(static_cast<int>(r)));
@@ -369,7 +525,7 @@ int encode_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, 
 }  // namespace
 
 struct ConvPlan {
-  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmO_hi, tmO_lo, tmR_hi, tmR_lo;
   ConvTcParams p;
   bool split;
   int grid;
@@ -430,9 +586,11 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   p.idesc = make_idesc_f16(kBlockM, p.block_n);
   p.b_bytes = static_cast<uint32_t>(p.block_n) * kBlockK * 2;
   p.stage_bytes = (kABytes + p.b_bytes) * (split ? 2 : 1);
-  p.num_stages = kSmemBudget / static_cast<int>(p.stage_bytes);
+  const int epi_bytes = kEpiBufs * 2 * kEpiPlaneBytes;   // 32 KB staging ring (always reserved)
+  p.num_stages = (kSmemBudget + 24 * 1024 - epi_bytes) / static_cast<int>(p.stage_bytes);
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   B2_CHECK(p.num_stages >= 2, "conv_tc: tile too large for shared memory");
+  p.epi_off = static_cast<uint32_t>(p.num_stages) * p.stage_bytes;
   p.out_hi = io.out_hi;
   p.out_lo = io.out_lo;
   p.out_f32 = io.out_f32;
@@ -453,7 +611,12 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   p.relu = d.relu;
   pl->split = split;
   pl->grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  pl->smem_bytes = static_cast<size_t>(p.num_stages) * p.stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  pl->smem_bytes = static_cast<size_t>(p.num_stages) * p.stage_bytes + epi_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  // TMA-staged epilogue: fp16 plane output with a 1:1 row mapping (no placement offset, no shifted residual)
+  const bool one_to_one = d.off_h == 0 && d.off_w == 0 && d.out_H == Ho && d.out_W == Wo;
+  const bool res_ok = io.res_hi == nullptr || (d.res_shift == 0 && d.res_H == d.out_H && d.res_W == d.out_W);
+  p.epi_mode = (io.out_f32 == nullptr && one_to_one && res_ok && d.force_epi_mode != 0) ? 1 : 0;
+  if (getenv("B2_EPI_DIRECT") != nullptr) p.epi_mode = 0;   // test hook: exercise the per-thread epilogue
 
   const int in_ld = d.in_ld > 0 ? d.in_ld : d.Cin;
   const bool plain = (d.R == 1 && d.S == 1 && d.stride == 1 && d.pad_t == 0 && d.pad_b == 0 && d.pad_l == 0 &&
@@ -500,6 +663,29 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
     pl->tmA_lo = pl->tmA_hi;
     pl->tmB_lo = pl->tmB_hi;
   }
+  pl->tmO_hi = pl->tmO_lo = pl->tmR_hi = pl->tmR_lo = pl->tmB_hi;   // valid placeholders for the direct mode
+  if (p.epi_mode == 1) {
+    const uint64_t rows = static_cast<uint64_t>(p.M);
+    if (encode_2d(&pl->tmO_hi, io.out_hi, w.Cout_pad, rows, static_cast<uint64_t>(d.ldc) * 2, 16, kBlockM,
+                  CU_TENSOR_MAP_SWIZZLE_32B))
+      return -1;
+    pl->tmO_lo = pl->tmO_hi;
+    if (split && io.out_lo &&
+        encode_2d(&pl->tmO_lo, io.out_lo, w.Cout_pad, rows, static_cast<uint64_t>(d.ldc) * 2, 16, kBlockM,
+                  CU_TENSOR_MAP_SWIZZLE_32B))
+      return -1;
+    pl->tmR_hi = pl->tmR_lo = pl->tmO_hi;
+    if (io.res_hi) {
+      if (encode_2d(&pl->tmR_hi, io.res_hi, w.Cout_pad, rows, static_cast<uint64_t>(d.ldr) * 2, 16, kBlockM,
+                    CU_TENSOR_MAP_SWIZZLE_32B))
+        return -1;
+      pl->tmR_lo = pl->tmR_hi;
+      if (split && io.res_lo &&
+          encode_2d(&pl->tmR_lo, io.res_lo, w.Cout_pad, rows, static_cast<uint64_t>(d.ldr) * 2, 16, kBlockM,
+                    CU_TENSOR_MAP_SWIZZLE_32B))
+        return -1;
+    }
+  }
   return 0;
 }
 
@@ -517,10 +703,12 @@ void conv_tc_plan_destroy(ConvPlan* p) { delete p; }
 int conv_tc_launch(const ConvPlan* pl, cudaStream_t stream) {
   if (pl->split)
     conv_tc_kernel<true><<<pl->grid, kThreads, pl->smem_bytes, stream>>>(pl->tmA_hi, pl->tmA_lo, pl->tmB_hi,
-                                                                          pl->tmB_lo, pl->p);
+                                                                          pl->tmB_lo, pl->tmO_hi, pl->tmO_lo,
+                                                                          pl->tmR_hi, pl->tmR_lo, pl->p);
   else
     conv_tc_kernel<false><<<pl->grid, kThreads, pl->smem_bytes, stream>>>(pl->tmA_hi, pl->tmA_lo, pl->tmB_hi,
-                                                                           pl->tmB_lo, pl->p);
+                                                                           pl->tmB_lo, pl->tmO_hi, pl->tmO_lo,
+                                                                           pl->tmR_hi, pl->tmR_lo, pl->p);
   B2_CUDA(cudaGetLastError());
   return 0;
 }

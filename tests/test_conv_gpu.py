@@ -89,3 +89,26 @@ def test_tensor_core_kernel_vs_cuda_core_kernel_same_operands(name):
     a = engine.op_conv2d(x, w, bias, res, impl="tcgen05", **kw)
     b = engine.op_conv2d(x, w, bias, res, impl="simt", **kw)
     assert np.abs(a - b).max() <= 5e-6 * np.abs(ref).max()
+
+
+def test_direct_epilogue_path_equals_tma_staged_epilogue():
+    """Both epilogue implementations (per-thread global access vs TMA-staged shared memory) give the same bits."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, sys; sys.path.insert(0, %r)\n"
+        "from object_detection_tracking_b200 import engine\n"
+        "rng = np.random.default_rng(0)\n"
+        "x = rng.standard_normal((2, 20, 28, 64)).astype(np.float32)\n"
+        "w = (rng.standard_normal((3, 3, 64, 128)) / 24).astype(np.float32)\n"
+        "b = rng.standard_normal(128).astype(np.float32)\n"
+        "r = rng.standard_normal((2, 20, 28, 128)).astype(np.float32)\n"
+        "o = engine.op_conv2d(x, w, b, r, pad=(1, 1, 1, 1), relu=True, split=True)\n"
+        "np.save(sys.argv[1], o)\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for i, env in enumerate([{}, {"B2_EPI_DIRECT": "1"}]):
+        path = "/tmp/b2_epi_%d.npy" % i
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=dict(os.environ, **env), timeout=300)
+        outs.append(np.load(path))
+    np.testing.assert_array_equal(outs[0], outs[1])
