@@ -80,6 +80,22 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
+def usable_cores():
+    """Host cores this process may actually use: affinity mask capped by the cgroup CPU quota
+    (os.cpu_count() reports the whole machine and oversubscribes a quota-limited container)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_oracle_fps(n_frames, threads):
     """Times the CPU oracle (the port of the reference's TF graph) on `n_frames` 720x1280 frames."""
     import torch
@@ -100,7 +116,7 @@ def cpu_oracle_fps(n_frames, threads):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = min(usable_cores(), 32)   # the conv stack stops scaling (and oversubscribes) beyond ~32 threads
     frames_per_step = 1
     import torch
     torch.set_num_threads(threads)
@@ -207,13 +223,10 @@ def main():
     dt_e2e = time.perf_counter() - t1
     barrier()
 
-    times = torch.tensor([dt, dt_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dt, dt_e2e = float(times[0]), float(times[1])
-    frames_total = args.steps * BATCH * world
-    value = frames_total / dt
-    e2e_value = frames_total / dt_e2e
+    from object_detection_tracking_b200 import replicas
+    dt, dt_e2e = replicas.max_over_ranks([dt, dt_e2e], device="cuda")     # slowest rank bounds the job
+    value = replicas.aggregate_fps(args.steps * BATCH, dt, world)
+    e2e_value = replicas.aggregate_fps(args.steps * BATCH, dt_e2e, world)
     h2d = host[0].numel() * 4
     d2h = sum(v.numel() * v.element_size() for v in outs.values())
 
@@ -238,7 +251,7 @@ def main():
                 json.dump({"precision": args.precision, "batch": BATCH, "steps": prof}, f, indent=1)
         cpu = None
         if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = min(usable_cores(), 32)
             fps, secs = cpu_oracle_fps(args.cpu_frames, threads)
             cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                    "sample": "%d frames 720x1280 (batch 1) through the CPU oracle in %.1f s" % (args.cpu_frames, secs)}
