@@ -221,7 +221,14 @@ __device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, con
   }
 }
 
-template <bool SPLIT>
+// ACC (split precision only): the tensor core adds into its fp32 accumulator with truncation (round
+// toward zero), a bias that grows with the number of accumulation steps (K/16) and compounds through 100+
+// layers.  With ACC the hi*hi accumulator is restarted every kAccChunkKb K-blocks in alternating TMEM
+// buffers and the epilogue warps sum the chunk results in registers with round-to-nearest fp32 adds
+// (overlapped with the MMAs of the next chunk), which brings the result to CUDA-core fp32 accuracy.
+constexpr int kAccChunkKb = 4;   // 4 K-blocks = 256 K-elements = 16 truncating accumulations per restart
+
+template <bool SPLIT, bool ACC>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -238,7 +245,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* tmem_full = bars + 2 * kMaxStages;
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;
   uint64_t* res_full = bars + 2 * kMaxStages + 4;                       // [kEpiBufs]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4 + kEpiBufs);
+  uint64_t* c_full = bars + 2 * kMaxStages + 4 + kEpiBufs;              // [2] ACC chunk accumulator ready
+  uint64_t* c_empty = c_full + 2;                                       // [2] ACC chunk accumulator drained
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(c_empty + 2);
   uint8_t* epi = tiles + p.epi_off;
 
   const int warp = threadIdx.x >> 5;
@@ -262,6 +271,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_init(&tmem_empty[i], 4);   // one arrive per epilogue warp
     }
     for (int i = 0; i < kEpiBufs; ++i) mbar_init(&res_full[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&c_full[i], 1);
+      mbar_init(&c_empty[i], 4);
+    }
     fence_mbar_init();
     fence_proxy_async();
   }
@@ -332,12 +345,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
+      uint32_t qg = 0;     // ACC: running chunk counter -> chunk accumulator qg & 1
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t acc0 = tmem_base + as * acc_stage_cols;
-        const uint32_t acc1 = acc0 + 128;
+        // plain: acc0 at as*256, acc1 at as*256+128.  ACC: acc0 chunk buffers at 0 / 128, acc1 at 256 + as*128.
+        uint32_t acc0 = tmem_base + as * acc_stage_cols;
+        const uint32_t acc1 = ACC ? tmem_base + 256 + as * 128 : acc0 + 128;
+        int kq = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
+          if (ACC && kq == 0) {
+            const uint32_t cbuf = qg & 1;
+            mbar_wait(&c_empty[cbuf], ((qg >> 1) & 1) ^ 1);
+            acc0 = tmem_base + cbuf * 128;
+          }
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(tiles + static_cast<size_t>(stage) * p.stage_bytes);
@@ -347,7 +368,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const uint64_t a_hi = make_smem_desc_sw128(st + koff);
             const uint64_t b_hi = make_smem_desc_sw128(st + b_hi_off + koff);
             const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
-            umma_f16(acc0, a_hi, b_hi, p.idesc, first);
+            umma_f16(acc0, a_hi, b_hi, p.idesc, ACC ? ((kq > 0 || k > 0) ? 1u : 0u) : first);
             if (SPLIT) {
               const uint64_t a_lo = make_smem_desc_sw128(st + a_lo_off + koff);
               const uint64_t b_lo = make_smem_desc_sw128(st + b_lo_off + koff);
@@ -356,6 +377,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
           }
           umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
+          if (ACC) {
+            if (++kq == kAccChunkKb || kb == p.num_kb - 1) {
+              umma_commit(&c_full[qg & 1]);   // chunk accumulator complete -> epilogue sums it
+              ++qg;
+              kq = 0;
+            }
+          }
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1;
@@ -374,6 +402,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int row = ew * 32 + lane;
     int as = 0;
     uint32_t aphase = 0;
+    uint32_t qe = 0;     // ACC: running chunk counter (mirrors the MMA issuer's)
     if (p.epi_mode == 1) {
       // ---- TMA-staged: residual chunk arrives in a swizzled smem buffer (TMA load, issued two chunks
       // ahead, also across tile boundaries), the result overwrites it in place and leaves by TMA store.
@@ -409,15 +438,56 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int m_blk = tile / p.num_n_blocks;
         const int n_blk = tile - m_blk * p.num_n_blocks;
         const int n0 = n_blk * p.block_n;
+        float sums[ACC ? 128 : 1];
+        if (ACC) {
+          const int nq = (p.num_kb + kAccChunkKb - 1) / kAccChunkKb;
+          const int nch_acc = p.block_n >> 4;
+          for (int q = 0; q < nq; ++q, ++qe) {
+            const uint32_t cbuf = qe & 1;
+            mbar_wait(&c_full[cbuf], (qe >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tsrc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + cbuf * 128;
+#pragma unroll
+            for (int cc = 0; cc < 8; cc += 2) {
+              if (cc < nch_acc) {
+                uint32_t t0[16], t1[16];
+                tmem_ld_32x32b_x16(tsrc + cc * 16, t0);
+                if (cc + 1 < nch_acc) tmem_ld_32x32b_x16(tsrc + cc * 16 + 16, t1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  sums[(ACC ? cc : 0) * 16 + (ACC ? i : 0)] =
+                      q == 0 ? __uint_as_float(t0[i]) : __fadd_rn(sums[(ACC ? cc : 0) * 16 + (ACC ? i : 0)], __uint_as_float(t0[i]));
+                  if (cc + 1 < nch_acc)
+                    sums[(ACC ? cc + 1 : 0) * 16 + (ACC ? i : 0)] =
+                        q == 0 ? __uint_as_float(t1[i])
+                               : __fadd_rn(sums[(ACC ? cc + 1 : 0) * 16 + (ACC ? i : 0)], __uint_as_float(t1[i]));
+                }
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&c_empty[cbuf]);
+          }
+        }
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * acc_stage_cols;
-        for (int c = 0; c < nch; ++c, ++g) {
+        const uint32_t lane_off = static_cast<uint32_t>(ew * 32) << 16;
+        const uint32_t tacc = tmem_base + lane_off + as * acc_stage_cols;
+        const uint32_t tacc1 = ACC ? tmem_base + lane_off + 256 + as * 128 : tacc + 128;
+#pragma unroll
+        for (int c = 0; c < (ACC ? 8 : 16); ++c) {
+          if (c >= nch) continue;
           const uint32_t j = g & (kEpiBufs - 1);
           uint8_t* buf = epi + j * buf_bytes;
           uint32_t a0[16], a1[16];
-          tmem_ld_32x32b_x16(tacc + c * 16, a0);
-          if (SPLIT) tmem_ld_32x32b_x16(tacc + 128 + c * 16, a1);
+          if (ACC) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a0[i] = __float_as_uint(sums[(ACC ? c : 0) * 16 + (ACC ? i : 0)]);
+          } else {
+            tmem_ld_32x32b_x16(tacc + c * 16, a0);
+          }
+          if (SPLIT) tmem_ld_32x32b_x16(tacc1 + c * 16, a1);
           if (has_res) {
             mbar_wait(&res_full[j], (rph >> j) & 1u);
             rph ^= 1u << j;
@@ -433,6 +503,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             bulk_commit();
             if (has_res) issue_res(g + 2);
           }
+          ++g;
         }
         tc_fence_before();
         __syncwarp();
@@ -459,15 +530,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           opix = (static_cast<size_t>(img) * p.out_H + pp) * p.out_W + qq;
           rpix = (static_cast<size_t>(img) * p.res_H + (pp >> p.res_shift)) * p.res_W + (qq >> p.res_shift);
         }
+        float sums[ACC ? 128 : 1];
+        if (ACC) {
+          const int nq = (p.num_kb + kAccChunkKb - 1) / kAccChunkKb;
+          const int nch_acc = p.block_n >> 4;
+          for (int q = 0; q < nq; ++q, ++qe) {
+            const uint32_t cbuf = qe & 1;
+            mbar_wait(&c_full[cbuf], (qe >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tsrc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + cbuf * 128;
+#pragma unroll
+            for (int cc = 0; cc < 8; cc += 2) {
+              if (cc < nch_acc) {
+                uint32_t t0[16], t1[16];
+                tmem_ld_32x32b_x16(tsrc + cc * 16, t0);
+                if (cc + 1 < nch_acc) tmem_ld_32x32b_x16(tsrc + cc * 16 + 16, t1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  sums[(ACC ? cc : 0) * 16 + (ACC ? i : 0)] =
+                      q == 0 ? __uint_as_float(t0[i]) : __fadd_rn(sums[(ACC ? cc : 0) * 16 + (ACC ? i : 0)], __uint_as_float(t0[i]));
+                  if (cc + 1 < nch_acc)
+                    sums[(ACC ? cc + 1 : 0) * 16 + (ACC ? i : 0)] =
+                        q == 0 ? __uint_as_float(t1[i])
+                               : __fadd_rn(sums[(ACC ? cc + 1 : 0) * 16 + (ACC ? i : 0)], __uint_as_float(t1[i]));
+                }
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&c_empty[cbuf]);
+          }
+        }
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * acc_stage_cols;
-        for (int c = 0; c < p.block_n; c += 16) {
+        const uint32_t lane_off = static_cast<uint32_t>(ew * 32) << 16;
+        const uint32_t tacc = tmem_base + lane_off + as * acc_stage_cols;
+        const uint32_t tacc1 = ACC ? tmem_base + lane_off + 256 + as * 128 : tacc + 128;
+        const int nch = p.block_n >> 4;
+#pragma unroll
+        for (int c = 0; c < (ACC ? 8 : 16); ++c) {
+          if (c >= nch) continue;
           uint32_t a0[16], a1[16];
-          tmem_ld_32x32b_x16(tacc + c, a0);
-          if (SPLIT) tmem_ld_32x32b_x16(tacc + 128 + c, a1);
+          if (ACC) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a0[i] = __float_as_uint(sums[(ACC ? c : 0) * 16 + (ACC ? i : 0)]);
+          } else {
+            tmem_ld_32x32b_x16(tacc + c * 16, a0);
+          }
+          if (SPLIT) tmem_ld_32x32b_x16(tacc1 + c * 16, a1);
           tmem_ld_wait();
-          epilogue_chunk16<SPLIT>(p, a0, a1, opix, rpix, n0 + c, valid);
+          epilogue_chunk16<SPLIT>(p, a0, a1, opix, rpix, n0 + c * 16, valid);
         }
         tc_fence_before();
         __syncwarp();
@@ -528,6 +641,7 @@ struct ConvPlan {
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmO_hi, tmO_lo, tmR_hi, tmR_lo;
   ConvTcParams p;
   bool split;
+  bool acc;
   int grid;
   size_t smem_bytes;
 };
@@ -544,8 +658,9 @@ int conv_tc_init() {
   B2_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q));
   B2_CHECK(fn != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeIm2col not available");
   g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
-  B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   return 0;
 }
 
@@ -610,6 +725,8 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   p.res_shift = d.res_shift;
   p.relu = d.relu;
   pl->split = split;
+  // accurate accumulation: on by default in split precision when K spans more than one chunk
+  pl->acc = split && p.num_kb > kAccChunkKb && getenv("B2_NO_ACC") == nullptr;
   pl->grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   pl->smem_bytes = static_cast<size_t>(p.num_stages) * p.stage_bytes + epi_bytes + 1024 /*align*/ + 256 /*barriers*/;
   // TMA-staged epilogue: fp16 plane output with a 1:1 row mapping (no placement offset, no shifted residual)
@@ -701,14 +818,15 @@ ConvPlan* conv_tc_plan_create(const ConvDesc& d, const ConvWeights& w, const Con
 void conv_tc_plan_destroy(ConvPlan* p) { delete p; }
 
 int conv_tc_launch(const ConvPlan* pl, cudaStream_t stream) {
-  if (pl->split)
-    conv_tc_kernel<true><<<pl->grid, kThreads, pl->smem_bytes, stream>>>(pl->tmA_hi, pl->tmA_lo, pl->tmB_hi,
-                                                                          pl->tmB_lo, pl->tmO_hi, pl->tmO_lo,
-                                                                          pl->tmR_hi, pl->tmR_lo, pl->p);
+  if (pl->split && pl->acc)
+    conv_tc_kernel<true, true><<<pl->grid, kThreads, pl->smem_bytes, stream>>>(
+        pl->tmA_hi, pl->tmA_lo, pl->tmB_hi, pl->tmB_lo, pl->tmO_hi, pl->tmO_lo, pl->tmR_hi, pl->tmR_lo, pl->p);
+  else if (pl->split)
+    conv_tc_kernel<true, false><<<pl->grid, kThreads, pl->smem_bytes, stream>>>(
+        pl->tmA_hi, pl->tmA_lo, pl->tmB_hi, pl->tmB_lo, pl->tmO_hi, pl->tmO_lo, pl->tmR_hi, pl->tmR_lo, pl->p);
   else
-    conv_tc_kernel<false><<<pl->grid, kThreads, pl->smem_bytes, stream>>>(pl->tmA_hi, pl->tmA_lo, pl->tmB_hi,
-                                                                           pl->tmB_lo, pl->tmO_hi, pl->tmO_lo,
-                                                                           pl->tmR_hi, pl->tmR_lo, pl->p);
+    conv_tc_kernel<false, false><<<pl->grid, kThreads, pl->smem_bytes, stream>>>(
+        pl->tmA_hi, pl->tmA_lo, pl->tmB_hi, pl->tmB_lo, pl->tmO_hi, pl->tmO_lo, pl->tmR_hi, pl->tmR_lo, pl->p);
   B2_CUDA(cudaGetLastError());
   return 0;
 }

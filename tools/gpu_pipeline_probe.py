@@ -36,7 +36,10 @@ def main():
         o = frcnn.forward(cfg, Wt, frames[b])
         for i in range(4):
             g = det.get_stage("c%d" % (i + 2))[b].transpose(2, 0, 1)
-            print("b%d c%d rel %.3e" % (b, i + 2, rel(g, o["c2345"][i])))
+            e = (g.astype(np.float64) - o["c2345"][i]) / np.abs(o["c2345"][i]).max()
+            print("b%d c%d rel %.3e  signed-mean %.2e rms %.2e  (|gpu|-|ref|)/|ref| mean %.2e" % (
+                b, i + 2, rel(g, o["c2345"][i]), e.mean(), np.sqrt((e ** 2).mean()),
+                ((np.abs(g) - np.abs(o["c2345"][i])).sum() / np.abs(o["c2345"][i]).sum())))
         for i in range(5):
             g = det.get_stage("p%d" % (i + 2))[b].transpose(2, 0, 1)
             ref = o["p23456"][i]
