@@ -97,3 +97,20 @@ def test_oracle_forward_small_is_deterministic_and_shaped():
     np.testing.assert_array_equal(a["final_boxes"], b["final_boxes"])
     assert np.all(np.diff(a["final_probs"]) <= 0)
     assert a["final_boxes"][:, [0, 2]].max() <= 160 and a["final_boxes"][:, [1, 3]].max() <= 96
+
+
+def _golden_frames(golden_dir):
+    g = np.load(os.path.join(golden_dir, "deepsort_tracker.npz"))
+    n = len([k for k in g.files if k.startswith("frame")])
+    return [g["frame%d" % i] for i in range(n)], g["results"]
+
+
+def test_deepsort_restatement_reproduces_reference_tracker_run(golden_dir):
+    """oracle/deepsort.py vs the reference's Tracker (golden run): identical ids, identical boxes."""
+    from oracle import deepsort
+    frames, expect = _golden_frames(golden_dir)
+    got = deepsort.run_sequence(frames, nn_matching.NearestNeighborDistanceMetric("cosine", 0.5, 5))
+    assert got.shape == expect.shape
+    np.testing.assert_array_equal(got[:, :2], expect[:, :2])           # frame, track id: bit-exact
+    np.testing.assert_allclose(got[:, 2:], expect[:, 2:], rtol=0, atol=1e-9)
+    assert len(set(expect[:, 1].tolist())) >= 5                         # the fixture really tracks several objects

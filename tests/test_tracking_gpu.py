@@ -51,3 +51,17 @@ def test_large_gallery_many_tiles():
     cost = cosine_cost(gal, seg, dets)
     ref = np.stack([nn_matching.nn_cosine_distance(gal[seg[t]:seg[t + 1]], dets) for t in range(T)])
     assert np.abs(cost - ref).max() < 2e-6
+
+
+def test_track_ids_with_gpu_metric_equal_reference_run(golden_dir):
+    """The whole association loop with the GPU appearance metric reproduces the reference tracker's
+    ids bit-exactly and its boxes to 1e-6 on the golden sequence (ids depend on thresholded costs)."""
+    from object_detection_tracking_b200.tracking import GpuNearestNeighborDistanceMetric
+    from oracle import deepsort
+    g = np.load(os.path.join(golden_dir, "deepsort_tracker.npz"))
+    n = len([k for k in g.files if k.startswith("frame")])
+    frames = [g["frame%d" % i] for i in range(n)]
+    got = deepsort.run_sequence(frames, GpuNearestNeighborDistanceMetric("cosine", 0.5, 5))
+    assert got.shape == g["results"].shape
+    np.testing.assert_array_equal(got[:, :2], g["results"][:, :2])
+    assert np.abs(got[:, 2:] - g["results"][:, 2:]).max() < 1e-6
