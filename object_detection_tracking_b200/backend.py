@@ -83,7 +83,7 @@ class Mask_RCNN_FPN:
             if self._weights is None:
                 raise RuntimeError("model has no weights: call set_weights()/load_npz() first")
             det = Detector(self.config, B, H, W, device=self.gpuid, input_dtype=self.input_dtype,
-                           precision=self.precision)
+                           precision=self.precision, multi_semantics=self.is_multi)
             det.load_weights(self._weights)
             self._detectors[key] = det
         return det
@@ -132,7 +132,8 @@ class Mask_RCNN_FPN:
 
 
 class Mask_RCNN_FPN_multi(Mask_RCNN_FPN):
-    """Fixed-batch model object (reference: models.py:1969-3487)."""
+    """Fixed-batch model object (reference: models.py:1969-3487): post-processing follows the batch graph
+    (combined_non_max_suppression semantics, `multi_semantics` in the C ABI)."""
 
     is_multi = True
 

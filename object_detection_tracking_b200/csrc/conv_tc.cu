@@ -58,6 +58,7 @@ struct ConvTcParams {
   const __half* res_lo;
   int ldr, res_H, res_W, res_shift;
   int relu;
+  int acc_kb;        // ACC: K-blocks per tensor-core accumulation chunk
   int epi_mode;      // 0 = direct global loads/stores per thread, 1 = TMA-staged (residual in, result out)
   uint32_t epi_off;  // byte offset of the epilogue staging buffers inside the tile area
 };
@@ -226,7 +227,7 @@ __device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, con
 // layers.  With ACC the hi*hi accumulator is restarted every kAccChunkKb K-blocks in alternating TMEM
 // buffers and the epilogue warps sum the chunk results in registers with round-to-nearest fp32 adds
 // (overlapped with the MMAs of the next chunk), which brings the result to CUDA-core fp32 accuracy.
-constexpr int kAccChunkKb = 4;   // 4 K-blocks = 256 K-elements = 16 truncating accumulations per restart
+constexpr int kAccChunkKb = 4;   // default: 4 K-blocks = 256 K-elements = 16 truncating accumulations per restart
 
 template <bool SPLIT, bool ACC>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -378,7 +379,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
           umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
           if (ACC) {
-            if (++kq == kAccChunkKb || kb == p.num_kb - 1) {
+            if (++kq == p.acc_kb || kb == p.num_kb - 1) {
               umma_commit(&c_full[qg & 1]);   // chunk accumulator complete -> epilogue sums it
               ++qg;
               kq = 0;
@@ -440,7 +441,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int n0 = n_blk * p.block_n;
         float sums[ACC ? 128 : 1];
         if (ACC) {
-          const int nq = (p.num_kb + kAccChunkKb - 1) / kAccChunkKb;
+          const int nq = (p.num_kb + p.acc_kb - 1) / p.acc_kb;
           const int nch_acc = p.block_n >> 4;
           for (int q = 0; q < nq; ++q, ++qe) {
             const uint32_t cbuf = qe & 1;
@@ -532,7 +533,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         float sums[ACC ? 128 : 1];
         if (ACC) {
-          const int nq = (p.num_kb + kAccChunkKb - 1) / kAccChunkKb;
+          const int nq = (p.num_kb + p.acc_kb - 1) / p.acc_kb;
           const int nch_acc = p.block_n >> 4;
           for (int q = 0; q < nq; ++q, ++qe) {
             const uint32_t cbuf = qe & 1;
@@ -726,7 +727,9 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   p.relu = d.relu;
   pl->split = split;
   // accurate accumulation: on by default in split precision when K spans more than one chunk
-  pl->acc = split && p.num_kb > kAccChunkKb && getenv("B2_NO_ACC") == nullptr;
+  p.acc_kb = kAccChunkKb;
+  if (const char* e = getenv("B2_ACC_KB")) p.acc_kb = atoi(e) > 0 ? atoi(e) : kAccChunkKb;
+  pl->acc = split && p.num_kb > p.acc_kb && getenv("B2_NO_ACC") == nullptr;
   pl->grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   pl->smem_bytes = static_cast<size_t>(p.num_stages) * p.stage_bytes + epi_bytes + 1024 /*align*/ + 256 /*barriers*/;
   // TMA-staged epilogue: fp16 plane output with a 1:1 row mapping (no placement offset, no shifted residual)

@@ -365,6 +365,7 @@ int build_plan(b2_ctx* c) {
     rp.decode_clip = static_cast<float>(dc);
   }
   rp.min_size = cfg.rpn_min_size;
+  rp.multi = cfg.multi_semantics;
   rp.nms_thr = cfg.rpn_nms_thres;
   rp.lvl_boxes = c->alloc<float>(static_cast<size_t>(B) * 5 * K * 4);
   rp.lvl_scores = c->alloc<float>(static_cast<size_t>(B) * 5 * K);
@@ -430,7 +431,9 @@ int build_plan(b2_ctx* c) {
   for (int i = 0; i < 4; ++i) hp.reg_w[i] = cfg.bbox_reg_weights[i];
   hp.decode_clip = static_cast<float>(log(1333.0 / 16.0));   // decode_bbox_target default (nn.py:1518)
   hp.img_h = static_cast<float>(H); hp.img_w = static_cast<float>(W);
-  hp.score_thresh = cfg.result_score_thres; hp.nms_thr = cfg.fastrcnn_nms_iou_thres;
+  // batch graph: combined_non_max_suppression is called without a score threshold (models.py:2959-2965)
+  hp.score_thresh = cfg.multi_semantics ? -INFINITY : cfg.result_score_thres;
+  hp.nms_thr = cfg.fastrcnn_nms_iou_thres;
   hp.max_per_class = R; hp.max_total = R;
   hp.probs = c->alloc<float>(static_cast<size_t>(M) * cfg.num_class);
   hp.dec_boxes = c->alloc<float>(static_cast<size_t>(M) * nc1 * 4);

@@ -21,6 +21,7 @@ struct RpnParams {
   float cell[5][3][4];      // cell anchors x1,y1,x2,y2 (generate_anchors.py semantics, before the +1)
   int B, topk;
   float img_h, img_w, decode_clip, min_size, nms_thr;
+  int multi;                // batch-graph semantics: no min-size filter, zero-padded merge, zero-area drop
   float* lvl_boxes;         // [B][5][topk][4]
   float* lvl_scores;        // [B][5][topk]
   int* lvl_count;           // [B][5]

@@ -150,7 +150,8 @@ __global__ void __launch_bounds__(1024, 1) rpn_level_kernel(const __grid_constan
     x2 = fminf(fmaxf(x2, 0.f), p.img_w);
     y2 = fminf(fmaxf(y2, 0.f), p.img_h);
     bx = make_float4(x1, y1, x2, y2);
-    valid = (__fsub_rn(x2, x1) > p.min_size) && (__fsub_rn(y2, y1) > p.min_size);
+    // single-image graph drops w/h <= rpn_min_size (nn.py:1375-1380); the batch graph does not (nn.py:1441-1455)
+    valid = p.multi ? true : ((__fsub_rn(x2, x1) > p.min_size) && (__fsub_rn(y2, y1) > p.min_size));
   }
   __syncthreads();   // keys fully consumed before boxes/scores are written (separate arrays, but keep order clear)
   const uint32_t vb = __ballot_sync(0xffffffffu, valid);
@@ -188,46 +189,67 @@ __global__ void __launch_bounds__(1024, 1) rpn_level_kernel(const __grid_constan
 
 // Merge: concat the 5 levels (level order, selection order inside a level), take top-k by score
 // (ties -> lower concat position), canonical order = score descending.  models.py:425-434.
+// Batch graph (models.py:2490-2520): the levels are zero-padded to topk each (box 0, score 0) before the
+// top-k -- so padding outranks negative logits -- and zero-area boxes are dropped afterwards.
 __global__ void __launch_bounds__(1024, 1) rpn_merge_kernel(const __grid_constant__ RpnParams p, int KP2) {
   extern __shared__ __align__(16) uint8_t sm[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(sm);   // [KP2]
-  const int b = blockIdx.x, tid = threadIdx.x;
-  __shared__ int base[6];
-  if (tid == 0) {
-    int a = 0;
-    for (int l = 0; l < 5; ++l) {
-      base[l] = a;
-      a += p.lvl_count[b * 5 + l];
-    }
-    base[5] = a;
-  }
-  __syncthreads();
-  const int total = base[5];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int cnt[5];
+  __shared__ int wsum[32];
+  __shared__ int s_total;
+  if (tid < 5) cnt[tid] = p.lvl_count[b * 5 + tid];
   for (int i = tid; i < KP2; i += blockDim.x) keys[i] = ~0ull;
   __syncthreads();
+  int total = 0;
   for (int l = 0; l < 5; ++l) {
-    const int cnt = base[l + 1] - base[l];
     const float* s = p.lvl_scores + (static_cast<size_t>(b) * 5 + l) * p.topk;
-    for (int j = tid; j < cnt; j += blockDim.x) keys[base[l] + j] = desc_key(s[j], static_cast<uint32_t>(base[l] + j));
+    const int n = p.multi ? p.topk : cnt[l];
+    for (int j = tid; j < n; j += blockDim.x)
+      keys[l * p.topk + j] = desc_key(j < cnt[l] ? s[j] : 0.f, static_cast<uint32_t>(l * p.topk + j));
+    total += n;
   }
   block_bitonic_sort(keys, KP2);
   const int K = min(total, p.topk);
+  // gather the selected entries (one per thread), then order-preserving compaction of the non-degenerate ones
+  float4 bx = make_float4(0, 0, 0, 0);
+  float sc = 0.f;
+  bool keep = false;
+  if (tid < K) {
+    const int pos = static_cast<int>(keys[tid] & 0xffffffffu);
+    const int l = pos / p.topk, j = pos - l * p.topk;
+    if (j < cnt[l]) {
+      const size_t src = (static_cast<size_t>(b) * 5 + l) * p.topk + j;
+      bx = reinterpret_cast<const float4*>(p.lvl_boxes)[src];
+      sc = p.lvl_scores[src];
+    }
+    keep = p.multi ? (__fmul_rn(__fsub_rn(bx.w, bx.y), __fsub_rn(bx.z, bx.x)) > 0.f) : true;
+  }
+  const uint32_t vb = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) wsum[warp] = __popc(vb);
+  __syncthreads();
+  if (tid == 0) {
+    int a = 0;
+    for (int w = 0; w < 32; ++w) {
+      const int t = wsum[w];
+      wsum[w] = a;
+      a += t;
+    }
+    s_total = a;
+  }
+  __syncthreads();
   float4* ob = reinterpret_cast<float4*>(p.prop_boxes) + static_cast<size_t>(b) * p.topk;
   float* os = p.prop_scores + static_cast<size_t>(b) * p.topk;
-  for (int j = tid; j < p.topk; j += blockDim.x) {
-    if (j < K) {
-      const int pos = static_cast<int>(keys[j] & 0xffffffffu);
-      int l = 0;
-      while (pos >= base[l + 1]) ++l;
-      const size_t src = (static_cast<size_t>(b) * 5 + l) * p.topk + (pos - base[l]);
-      ob[j] = reinterpret_cast<const float4*>(p.lvl_boxes)[src];
-      os[j] = p.lvl_scores[src];
-    } else {
-      ob[j] = make_float4(0, 0, 0, 0);
-      os[j] = 0.f;
-    }
+  if (keep) {
+    const int o = wsum[warp] + __popc(vb & ((1u << lane) - 1));
+    ob[o] = bx;
+    os[o] = sc;
   }
-  if (tid == 0) p.prop_count[b] = K;
+  for (int j = s_total + tid; j < p.topk; j += blockDim.x) {
+    ob[j] = make_float4(0, 0, 0, 0);
+    os[j] = 0.f;
+  }
+  if (tid == 0) p.prop_count[b] = s_total;
 }
 
 int next_pow2(int v) {

@@ -305,3 +305,83 @@ def forward(cfg, W, img_hwc_f32: np.ndarray, stages: bool = True) -> dict:
                    roi_feat=roi, roi_level=roi_lvl, cls_logits=cls_logits, box_logits=box_logits,
                    hidden=hidden, decoded_boxes=dec, probs=probs, pred_indices=pred)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Batch graph: Mask_RCNN_FPN_multi (models.py:1969-3487).  Same layers; the post-processing differs
+# because it is built on tf.image.combined_non_max_suppression (zero-padded, no score threshold).
+
+def combined_nms_single_class(boxes, scores, max_out, iou_thr):
+    """tf.image.combined_non_max_suppression with q = 1, one class, score_threshold = -inf,
+    pad_per_class=False, clip_boxes=False (call site nn.py:1468-1474): hard NMS, zero-padded outputs.
+    Returns (boxes [max_out,4], scores [max_out], valid)."""
+    keep = tf_ops.non_max_suppression(boxes[:, [1, 0, 3, 2]], scores, max_out, iou_thr)
+    ob = np.zeros((max_out, 4), np.float32); os_ = np.zeros((max_out,), np.float32)
+    ob[:len(keep)] = boxes[keep]; os_[:len(keep)] = scores[keep]
+    return ob, os_, len(keep)
+
+
+def forward_multi(cfg, W, imgs, stages=False):
+    """Inference branch of Mask_RCNN_FPN_multi.build_forward (models.py:2058-2409) for a batch of equally
+    sized frames.  Returns zero-padded [B,100,...] outputs + valid counts + concatenated box features."""
+    B = len(imgs)
+    K, R = cfg.rpn_test_post_nms_topk, cfg.result_per_im
+    nc1 = cfg.num_class - 1
+    out_boxes = np.zeros((B, R, 4), np.float32); out_probs = np.zeros((B, R), np.float32)
+    out_labels = np.zeros((B, R), np.float32); valid = np.zeros((B,), np.int32)
+    feats_all, per_image = [], []
+    na = len(cfg.anchor_ratios)
+    for b in range(B):
+        x = preprocess(imgs[b])
+        H, W_ = x.shape[2:]
+        hw = (H, W_)
+        with torch.no_grad():
+            p23456 = fpn(backbone(x, W, cfg), W)
+        for i, s in enumerate(cfg.anchor_strides):
+            if i < 3:
+                p23456[i] = p23456[i][:, :, :int(math.ceil(H / float(s))), :int(math.ceil(W_ / float(s)))]
+        lvl_b, lvl_s = [], []
+        for i, (s, size) in enumerate(zip(cfg.anchor_strides, cfg.anchor_sizes)):
+            with torch.no_grad():
+                cls, box = rpn_head(p23456[i], W, na)
+            fh, fw = cls.shape[:2]
+            anchors = get_all_anchors(s, [size], cfg.anchor_ratios, cfg.max_size)[:fh, :fw]
+            dec = decode_bbox_target(box, anchors, cfg.bbox_decode_clip).reshape(-1, 4)   # nn.py:1486-1514
+            sc, idx = tf_ops.top_k(cls.reshape(-1), min(K, cls.size))                      # nn.py:1431
+            bx = clip_boxes(dec[idx], hw)                                                  # no min-size filter (:1441-1455)
+            ob, os_, _ = combined_nms_single_class(bx, sc, K, cfg.rpn_proposal_nms_thres)
+            lvl_b.append(ob); lvl_s.append(os_)
+        cb = np.concatenate(lvl_b, 0); cs = np.concatenate(lvl_s, 0)                       # zero padded (models.py:2490-2496)
+        ps, ti = tf_ops.top_k(cs, min(cs.shape[0], K))
+        pb = cb[ti]
+        area = ((pb[:, 3] - pb[:, 1]) * (pb[:, 2] - pb[:, 0])).astype(np.float32)
+        keep = area > 0                                                                    # models.py:2516-2520
+        pb, ps = pb[keep], ps[keep]
+        fmaps = [p[0].numpy() for p in p23456[:4]]
+        roi, _ = multilevel_roi_align(fmaps, pb, 7, cfg.anchor_strides)
+        with torch.no_grad():
+            cls_logits, box_logits, _ = fastrcnn_head(roi, W, cfg)
+        rw = np.asarray(cfg.fastrcnn_bbox_reg_weights, dtype=np.float32)
+        dec = clip_boxes(decode_bbox_target((box_logits / rw).astype(np.float32), np.tile(pb[:, None, :], (1, nc1, 1))), hw)
+        probs = softmax(cls_logits)
+        # combined NMS over classes (models.py:2924-2976): per class hard NMS (<= R), no score threshold,
+        # merge, sort by score, keep R.  Canonical tie order: (class, selection order).
+        cand = []
+        for c in range(nc1):
+            keep = tf_ops.non_max_suppression(dec[:, c], probs[:, c + 1], R, cfg.fastrcnn_nms_iou_thres)
+            cand += [(c, int(k)) for k in keep]
+        sc = np.array([probs[k, c + 1] for c, k in cand], np.float32)
+        tp, ti = tf_ops.top_k(sc, min(R, len(cand)))
+        n = len(ti)
+        valid[b] = n
+        for j, t in enumerate(ti):
+            c, k = cand[t]
+            out_boxes[b, j] = dec[k, c]; out_probs[b, j] = probs[k, c + 1]; out_labels[b, j] = c + 1
+        bf, _ = multilevel_roi_align(fmaps, out_boxes[b, :n], 7, cfg.anchor_strides) if n else (np.zeros((0, 256, 7, 7), np.float32), None)
+        feats_all.append(bf)
+        per_image.append(dict(proposal_boxes=pb, proposal_scores=ps, probs=probs, decoded_boxes=dec))
+    res = dict(final_boxes=out_boxes, final_probs=out_probs, final_labels=out_labels, final_valid_indices=valid,
+               fpn_box_feat=np.concatenate(feats_all, 0))
+    if stages:
+        res["per_image"] = per_image
+    return res

@@ -191,3 +191,36 @@ def test_cuda_graph_replay_equals_eager_and_outputs_are_fresh(small):
     np.testing.assert_array_equal(o3["labels"], o1["labels"])
     np.testing.assert_array_equal(o3["boxes"], o1["boxes"])
     dg.close(); du.close()
+
+
+def test_batch_graph_semantics_match_oracle_multi():
+    """multi_semantics=1 (Mask_RCNN_FPN_multi: combined_non_max_suppression) vs oracle.forward_multi."""
+    from object_detection_tracking_b200.config import make_config
+    from object_detection_tracking_b200.engine import Detector
+    from object_detection_tracking_b200.synth import synth_frame, synth_weights
+    from oracle import frcnn
+    H, W, B = 192, 256, 2
+    cfg = make_config(resnet_num_block=(1, 1, 1, 1), max_size=W, short_edge_size=H, im_batch_size=B)
+    Wt = synth_weights(cfg, 21)
+    frames = np.stack([synth_frame(H, W, seed=s) for s in (8, 9)]).astype(np.float32)
+    det = Detector(cfg, B, H, W, precision="split", use_cuda_graph=False, multi_semantics=True)
+    det.load_weights(Wt)
+    out = det.detect_host(frames)
+    ref = frcnn.forward_multi(cfg, Wt, list(frames), stages=True)
+    np.testing.assert_array_equal(out["valid"], ref["final_valid_indices"])
+    K = cfg.rpn_test_post_nms_topk
+    for b in range(B):
+        # proposal set after the zero-padded merge + zero-area drop
+        pc = int(det.get_stage("proposal_count")[b].reshape(-1)[0])
+        assert pc == len(ref["per_image"][b]["proposal_scores"])
+        pb = det.get_stage("proposal_boxes")[b].reshape(K, 4)[:pc]
+        assert unmatched(pb, ref["per_image"][b]["proposal_boxes"], 1e-3) <= 1
+        r = int(out["valid"][b])
+        got = np.concatenate([out["labels"][b, :r, None] * 10.0, out["boxes"][b, :r], out["probs"][b, :r, None]], 1)
+        exp = np.concatenate([ref["final_labels"][b, :r, None] * 10.0, ref["final_boxes"][b, :r],
+                              ref["final_probs"][b, :r, None]], 1)
+        assert unmatched(got, exp, 1e-3) == 0 and unmatched(exp, got, 1e-3) == 0
+    # the single-image semantics differ on the same frames (score threshold / min-size / padding rules)
+    single = frcnn.forward(cfg, Wt, frames[0], stages=True)
+    assert len(single["proposal_scores"]) >= len(ref["per_image"][0]["proposal_scores"])
+    det.close()
