@@ -50,6 +50,8 @@ typedef struct b2_config {
   float rpn_min_size, rpn_nms_thres, fastrcnn_nms_iou_thres, result_score_thres;
   float anchor_strides[5], anchor_sizes[5], anchor_ratios[3];
   float bbox_reg_weights[4];
+  int32_t accum_chunk;        /* split precision: K-blocks (64 elements) the tensor core accumulates before the
+                                 partial sum is folded in with round-to-nearest; 0 = default (1), <0 = never */
   int32_t multi_semantics;    /* 1 = post-processing of Mask_RCNN_FPN_multi (combined_non_max_suppression:
                                  no RPN min-size filter, zero-padded level merge + zero-area drop, no score threshold) */
 } b2_config;

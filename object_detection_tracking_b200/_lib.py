@@ -22,7 +22,7 @@ class B2Config(ctypes.Structure):
         ("max_size", c_float), ("rpn_min_size", c_float), ("rpn_nms_thres", c_float),
         ("fastrcnn_nms_iou_thres", c_float), ("result_score_thres", c_float),
         ("anchor_strides", c_float * 5), ("anchor_sizes", c_float * 5), ("anchor_ratios", c_float * 3),
-        ("bbox_reg_weights", c_float * 4), ("multi_semantics", c_int32),
+        ("bbox_reg_weights", c_float * 4), ("accum_chunk", c_int32), ("multi_semantics", c_int32),
     ]
 
 
@@ -89,7 +89,8 @@ def ptr(a) -> c_void_p:
 
 
 def make_config(cfg, batch: int, height: int, width: int, input_dtype: str = "float32", precision: str = "split",
-                conv_impl: str = "tcgen05", use_cuda_graph: bool = True, multi_semantics: bool = False) -> B2Config:
+                conv_impl: str = "tcgen05", use_cuda_graph: bool = True, multi_semantics: bool = False,
+                accum_chunk: int = 0) -> B2Config:
     """Translate the reference-style namespace (config.py / obj_detect_tracking.py:236-389)."""
     c = B2Config()
     c.batch, c.height, c.width = int(batch), int(height), int(width)
@@ -119,4 +120,5 @@ def make_config(cfg, batch: int, height: int, width: int, input_dtype: str = "fl
     for i in range(4):
         c.bbox_reg_weights[i] = float(cfg.fastrcnn_bbox_reg_weights[i])
     c.multi_semantics = int(bool(multi_semantics))
+    c.accum_chunk = int(accum_chunk)
     return c

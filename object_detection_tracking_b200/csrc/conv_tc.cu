@@ -227,7 +227,7 @@ __device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, con
 // layers.  With ACC the hi*hi accumulator is restarted every kAccChunkKb K-blocks in alternating TMEM
 // buffers and the epilogue warps sum the chunk results in registers with round-to-nearest fp32 adds
 // (overlapped with the MMAs of the next chunk), which brings the result to CUDA-core fp32 accuracy.
-constexpr int kAccChunkKb = 4;   // default: 4 K-blocks = 256 K-elements = 16 truncating accumulations per restart
+constexpr int kAccChunkKb = 1;   // default: restart every K-block (64 K-elements = 4 truncating accumulations)
 
 template <bool SPLIT, bool ACC>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -727,9 +727,9 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   p.relu = d.relu;
   pl->split = split;
   // accurate accumulation: on by default in split precision when K spans more than one chunk
-  p.acc_kb = kAccChunkKb;
-  if (const char* e = getenv("B2_ACC_KB")) p.acc_kb = atoi(e) > 0 ? atoi(e) : kAccChunkKb;
-  pl->acc = split && p.num_kb > p.acc_kb && getenv("B2_NO_ACC") == nullptr;
+  p.acc_kb = d.acc_kb > 0 ? d.acc_kb : kAccChunkKb;
+  if (const char* e = getenv("B2_ACC_KB")) p.acc_kb = atoi(e) > 0 ? atoi(e) : kAccChunkKb;   // experiment hook
+  pl->acc = split && d.acc_kb >= 0 && p.num_kb > p.acc_kb && getenv("B2_NO_ACC") == nullptr;
   pl->grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   pl->smem_bytes = static_cast<size_t>(p.num_stages) * p.stage_bytes + epi_bytes + 1024 /*align*/ + 256 /*barriers*/;
   // TMA-staged epilogue: fp16 plane output with a 1:1 row mapping (no placement offset, no shifted residual)

@@ -171,6 +171,7 @@ Layer* add_conv(b2_ctx* c, int phase, const std::string& name, const Planes& in,
   d.pad_t = pt; d.pad_b = pb; d.pad_l = pl; d.pad_r = pr;
   d.Cout = Cout;
   d.relu = relu ? 1 : 0;
+  d.acc_kb = c->cfg.accum_chunk;
   d.off_h = off_h; d.off_w = off_w;
   if (out_f32) {
     d.out_H = d.Ho(); d.out_W = d.Wo(); d.ldc = ldc_f32;

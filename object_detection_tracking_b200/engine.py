@@ -14,7 +14,7 @@ from .config import normalize_config
 class Detector:
     def __init__(self, cfg, batch: int, height: int, width: int, device: int = 0, input_dtype: str = "float32",
                  precision: str = "split", conv_impl: str = "tcgen05", use_cuda_graph: bool = True,
-                 multi_semantics: bool = False):
+                 multi_semantics: bool = False, accum_chunk: int = 0):
         self.lib = _lib.load()
         self.cfg = normalize_config(cfg)
         self.batch, self.height, self.width = int(batch), int(height), int(width)
@@ -22,7 +22,7 @@ class Detector:
         self.input_dtype = input_dtype
         self.precision = precision
         self._c = _lib.make_config(self.cfg, batch, height, width, input_dtype, precision, conv_impl, use_cuda_graph,
-                                   multi_semantics)
+                                   multi_semantics, accum_chunk)
         self._ctx = c_void_p(0)
         _lib.check(self.lib.b2_create(ctypes.byref(self._ctx), self.device, ctypes.byref(self._c)), "b2_create")
         self.R = int(self.cfg.result_per_im)
