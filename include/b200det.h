@@ -101,6 +101,22 @@ int b2_step_info(b2_ctx* ctx, int idx, char* name, int name_cap, double* flops, 
 int b2_cosine_cost(int device, const float* gallery, const int32_t* seg_offsets, int T, const float* dets, int N,
                    int D, int precision, float* cost);
 
+/* ---- ReID embedding: torchreid FeatureExtractor (torchreid/feature_extractor.py:121-252) with osnet_x1_0
+ * (torchreid/models/osnet.py:522-534).  b2_reid_create fixes the crop batch; b2_reid_load_weights takes the
+ * model's state_dict (torch names, fp32); b2_reid_embed takes host RGB uint8 crops already resized to
+ * 256x128 ([n,256,128,3], n <= batch) and returns [n,512] fp32 (ToTensor + Normalize + OSNet eval forward). */
+typedef struct b2_reid b2_reid;
+int b2_reid_create(b2_reid** out, int device, int batch, int precision);
+void b2_reid_destroy(b2_reid* ctx);
+int b2_reid_load_weights(b2_reid* ctx, const char* const* names, const float* const* data, const int64_t* numel, int n);
+int b2_reid_embed(b2_reid* ctx, const uint8_t* crops_host, int n, float* feats_host);
+int b2_reid_num_launches(b2_reid* ctx);
+
+/* Distance matrix of torchreid/distance.py:6-80 on the tensor cores: a [na,D], b [nb,D] (host) -> out [na,nb].
+ * metric 0 = cosine (1 - a^.b^), 1 = squared euclidean (|a|^2 + |b|^2 - 2 a.b). */
+int b2_distance_matrix(int device, const float* a, int na, const float* b, int nb, int D, int metric, int precision,
+                       float* out);
+
 /* Single-op entry used by the kernel parity tests (host pointers, NHWC activations, HWIO kernel). */
 int b2_op_conv2d(int device, const float* x, const float* w, const float* bias, const float* res, int B, int H, int W,
                  int Cin, int R, int S, int Cout, int stride, int dil, int pad_t, int pad_b, int pad_l, int pad_r,

@@ -45,6 +45,12 @@ SYMBOLS = [
     ("b2_profile_steps", c_int, [c_void_p, c_int, POINTER(c_float), c_int, POINTER(c_int)]),
     ("b2_step_info", c_int, [c_void_p, c_int, ctypes.c_char_p, c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int)]),
     ("b2_cosine_cost", c_int, [c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    ("b2_reid_create", c_int, [POINTER(c_void_p), c_int, c_int, c_int]),
+    ("b2_reid_destroy", None, [c_void_p]),
+    ("b2_reid_load_weights", c_int, [c_void_p, POINTER(c_char_p), POINTER(c_void_p), POINTER(c_int64), c_int]),
+    ("b2_reid_embed", c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    ("b2_reid_num_launches", c_int, [c_void_p]),
+    ("b2_distance_matrix", c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     ("b2_op_conv2d", c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 18 + [c_void_p]),
 ]
 

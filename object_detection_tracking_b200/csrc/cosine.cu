@@ -41,7 +41,53 @@ __global__ void cosine_segmin_kernel(const float* __restrict__ dots, int ld, con
   cost[idx] = best;
 }
 
+// plain (un-normalised) rows -> (hi, lo) planes + squared norms
+__global__ void rows_to_planes_kernel(const float* __restrict__ src, int rows, int D, __half* __restrict__ hi,
+                                      __half* __restrict__ lo, int ld, float* __restrict__ sqnorm) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* x = src + static_cast<size_t>(row) * D;
+  float ss = 0.f;
+  for (int c = lane; c < ld; c += 32) {
+    const float v = c < D ? x[c] : 0.f;
+    ss = fmaf(v, v, ss);
+    const __half h = __float2half_rn(v);
+    hi[static_cast<size_t>(row) * ld + c] = h;
+    if (lo) lo[static_cast<size_t>(row) * ld + c] = __float2half_rn((v - __half2float(h)) * kLoScale);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) sqnorm[row] = ss;
+}
+
+// out[i][j] = metric 0: 1 - dots[i][j]   metric 1: na2[i] + nb2[j] - 2 dots[i][j]
+__global__ void distance_finish_kernel(const float* __restrict__ dots, int ld, int na, int nb, int metric,
+                                       const float* __restrict__ na2, const float* __restrict__ nb2,
+                                       float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= na * nb) return;
+  const int i = idx / nb, j = idx - i * nb;
+  const float d = dots[static_cast<size_t>(i) * ld + j];
+  out[idx] = metric == 0 ? __fsub_rn(1.f, d) : __fsub_rn(__fadd_rn(na2[i], nb2[j]), __fmul_rn(2.f, d));
+}
+
 }  // namespace
+
+int rows_to_planes(const float* src, int rows, int D, __half* hi, __half* lo, int ld, float* sqnorm, cudaStream_t s) {
+  if (rows <= 0) return 0;
+  rows_to_planes_kernel<<<(rows * 32 + 255) / 256, 256, 0, s>>>(src, rows, D, hi, lo, ld, sqnorm);
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int distance_finish(const float* dots, int ld, int na, int nb, int metric, const float* na2, const float* nb2, float* out,
+                    cudaStream_t s) {
+  if (na * nb <= 0) return 0;
+  distance_finish_kernel<<<(na * nb + 255) / 256, 256, 0, s>>>(dots, ld, na, nb, metric, na2, nb2, out);
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int cosine_normalize_rows(const float* src, int rows, int D, __half* hi, __half* lo, int ld, cudaStream_t s) {
   if (rows <= 0) return 0;

@@ -485,7 +485,7 @@ int run_step(b2_ctx* c, const b2_ctx::Step& s) {
       return conv_simt_launch(s.layer->d, s.layer->w, s.layer->io, c->split, st);
     case 1:
       return stem_pack_launch(c->img, cfg.input_dtype == 1, cfg.batch, cfg.height, cfg.width, c->stem_u.hi,
-                              c->stem_u.lo, c->stem_u.H, c->stem_u.W, st);
+                              c->stem_u.lo, c->stem_u.H, c->stem_u.W, 0, st);
     case 2:
       return maxpool_launch(c->c1.hi, c->c1.lo, cfg.batch, c->c1h, c->c1w, 64, c->pool.hi, c->pool.lo, c->ch[0],
                             c->cw[0], st);
@@ -986,6 +986,66 @@ int b2_cosine_cost(int device, const float* gallery, const int32_t* seg_offsets,
   conv_tc_plan_destroy(plan);
   cudaFree(d_g); cudaFree(d_d); cudaFree(d_dots); cudaFree(d_cost); cudaFree(d_bias); cudaFree(d_off);
   cudaFree(g_hi); cudaFree(g_lo); cudaFree(q_hi); cudaFree(q_lo);
+  if (rc) return -1;
+  B2_CUDA(e);
+  return 0;
+}
+
+// ---- distance matrix (torchreid/distance.py:6-80) ------------------------------------------------
+int b2_distance_matrix(int device, const float* a, int na, const float* b, int nb, int D, int metric, int precision,
+                       float* out) {
+  B2_CHECK(a && b && out, "b2_distance_matrix: null argument");
+  B2_CHECK(metric == 0 || metric == 1, "b2_distance_matrix: metric must be 0 (cosine) or 1 (squared euclidean)");
+  if (na <= 0 || nb <= 0) return 0;
+  B2_CUDA(cudaSetDevice(device));
+  const bool split = precision == 1;
+  const int Dp = (D + 63) / 64 * 64, Np = (nb + 15) / 16 * 16, Sp = (na + 127) / 128 * 128;
+  cudaStream_t st = nullptr;
+  float *d_a = nullptr, *d_b = nullptr, *d_dots = nullptr, *d_out = nullptr, *d_bias = nullptr, *d_na2 = nullptr,
+        *d_nb2 = nullptr;
+  __half *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
+  B2_CUDA(cudaMalloc(&d_a, sizeof(float) * na * D));
+  B2_CUDA(cudaMalloc(&d_b, sizeof(float) * nb * D));
+  B2_CUDA(cudaMalloc(&d_dots, sizeof(float) * Sp * Np));
+  B2_CUDA(cudaMalloc(&d_out, sizeof(float) * na * nb));
+  B2_CUDA(cudaMalloc(&d_bias, sizeof(float) * Np));
+  B2_CUDA(cudaMalloc(&d_na2, sizeof(float) * Sp));
+  B2_CUDA(cudaMalloc(&d_nb2, sizeof(float) * Np));
+  B2_CUDA(cudaMalloc(&a_hi, sizeof(__half) * Sp * Dp));
+  B2_CUDA(cudaMalloc(&a_lo, sizeof(__half) * Sp * Dp));
+  B2_CUDA(cudaMalloc(&b_hi, sizeof(__half) * Np * Dp));
+  B2_CUDA(cudaMalloc(&b_lo, sizeof(__half) * Np * Dp));
+  B2_CUDA(cudaMemset(a_hi, 0, sizeof(__half) * Sp * Dp));
+  B2_CUDA(cudaMemset(a_lo, 0, sizeof(__half) * Sp * Dp));
+  B2_CUDA(cudaMemset(b_hi, 0, sizeof(__half) * Np * Dp));
+  B2_CUDA(cudaMemset(b_lo, 0, sizeof(__half) * Np * Dp));
+  B2_CUDA(cudaMemset(d_bias, 0, sizeof(float) * Np));
+  B2_CUDA(cudaMemcpy(d_a, a, sizeof(float) * na * D, cudaMemcpyHostToDevice));
+  B2_CUDA(cudaMemcpy(d_b, b, sizeof(float) * nb * D, cudaMemcpyHostToDevice));
+  if (metric == 0) {
+    if (cosine_normalize_rows(d_a, na, D, a_hi, a_lo, Dp, st) || cosine_normalize_rows(d_b, nb, D, b_hi, b_lo, Dp, st))
+      return -1;
+  } else {
+    if (rows_to_planes(d_a, na, D, a_hi, a_lo, Dp, d_na2, st) || rows_to_planes(d_b, nb, D, b_hi, b_lo, Dp, d_nb2, st))
+      return -1;
+  }
+  ConvDesc d;
+  d.B = 1; d.in_H = 1; d.in_W = na; d.Cin = Dp; d.in_pitch_H = 1; d.in_pitch_W = na; d.in_ld = Dp;
+  d.Cout = nb; d.out_H = 1; d.out_W = na; d.ldc = Np;
+  ConvWeights w;
+  w.w_hi = b_hi; w.w_lo = split ? b_lo : nullptr; w.bias = d_bias; w.Cout_pad = Np; w.K = Dp;
+  ConvIO io;
+  io.in_hi = a_hi; io.in_lo = split ? a_lo : nullptr; io.out_f32 = d_dots;
+  cudaDeviceProp prop;
+  B2_CUDA(cudaGetDeviceProperties(&prop, device));
+  ConvPlan* plan = conv_tc_plan_create(d, w, io, split, prop.multiProcessorCount);
+  B2_CHECK(plan != nullptr, std::string("b2_distance_matrix: ") + last_error());
+  int rc = conv_tc_launch(plan, st);
+  if (!rc) rc = distance_finish(d_dots, Np, na, nb, metric, d_na2, d_nb2, d_out, st);
+  cudaError_t e = cudaMemcpy(out, d_out, sizeof(float) * na * nb, cudaMemcpyDeviceToHost);
+  conv_tc_plan_destroy(plan);
+  cudaFree(d_a); cudaFree(d_b); cudaFree(d_dots); cudaFree(d_out); cudaFree(d_bias); cudaFree(d_na2); cudaFree(d_nb2);
+  cudaFree(a_hi); cudaFree(a_lo); cudaFree(b_hi); cudaFree(b_lo);
   if (rc) return -1;
   B2_CUDA(e);
   return 0;

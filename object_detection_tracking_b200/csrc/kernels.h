@@ -8,8 +8,10 @@ namespace b2 {
 // stem.cu
 int f32_to_planes(const float* src, __half* hi, __half* lo, size_t n, cudaStream_t s);
 int planes_to_f32(const __half* hi, const __half* lo, float* dst, size_t n, cudaStream_t s);
+// norm_mode 0: detector (x * (1/255) - mean) / std with BGR constants (models.py:345-355);
+// norm_mode 1: torchvision ToTensor + Normalize (x / 255 - mean) / std with RGB constants (feature_extractor.py:190-196)
 int stem_pack_launch(const void* img, int is_u8, int B, int H, int W, __half* out_hi, __half* out_lo, int Hu, int Wu,
-                     cudaStream_t s);
+                     int norm_mode, cudaStream_t s);
 int maxpool_launch(const __half* in_hi, const __half* in_lo, int B, int H, int W, int C, __half* out_hi,
                    __half* out_lo, int Ho, int Wo, cudaStream_t s);
 
@@ -69,8 +71,22 @@ struct HeadPostParams {
 };
 int head_post_launch(const HeadPostParams& p, cudaStream_t s);
 
+// reid.cu
+int dwconv3x3_launch(const __half* in_hi, const __half* in_lo, int B, int H, int W, int C, const float* w,
+                     const float* bias, __half* out_hi, __half* out_lo, cudaStream_t s);
+int gap_launch(const __half* in_hi, const __half* in_lo, int B, int HW, int C, float* out, int out_ld, cudaStream_t s);
+int gate_mlp_launch(const float* g, int rows, int C, int Creal, int Cr, const float* w1, const float* b1,
+                    const float* w2, const float* b2, float* gates, cudaStream_t s);
+int gated_sum4_launch(const __half* const hi[4], const __half* const lo[4], const float* gates, int B, int HW, int C,
+                      __half* out_hi, __half* out_lo, cudaStream_t s);
+int avgpool2_launch(const __half* in_hi, const __half* in_lo, int B, int H, int W, int C, __half* out_hi,
+                    __half* out_lo, cudaStream_t s);
+
 // cosine.cu
 int cosine_normalize_rows(const float* src, int rows, int D, __half* hi, __half* lo, int ld, cudaStream_t s);
+int rows_to_planes(const float* src, int rows, int D, __half* hi, __half* lo, int ld, float* sqnorm, cudaStream_t s);
+int distance_finish(const float* dots, int ld, int na, int nb, int metric, const float* na2, const float* nb2, float* out,
+                    cudaStream_t s);
 int cosine_segmin(const float* dots, int ld, const int* seg_offsets, int T, int N, float* cost, cudaStream_t s);
 
 }  // namespace b2

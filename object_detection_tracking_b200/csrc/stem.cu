@@ -40,9 +40,10 @@ __global__ void planes_to_f32_kernel(const __half* __restrict__ hi, const __half
 template <typename TIn>
 __global__ void __launch_bounds__(256) stem_pack_kernel(const TIn* __restrict__ img, int B, int H, int W,
                                                         __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                                                        int Hu, int Wu) {
-  const float mean[3] = {0.406f, 0.456f, 0.485f};   // BGR order (models.py:350-352)
-  const float stdv[3] = {0.225f, 0.224f, 0.229f};
+                                                        int Hu, int Wu, int norm_mode) {
+  // mode 0: BGR order (models.py:350-352); mode 1: RGB order (torchvision Normalize defaults of the extractor)
+  const float mean[3] = {norm_mode ? 0.485f : 0.406f, 0.456f, norm_mode ? 0.406f : 0.485f};
+  const float stdv[3] = {norm_mode ? 0.229f : 0.225f, 0.224f, norm_mode ? 0.225f : 0.229f};
   const size_t total = static_cast<size_t>(B) * Hu * Wu * 8;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(256) stem_pack_kernel(const TIn* __restrict__ 
         const int iy = 2 * y + ry - 3, ix = 2 * (q + s) + sx - 3;
         if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
           float x = static_cast<float>(img[((static_cast<size_t>(b) * H + iy) * W + ix) * 3 + c]);
-          x = __fmul_rn(x, 1.0f / 255);
+          x = norm_mode ? __fdiv_rn(x, 255.0f) : __fmul_rn(x, 1.0f / 255);   // ToTensor divides, TF multiplies
           x = __fsub_rn(x, mean[c]);
           v = __fdiv_rn(x, stdv[c]);
         }
@@ -147,13 +148,13 @@ int planes_to_f32(const __half* hi, const __half* lo, float* dst, size_t n, cuda
 }
 
 int stem_pack_launch(const void* img, int is_u8, int B, int H, int W, __half* out_hi, __half* out_lo, int Hu, int Wu,
-                     cudaStream_t s) {
+                     int norm_mode, cudaStream_t s) {
   const size_t total = static_cast<size_t>(B) * Hu * Wu * 8;
   const unsigned grid = grid_for(total, 256, 148 * 32);
   if (is_u8)
-    stem_pack_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(img), B, H, W, out_hi, out_lo, Hu, Wu);
+    stem_pack_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(img), B, H, W, out_hi, out_lo, Hu, Wu, norm_mode);
   else
-    stem_pack_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(img), B, H, W, out_hi, out_lo, Hu, Wu);
+    stem_pack_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(img), B, H, W, out_hi, out_lo, Hu, Wu, norm_mode);
   B2_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,143 @@
+"""GPU drop-in for the reference's ReID embedding API and distance matrices.
+
+`FeatureExtractor` mirrors torchreid.utils.FeatureExtractor (torchreid/feature_extractor.py:121-252): same
+constructor arguments, callable on a list of HWC RGB uint8 arrays / a single array / image paths, returns a
+`torch.Tensor [B, 512]`.  The PIL resize of the reference's transform pipeline stays on the host (it is the
+reference's own library call); ToTensor + Normalize + the whole OSNet-x1.0 forward run in libb200det
+(b2_reid_embed).  `compute_distance_matrix` mirrors torchreid/distance.py:6-46.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_int64, c_void_p
+
+import numpy as np
+
+from . import _lib
+
+
+class ReidEngine:
+    """Owner of a b2_reid context for one crop batch size."""
+
+    def __init__(self, batch: int, device: int = 0, precision: str = "split"):
+        self.lib = _lib.load()
+        self.batch = int(batch)
+        self._ctx = c_void_p(0)
+        _lib.check(self.lib.b2_reid_create(ctypes.byref(self._ctx), int(device), self.batch,
+                                           {"fp16": 0, "split": 1}[precision]), "b2_reid_create")
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self.lib.b2_reid_destroy(self._ctx)
+            self._ctx = c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_state(self, state: dict):
+        names = sorted(k for k in state if not k.startswith("classifier") and not k.endswith("num_batches_tracked"))
+        arrs = [np.ascontiguousarray(np.asarray(state[k]), dtype=np.float32) for k in names]
+        n = len(names)
+        _lib.check(self.lib.b2_reid_load_weights(self._ctx, (c_char_p * n)(*[k.encode() for k in names]),
+                                                 (c_void_p * n)(*[a.ctypes.data for a in arrs]),
+                                                 (c_int64 * n)(*[a.size for a in arrs]), n), "b2_reid_load_weights")
+
+    def embed(self, crops_u8: np.ndarray) -> np.ndarray:
+        """crops_u8: [n, 256, 128, 3] RGB uint8, n <= batch -> [n, 512] float32."""
+        crops_u8 = np.ascontiguousarray(crops_u8, dtype=np.uint8)
+        n = crops_u8.shape[0]
+        assert crops_u8.shape[1:] == (256, 128, 3), crops_u8.shape
+        out = np.empty((n, 512), dtype=np.float32)
+        _lib.check(self.lib.b2_reid_embed(self._ctx, _lib.ptr(crops_u8), n, _lib.ptr(out)), "b2_reid_embed")
+        return out
+
+    def num_launches(self) -> int:
+        return int(self.lib.b2_reid_num_launches(self._ctx))
+
+
+class FeatureExtractor(object):
+    """torchreid/feature_extractor.py:121-252 with model_name='osnet_x1_0'."""
+
+    def __init__(self, model_name="osnet_x1_0", model_path="", image_size=(256, 128),
+                 pixel_mean=(0.485, 0.456, 0.406), pixel_std=(0.229, 0.224, 0.225), pixel_norm=True,
+                 device="cuda", verbose=False, batch=32, precision="split", state_dict=None):
+        if model_name != "osnet_x1_0":
+            raise NotImplementedError("the B200 path implements osnet_x1_0 (person ReID, multi_video_reid.py:422-427)")
+        if tuple(image_size) != (256, 128) or not pixel_norm or tuple(pixel_mean) != (0.485, 0.456, 0.406) \
+                or tuple(pixel_std) != (0.229, 0.224, 0.225):
+            raise NotImplementedError("only the reference defaults (256x128, ImageNet mean/std) are built")
+        dev = 0
+        if isinstance(device, str) and ":" in device:
+            dev = int(device.split(":")[1])
+        self.image_size = tuple(image_size)
+        self.engine = ReidEngine(batch, dev, precision)
+        self.batch = batch
+        if state_dict is None and model_path and os.path.isfile(model_path):
+            import torch
+            ckpt = torch.load(model_path, map_location="cpu")
+            state_dict = ckpt.get("state_dict", ckpt)
+            state_dict = {(k[7:] if k.startswith("module.") else k): v.numpy() for k, v in state_dict.items()}
+        if state_dict is None:
+            raise RuntimeError("FeatureExtractor needs weights: pass model_path (torchreid checkpoint) or state_dict")
+        self.engine.load_state(state_dict)
+
+    def _resize(self, arr):
+        from PIL import Image       # T.Resize on a PIL image == Image.resize(bilinear) (feature_extractor.py:190-196)
+        img = arr if isinstance(arr, Image.Image) else Image.fromarray(np.asarray(arr, dtype=np.uint8))
+        h, w = self.image_size
+        return np.asarray(img.convert("RGB").resize((w, h), Image.BILINEAR), dtype=np.uint8)
+
+    def __call__(self, input):
+        import torch
+        from PIL import Image
+        if isinstance(input, (str, np.ndarray)):
+            input = [input]
+        if not isinstance(input, list):
+            raise NotImplementedError("expects a list of HWC uint8 arrays / paths (feature_extractor.py:209-236)")
+        crops = [self._resize(Image.open(e) if isinstance(e, str) else e) for e in input]
+        feats = []
+        for i in range(0, len(crops), self.batch):
+            feats.append(self.engine.embed(np.stack(crops[i:i + self.batch])))
+        return torch.from_numpy(np.concatenate(feats, 0) if feats else np.zeros((0, 512), np.float32))
+
+
+def compute_distance_matrix(input1, input2, metric="euclidean", device=0, precision="split"):
+    """torchreid/distance.py:6-46: [m,d] x [n,d] -> [m,n]; 'euclidean' is the SQUARED distance (:49-64)."""
+    import torch
+    a = np.ascontiguousarray(input1.detach().cpu().numpy() if hasattr(input1, "detach") else input1, dtype=np.float32)
+    b = np.ascontiguousarray(input2.detach().cpu().numpy() if hasattr(input2, "detach") else input2, dtype=np.float32)
+    assert a.ndim == 2 and b.ndim == 2 and a.shape[1] == b.shape[1]
+    if metric not in ("euclidean", "cosine"):
+        raise ValueError('Unknown distance metric: {}. Please choose either "euclidean" or "cosine"'.format(metric))
+    out = np.zeros((a.shape[0], b.shape[0]), dtype=np.float32)
+    if out.size:
+        lib = _lib.load()
+        _lib.check(lib.b2_distance_matrix(device, _lib.ptr(a), a.shape[0], _lib.ptr(b), b.shape[0], a.shape[1],
+                                          0 if metric == "cosine" else 1, {"fp16": 0, "split": 1}[precision],
+                                          _lib.ptr(out)), "b2_distance_matrix")
+    return torch.from_numpy(out)
+
+
+def allgather_gallery(local_feats, group=None):
+    """Multi-camera ReID exchange step: every rank contributes its stream's gallery
+    [rows_i, D]; returns (all_feats [sum rows, D], rows_per_rank).  torch.distributed is the plumbing:
+    NCCL over NVLink for CUDA tensors, gloo for CPU tensors in the tests."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local_feats, [int(local_feats.shape[0])]
+    world = dist.get_world_size(group)
+    rows = torch.tensor([local_feats.shape[0]], dtype=torch.int64, device=local_feats.device)
+    all_rows = [torch.zeros_like(rows) for _ in range(world)]
+    dist.all_gather(all_rows, rows, group=group)
+    counts = [int(r.item()) for r in all_rows]
+    mx = max(counts)
+    padded = torch.zeros((mx, local_feats.shape[1]), dtype=local_feats.dtype, device=local_feats.device)
+    padded[:local_feats.shape[0]] = local_feats
+    bufs = [torch.zeros_like(padded) for _ in range(world)]
+    dist.all_gather(bufs, padded, group=group)
+    return torch.cat([b[:c] for b, c in zip(bufs, counts)], 0), counts

@@ -101,3 +101,78 @@ def synth_frame(h: int, w: int, seed: int = 0, n_rects: int = 4) -> np.ndarray:
         img[ry:ry + rh, rx:rx + rw] = rng.uniform(0, 255, 3).astype(np.float32)
     img += rng.uniform(-10, 10, img.shape).astype(np.float32)
     return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def osnet_param_shapes() -> dict:
+    """Parameter / buffer names and shapes of torchreid's osnet_x1_0 state_dict (osnet.py:282-438, :522-534),
+    minus the unused classifier."""
+    shapes = {}
+
+    def bn(prefix, c):
+        for k in ("weight", "bias", "running_mean", "running_var"):
+            shapes[prefix + "." + k] = (c,)
+
+    def light(prefix, c):
+        shapes[prefix + ".conv1.weight"] = (c, c, 1, 1)
+        shapes[prefix + ".conv2.weight"] = (c, 1, 3, 3)
+        bn(prefix + ".bn", c)
+
+    def osblock(prefix, cin, cout):
+        mid = cout // 4
+        shapes[prefix + ".conv1.conv.weight"] = (mid, cin, 1, 1)
+        bn(prefix + ".conv1.bn", mid)
+        light(prefix + ".conv2a", mid)
+        for name, n in (("conv2b", 2), ("conv2c", 3), ("conv2d", 4)):
+            for j in range(n):
+                light("%s.%s.%d" % (prefix, name, j), mid)
+        shapes[prefix + ".gate.fc1.weight"] = (mid // 16, mid, 1, 1)
+        shapes[prefix + ".gate.fc1.bias"] = (mid // 16,)
+        shapes[prefix + ".gate.fc2.weight"] = (mid, mid // 16, 1, 1)
+        shapes[prefix + ".gate.fc2.bias"] = (mid,)
+        shapes[prefix + ".conv3.conv.weight"] = (cout, mid, 1, 1)
+        bn(prefix + ".conv3.bn", cout)
+        if cin != cout:
+            shapes[prefix + ".downsample.conv.weight"] = (cout, cin, 1, 1)
+            bn(prefix + ".downsample.bn", cout)
+
+    shapes["conv1.conv.weight"] = (64, 3, 7, 7)
+    bn("conv1.bn", 64)
+    chans = (64, 256, 384, 512)
+    for s in range(3):
+        name = "conv%d" % (s + 2)
+        osblock(name + ".0", chans[s], chans[s + 1])
+        osblock(name + ".1", chans[s + 1], chans[s + 1])
+        if s < 2:
+            shapes[name + ".2.0.conv.weight"] = (chans[s + 1], chans[s + 1], 1, 1)
+            bn(name + ".2.0.bn", chans[s + 1])
+    shapes["conv5.conv.weight"] = (512, 512, 1, 1)
+    bn("conv5.bn", 512)
+    shapes["fc.0.weight"] = (512, 512)
+    shapes["fc.0.bias"] = (512,)
+    bn("fc.1", 512)
+    return shapes
+
+
+def synth_osnet_state(seed: int = 4321) -> dict:
+    """Seeded float32 state_dict for osnet_x1_0 with non-trivial BatchNorm statistics (a fresh torch model has
+    mean 0 / var 1 / gamma 1, which would not exercise the BN folding)."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, shp in osnet_param_shapes().items():
+        if name.endswith("running_var"):
+            v = rng.uniform(0.6, 1.4, shp)
+        elif name.endswith("running_mean"):
+            v = rng.standard_normal(shp) * 0.1
+        elif name.endswith("bn.weight") or name == "fc.1.weight":
+            v = rng.uniform(0.7, 1.3, shp)
+        elif name.endswith("bias"):
+            v = rng.standard_normal(shp) * 0.05
+        elif len(shp) == 4 and shp[1] == 1:                 # depthwise 3x3: fan_in 9
+            v = rng.standard_normal(shp) * np.sqrt(2.0 / 9)
+        elif len(shp) >= 2:
+            fan_in = int(np.prod(shp[1:]))
+            v = rng.standard_normal(shp) * np.sqrt(2.0 / fan_in)
+        else:
+            v = rng.standard_normal(shp) * 0.05
+        out[name] = v.astype(np.float32)
+    return out

@@ -79,8 +79,38 @@ def tracker_run():
              **{"frame%d" % i: fr for i, fr in enumerate(frames)})
 
 
+
+
+def osnet():
+    """Reference torchreid osnet_x1_0 (eval) on seeded crops with the seeded synthetic state_dict."""
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from object_detection_tracking_b200.synth import synth_osnet_state
+    from torchreid.feature_extractor import FeatureExtractor
+    from torchreid import distance
+    state = synth_osnet_state(4321)
+    ext = FeatureExtractor("osnet_x1_0", model_path="", device="cpu", verbose=False)
+    sd = ext.model.state_dict()
+    for k, v in state.items():
+        assert tuple(sd[k].shape) == v.shape, (k, sd[k].shape, v.shape)
+        sd[k].copy_(torch.from_numpy(v))
+    ext.model.load_state_dict(sd)
+    ext.model.eval()
+    rng = np.random.default_rng(5)
+    crops = [rng.integers(0, 256, (int(rng.integers(60, 300)), int(rng.integers(30, 160)), 3), dtype=np.uint8)
+             for _ in range(6)]
+    feats = ext(crops).numpy()
+    # also the model on already-resized crops (isolates the network from PIL)
+    resized = np.stack([np.asarray(ext.to_pil(c).resize((128, 256), 2)) for c in crops])   # 2 = PIL BILINEAR
+    d_cos = distance.compute_distance_matrix(torch.from_numpy(feats[:4]), torch.from_numpy(feats[2:]), "cosine").numpy()
+    d_euc = distance.compute_distance_matrix(torch.from_numpy(feats[:4]), torch.from_numpy(feats[2:]), "euclidean").numpy()
+    np.savez_compressed(os.path.join(HERE, "osnet.npz"), feats=feats, resized=resized, d_cos=d_cos, d_euc=d_euc,
+                        **{"crop%d" % i: c for i, c in enumerate(crops)})
+
+
 if __name__ == "__main__":
     anchors()
     cosine()
     tracker_run()
+    osnet()
     print("golden fixtures written to", HERE)
