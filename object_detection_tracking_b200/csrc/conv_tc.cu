@@ -222,6 +222,29 @@ __device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, con
   }
 }
 
+// ACC drain: fold one chunk accumulator (128 TMEM columns of this thread's row) into the per-thread
+// running sums with round-to-nearest adds.  Four 16-column tcgen05.ld are in flight per wait.
+__device__ __forceinline__ void acc_drain(float (&sums)[128], uint32_t tsrc, int nch, bool first) {
+#pragma unroll
+  for (int cc = 0; cc < 8; cc += 4) {
+    if (cc < nch) {
+      uint32_t t[4][16];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (cc + u < nch) tmem_ld_32x32b_x16(tsrc + (cc + u) * 16, t[u]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (cc + u < nch) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            sums[(cc + u) * 16 + i] =
+                first ? __uint_as_float(t[u][i]) : __fadd_rn(sums[(cc + u) * 16 + i], __uint_as_float(t[u][i]));
+        }
+    }
+  }
+}
+
 // ACC (split precision only): the tensor core adds into its fp32 accumulator with truncation (round
 // toward zero), a bias that grows with the number of accumulation steps (K/16) and compounds through 100+
 // layers.  With ACC the hi*hi accumulator is restarted every kAccChunkKb K-blocks in alternating TMEM
@@ -439,7 +462,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int m_blk = tile / p.num_n_blocks;
         const int n_blk = tile - m_blk * p.num_n_blocks;
         const int n0 = n_blk * p.block_n;
-        float sums[ACC ? 128 : 1];
+        float sums[128];
         if (ACC) {
           const int nq = (p.num_kb + p.acc_kb - 1) / p.acc_kb;
           const int nch_acc = p.block_n >> 4;
@@ -448,24 +471,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             mbar_wait(&c_full[cbuf], (qe >> 1) & 1);
             tc_fence_after();
             const uint32_t tsrc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + cbuf * 128;
-#pragma unroll
-            for (int cc = 0; cc < 8; cc += 2) {
-              if (cc < nch_acc) {
-                uint32_t t0[16], t1[16];
-                tmem_ld_32x32b_x16(tsrc + cc * 16, t0);
-                if (cc + 1 < nch_acc) tmem_ld_32x32b_x16(tsrc + cc * 16 + 16, t1);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  sums[(ACC ? cc : 0) * 16 + (ACC ? i : 0)] =
-                      q == 0 ? __uint_as_float(t0[i]) : __fadd_rn(sums[(ACC ? cc : 0) * 16 + (ACC ? i : 0)], __uint_as_float(t0[i]));
-                  if (cc + 1 < nch_acc)
-                    sums[(ACC ? cc + 1 : 0) * 16 + (ACC ? i : 0)] =
-                        q == 0 ? __uint_as_float(t1[i])
-                               : __fadd_rn(sums[(ACC ? cc + 1 : 0) * 16 + (ACC ? i : 0)], __uint_as_float(t1[i]));
-                }
-              }
-            }
+            acc_drain(sums, tsrc, nch_acc, q == 0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&c_empty[cbuf]);
@@ -531,7 +537,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           opix = (static_cast<size_t>(img) * p.out_H + pp) * p.out_W + qq;
           rpix = (static_cast<size_t>(img) * p.res_H + (pp >> p.res_shift)) * p.res_W + (qq >> p.res_shift);
         }
-        float sums[ACC ? 128 : 1];
+        float sums[128];
         if (ACC) {
           const int nq = (p.num_kb + p.acc_kb - 1) / p.acc_kb;
           const int nch_acc = p.block_n >> 4;
@@ -540,24 +546,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             mbar_wait(&c_full[cbuf], (qe >> 1) & 1);
             tc_fence_after();
             const uint32_t tsrc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + cbuf * 128;
-#pragma unroll
-            for (int cc = 0; cc < 8; cc += 2) {
-              if (cc < nch_acc) {
-                uint32_t t0[16], t1[16];
-                tmem_ld_32x32b_x16(tsrc + cc * 16, t0);
-                if (cc + 1 < nch_acc) tmem_ld_32x32b_x16(tsrc + cc * 16 + 16, t1);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  sums[(ACC ? cc : 0) * 16 + (ACC ? i : 0)] =
-                      q == 0 ? __uint_as_float(t0[i]) : __fadd_rn(sums[(ACC ? cc : 0) * 16 + (ACC ? i : 0)], __uint_as_float(t0[i]));
-                  if (cc + 1 < nch_acc)
-                    sums[(ACC ? cc + 1 : 0) * 16 + (ACC ? i : 0)] =
-                        q == 0 ? __uint_as_float(t1[i])
-                               : __fadd_rn(sums[(ACC ? cc + 1 : 0) * 16 + (ACC ? i : 0)], __uint_as_float(t1[i]));
-                }
-              }
-            }
+            acc_drain(sums, tsrc, nch_acc, q == 0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&c_empty[cbuf]);
