@@ -163,15 +163,19 @@ def synth_osnet_state(seed: int = 4321) -> dict:
             v = rng.uniform(0.6, 1.4, shp)
         elif name.endswith("running_mean"):
             v = rng.standard_normal(shp) * 0.1
+        elif name.endswith("conv3.bn.weight"):              # residual-branch BN: small gamma keeps the sum bounded
+            v = rng.uniform(0.1, 0.3, shp)
         elif name.endswith("bn.weight") or name == "fc.1.weight":
             v = rng.uniform(0.7, 1.3, shp)
         elif name.endswith("bias"):
             v = rng.standard_normal(shp) * 0.05
         elif len(shp) == 4 and shp[1] == 1:                 # depthwise 3x3: fan_in 9
-            v = rng.standard_normal(shp) * np.sqrt(2.0 / 9)
+            v = rng.standard_normal(shp) * np.sqrt(1.0 / 9)
         elif len(shp) >= 2:
             fan_in = int(np.prod(shp[1:]))
-            v = rng.standard_normal(shp) * np.sqrt(2.0 / fan_in)
+            relu_follows = name.endswith("conv1.conv.weight") or name.endswith(".2.0.conv.weight") \
+                or name in ("conv5.conv.weight", "fc.0.weight")
+            v = rng.standard_normal(shp) * np.sqrt((2.0 if relu_follows else 1.0) / fan_in)
         else:
             v = rng.standard_normal(shp) * 0.05
         out[name] = v.astype(np.float32)
