@@ -111,6 +111,8 @@ void b2_reid_destroy(b2_reid* ctx);
 int b2_reid_load_weights(b2_reid* ctx, const char* const* names, const float* const* data, const int64_t* numel, int n);
 int b2_reid_embed(b2_reid* ctx, const uint8_t* crops_host, int n, float* feats_host);
 int b2_reid_num_launches(b2_reid* ctx);
+/* Stage-addressable activation of the last pass as fp32 NHWC (parity tests): "conv1", "maxpool", "conv2.0", ... */
+int b2_reid_get_activation(b2_reid* ctx, const char* name, float* dst_host, int64_t capacity_bytes, int64_t shape[4]);
 
 /* Distance matrix of torchreid/distance.py:6-80 on the tensor cores: a [na,D], b [nb,D] (host) -> out [na,nb].
  * metric 0 = cosine (1 - a^.b^), 1 = squared euclidean (|a|^2 + |b|^2 - 2 a.b). */

@@ -59,6 +59,7 @@ struct ConvTcParams {
   int ldr, res_H, res_W, res_shift;
   int relu;
   int acc_kb;        // ACC: K-blocks per tensor-core accumulation chunk
+  int dbg_nodrain;   // perf experiment only (wrong results): skip the TMEM reads of the ACC drain
   int epi_mode;      // 0 = direct global loads/stores per thread, 1 = TMA-staged (residual in, result out)
   uint32_t epi_off;  // byte offset of the epilogue staging buffers inside the tile area
 };
@@ -471,7 +472,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             mbar_wait(&c_full[cbuf], (qe >> 1) & 1);
             tc_fence_after();
             const uint32_t tsrc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + cbuf * 128;
-            acc_drain(sums, tsrc, nch_acc, q == 0);
+            if (!p.dbg_nodrain) acc_drain(sums, tsrc, nch_acc, q == 0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&c_empty[cbuf]);
@@ -520,7 +521,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           aphase ^= 1;
         }
       }
-      if (elected) bulk_wait_read<0>();
+      if (elected) bulk_wait_all();   // the output must be globally written before the CTA retires
     } else {
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int m_blk = tile / p.num_n_blocks;
@@ -546,7 +547,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             mbar_wait(&c_full[cbuf], (qe >> 1) & 1);
             tc_fence_after();
             const uint32_t tsrc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + cbuf * 128;
-            acc_drain(sums, tsrc, nch_acc, q == 0);
+            if (!p.dbg_nodrain) acc_drain(sums, tsrc, nch_acc, q == 0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&c_empty[cbuf]);
@@ -716,6 +717,7 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   p.relu = d.relu;
   pl->split = split;
   // accurate accumulation: on by default in split precision when K spans more than one chunk
+  p.dbg_nodrain = getenv("B2_ACC_NODRAIN") != nullptr;
   p.acc_kb = d.acc_kb > 0 ? d.acc_kb : kAccChunkKb;
   if (const char* e = getenv("B2_ACC_KB")) p.acc_kb = atoi(e) > 0 ? atoi(e) : kAccChunkKb;   // experiment hook
   pl->acc = split && d.acc_kb >= 0 && p.num_kb > p.acc_kb && getenv("B2_NO_ACC") == nullptr;

@@ -913,7 +913,8 @@ int b2_set_stage(b2_ctx* c, const char* name, const void* src, int64_t bytes) {
   B2_CUDA(cudaSetDevice(c->device));
   if (strcmp(name, "image") == 0) {
     B2_CHECK(bytes == static_cast<int64_t>(c->img_bytes), "b2_set_stage(image): size mismatch");
-    B2_CUDA(cudaMemcpy(c->img, src, bytes, cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMemcpyAsync(c->img, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
   }
   auto it = c->stages.find(name);
@@ -925,12 +926,13 @@ int b2_set_stage(b2_ctx* c, const char* name, const void* src, int64_t bytes) {
   if (s.kind == 0) {
     float* tmp = nullptr;
     B2_CUDA(cudaMalloc(&tmp, n * 4));
-    B2_CUDA(cudaMemcpy(tmp, src, n * 4, cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMemcpyAsync(tmp, src, n * 4, cudaMemcpyHostToDevice, c->stream));   // same stream as the kernel
     if (f32_to_planes(tmp, s.pl.hi, s.pl.lo, n, c->stream)) return -1;
     B2_CUDA(cudaStreamSynchronize(c->stream));
     B2_CUDA(cudaFree(tmp));
   } else {
-    B2_CUDA(cudaMemcpy(s.ptr, src, n * 4, cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMemcpyAsync(s.ptr, src, n * 4, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
   }
   return 0;
 }

@@ -8,6 +8,7 @@
 // Input contract (torchreid/feature_extractor.py:190-196,209-252): RGB uint8 crops already resized to
 // 256x128 (the PIL resize stays on the host), ToTensor + Normalize happen in the stem pack kernel.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -73,6 +74,7 @@ struct b2_reid {
   std::vector<std::unique_ptr<RDw>> dws;
   std::vector<std::unique_ptr<RGate>> gates;
   std::vector<RStep> steps;
+  std::map<std::string, RPlanes> named;     // stage-addressable activations (parity tests)
   uint8_t* crops = nullptr;
   RPlanes stem_u, gap_planes;
   float* gap_f32 = nullptr;
@@ -166,6 +168,9 @@ RPlanes add_osblock(b2_reid* c, const std::string& pre, const RPlanes& x, int ci
   G->w1 = c->alloc<float>(static_cast<size_t>(G->cr) * mid); G->b1 = c->alloc<float>(G->cr);
   G->w2 = c->alloc<float>(static_cast<size_t>(mid) * G->cr); G->b2 = c->alloc<float>(mid);
   RPlanes x2 = G->out;
+  c->named[pre + ".x1"] = x1;
+  for (int k = 0; k < 4; ++k) c->named[pre + ".s" + std::to_string(k)] = s[k];
+  c->named[pre + ".x2"] = x2;
   c->steps.push_back({4, static_cast<int>(c->gates.size()), RPlanes(), RPlanes()});
   c->gates.push_back(std::move(G));
   RPlanes identity = x;
@@ -197,22 +202,30 @@ int build(b2_reid* c) {
   }
   RPlanes p1 = c->planes(B, h1 / 2, w1 / 2, 64);       // maxpool 3/2 pad 1 (:308)
   c->steps.push_back({2, 0, c1, p1});
+  c->named["stem_u"] = c->stem_u;
+  c->named["conv1"] = c1;
+  c->named["maxpool"] = p1;
   RPlanes x = p1;
   const int chans[4] = {64, 256, 384, 512};
   for (int stage = 0; stage < 3; ++stage) {
     const std::string sn = "conv" + std::to_string(stage + 2);
     x = add_osblock(c, sn + ".0", x, chans[stage], chans[stage + 1]);
+    c->named[sn + ".0"] = x;
     x = add_osblock(c, sn + ".1", x, chans[stage + 1], chans[stage + 1]);
+    c->named[sn + ".1"] = x;
     if (stage < 2) {   // transition: Conv1x1 + AvgPool2d(2) (:375-381)
       RPlanes t = c->planes(B, x.H, x.W, x.C);
       add_pw(c, sn + ".2.0.conv.weight", sn + ".2.0.bn", "", x, x.C, t, x.C, true, nullptr);
       RPlanes q = c->planes(B, x.H / 2, x.W / 2, x.C);
       c->steps.push_back({5, 0, t, q});
+      c->named[sn + ".t"] = t;
       x = q;
+      c->named[sn] = x;
     }
   }
   RPlanes x5 = c->planes(B, x.H, x.W, 512);
   add_pw(c, "conv5.conv.weight", "conv5.bn", "", x, 512, x5, 512, true, nullptr);
+  c->named["conv5"] = x5;
   // global average pool -> fc + BN1d + ReLU (:428-431, fc built by _construct_fc_layer :386-405)
   const int Bp = (B + 127) / 128 * 128;
   c->gap_f32 = c->alloc<float>(static_cast<size_t>(Bp) * 512);
@@ -291,7 +304,9 @@ int bn_fold(const WS& ws, const std::string& bn, int C, std::vector<double>& sca
 int upload(b2_reid* c, RConv* L, const std::vector<float>& packed, const std::vector<float>& bias) {
   float* tmp = nullptr;
   B2_CUDA(cudaMalloc(&tmp, packed.size() * 4));
-  B2_CUDA(cudaMemcpy(tmp, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+  // same stream as the conversion kernel: a pageable cudaMemcpy on the legacy stream may return before its DMA
+  // lands, and the context stream is non-blocking (not ordered after the legacy stream)
+  B2_CUDA(cudaMemcpyAsync(tmp, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, c->stream));
   if (f32_to_planes(tmp, L->w.w_hi, L->w.w_lo, packed.size(), c->stream)) return -1;
   B2_CUDA(cudaMemcpyAsync(L->w.bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice, c->stream));
   B2_CUDA(cudaStreamSynchronize(c->stream));
@@ -378,8 +393,9 @@ int b2_reid_load_weights(b2_reid* c, const char* const* names, const float* cons
       for (int t = 0; t < 9; ++t) pw[t * C + ch] = static_cast<float>(w[ch * 9 + t] * scale[ch]);
       pb[ch] = static_cast<float>(shift[ch]);
     }
-    B2_CUDA(cudaMemcpy(D->w, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice));
-    B2_CUDA(cudaMemcpy(D->bias, pb.data(), pb.size() * 4, cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMemcpyAsync(D->w, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(D->bias, pb.data(), pb.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
   }
   for (auto& G : c->gates) {
     const int m = G->creal, r = G->cr;
@@ -388,10 +404,11 @@ int b2_reid_load_weights(b2_reid* c, const char* const* names, const float* cons
     const float* w2 = ws.get(G->prefix + ".fc2.weight", static_cast<int64_t>(m) * r);
     const float* b2 = ws.get(G->prefix + ".fc2.bias", m);
     if (!w1 || !b1 || !w2 || !b2) return -1;
-    B2_CUDA(cudaMemcpy(G->w1, w1, sizeof(float) * r * m, cudaMemcpyHostToDevice));
-    B2_CUDA(cudaMemcpy(G->b1, b1, sizeof(float) * r, cudaMemcpyHostToDevice));
-    B2_CUDA(cudaMemcpy(G->w2, w2, sizeof(float) * m * r, cudaMemcpyHostToDevice));
-    B2_CUDA(cudaMemcpy(G->b2, b2, sizeof(float) * m, cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMemcpyAsync(G->w1, w1, sizeof(float) * r * m, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(G->b1, b1, sizeof(float) * r, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(G->w2, w2, sizeof(float) * m * r, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(G->b2, b2, sizeof(float) * m, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
   }
   c->loaded = true;
   return 0;
@@ -412,6 +429,12 @@ int b2_reid_embed(b2_reid* c, const uint8_t* crops_host, int n, float* feats_hos
   const size_t per = 256 * 128 * 3;
   if (n < c->B) B2_CUDA(cudaMemsetAsync(c->crops + n * per, 0, (c->B - n) * per, c->stream));
   B2_CUDA(cudaMemcpyAsync(c->crops, crops_host, n * per, cudaMemcpyHostToDevice, c->stream));
+  if (getenv("B2_REID_NO_GRAPH") != nullptr) {
+    if (reid_enqueue(c)) return -1;
+    B2_CUDA(cudaMemcpyAsync(feats_host, c->feats, sizeof(float) * n * 512, cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+  }
   if (!c->graph) {
     if (reid_enqueue(c)) return -1;                 // eager warm-up before the capture
     B2_CUDA(cudaStreamSynchronize(c->stream));
@@ -427,6 +450,27 @@ int b2_reid_embed(b2_reid* c, const uint8_t* crops_host, int n, float* feats_hos
   B2_CUDA(cudaGraphLaunch(c->graph, c->stream));
   B2_CUDA(cudaMemcpyAsync(feats_host, c->feats, sizeof(float) * n * 512, cudaMemcpyDeviceToHost, c->stream));
   B2_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// Stage-addressable activation of the last pass as fp32 NHWC (names: "conv1", "maxpool", "conv2.0", "conv2.0.x1",
+// "conv2.0.s0".."s3", "conv2.0.x2", "conv2.1", "conv2", ..., "conv5").
+int b2_reid_get_activation(b2_reid* c, const char* name, float* dst, int64_t capacity, int64_t shape[4]) {
+  B2_CHECK(c && name && dst && shape, "b2_reid_get_activation: null argument");
+  B2_CUDA(cudaSetDevice(c->device));
+  auto it = c->named.find(name);
+  B2_CHECK(it != c->named.end(), std::string("unknown activation: ") + name);
+  const RPlanes& p = it->second;
+  shape[0] = p.B; shape[1] = p.H; shape[2] = p.W; shape[3] = p.C;
+  const int64_t n = static_cast<int64_t>(p.elems());
+  B2_CHECK(capacity >= n * 4, "b2_reid_get_activation: buffer too small");
+  float* tmp = nullptr;
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  B2_CUDA(cudaMalloc(&tmp, n * 4));
+  if (planes_to_f32(p.hi, p.lo, tmp, n, c->stream)) return -1;
+  B2_CUDA(cudaMemcpyAsync(dst, tmp, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  B2_CUDA(cudaFree(tmp));
   return 0;
 }
 

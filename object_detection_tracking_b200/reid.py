@@ -55,6 +55,16 @@ class ReidEngine:
         _lib.check(self.lib.b2_reid_embed(self._ctx, _lib.ptr(crops_u8), n, _lib.ptr(out)), "b2_reid_embed")
         return out
 
+    def get_activation(self, name: str) -> np.ndarray:
+        """fp32 NHWC copy of a named intermediate of the last pass (parity tests)."""
+        shape = (c_int64 * 4)()
+        cap = self.batch * 131 * 64 * 64 * 4 + 1024
+        buf = np.empty(cap // 4, dtype=np.float32)
+        _lib.check(self.lib.b2_reid_get_activation(self._ctx, name.encode(), _lib.ptr(buf), buf.nbytes, shape),
+                   "b2_reid_get_activation")
+        shp = tuple(int(v) for v in shape)
+        return buf[:int(np.prod(shp))].reshape(shp).copy()
+
     def num_launches(self) -> int:
         return int(self.lib.b2_reid_num_launches(self._ctx))
 
