@@ -40,36 +40,71 @@ def workload_config(n_gpus, precision):
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """Samples SM clock / throttle reasons during the timed region (B200_PROFILING.md): NVML every 10 ms
+    (nvidia-smi every 200 ms as a fallback when the NVML binding is unavailable)."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.sm = []
+        self.sm_max = None
+        self.reason_bits = 0
         self.stop = threading.Event()
+        self.how = "nvml"
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        # LOCAL_RANK indexes the visible devices; map through CUDA_VISIBLE_DEVICES when it is a plain index list
+        idx = self.index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if vis and all(v.strip().isdigit() for v in vis.split(",")):
+            idx = int(vis.split(",")[self.index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        while not self.stop.is_set():
+            self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            try:
+                self.reason_bits |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                self.reason_bits |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            self.stop.wait(0.01)
+
+    def _run_smi(self):
+        self.how = "nvidia-smi"
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        bits = [0x8, 0x40, 0x20, 0x4]
         while not self.stop.is_set():
-            try:
-                r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                parts = [p.strip() for p in r.stdout.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
-            except Exception:
-                pass
+            r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+            parts = [p.strip() for p in r.stdout.strip().split(",")]
+            if len(parts) >= 6:
+                self.sm.append(float(parts[0]))
+                self.sm_max = float(parts[1])
+                for b, v in zip(bits, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reason_bits |= b
             self.stop.wait(0.2)
 
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            try:
+                self._run_smi()
+            except Exception:
+                pass
+
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(self.samples)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unsampled"], "samples": 0}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.sm_max,
+                "reasons": [n for b, n in self.REASONS.items() if self.reason_bits & b],
+                "samples": len(sm), "source": self.how}
 
 
 def measured_peaks():
@@ -78,6 +113,17 @@ def measured_peaks():
         d = json.load(open(p))
         return d, "measured (MEASURED_PEAKS.json)"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(precision):
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv_tc_kernel launch (average over the launches of one
+    pass) from the committed ncu capture of the same workload, or None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "r1_conv_tc_dram_%s_b8.json" % precision)
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return {"bytes_per_launch_avg": d["dram_bytes_total"] / d["launches"], "launches": d["launches"],
+            "source": "profiles/" + os.path.basename(p)}
 
 
 def usable_cores():
@@ -245,7 +291,9 @@ def main():
                     "peak_source": peak_src + ", fp16/bf16 dense sustained",
                     "algorithmic_gflop_per_launch_avg": conv_flops / len(conv) / 1e9,
                     "avg_launch_ms": conv_ms / len(conv), "share_of_step": conv_ms / total_ms,
-                    "traffic": None}
+                    "mma_flop_multiplier": 3 if args.precision == "split" else 1,
+                    "tensor_pipe_work_frac": achieved_tf * (3 if args.precision == "split" else 1) / peak_tf,
+                    "traffic": ncu_traffic(args.precision)}
         if args.profile_json:
             with open(args.profile_json, "w") as f:
                 json.dump({"precision": args.precision, "batch": BATCH, "steps": prof}, f, indent=1)
