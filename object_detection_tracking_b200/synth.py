@@ -180,3 +180,60 @@ def synth_osnet_state(seed: int = 4321) -> dict:
             v = rng.standard_normal(shp) * 0.05
         out[name] = v.astype(np.float32)
     return out
+
+
+def synth_effdet_weights(cfg, seed: int = 99) -> dict:
+    """Seeded weights of the EfficientDet feature network + class/box nets in the TF variable naming of
+    efficientdet_arch.py (kernels HWIO, depthwise [3,3,C,1]); BN statistics non-trivial; predict biases spread
+    so that the top-k / NMS path sees a non-degenerate score distribution."""
+    from .effdet_config import BIFPN_NODES
+    rng = np.random.default_rng(seed)
+    W = {}
+    F_ = cfg.fpn_num_filters
+
+    def bn(name, c):
+        W[name + "/gamma"] = rng.uniform(0.7, 1.3, c).astype(np.float32)
+        W[name + "/beta"] = (rng.standard_normal(c) * 0.1).astype(np.float32)
+        W[name + "/moving_mean"] = (rng.standard_normal(c) * 0.1).astype(np.float32)
+        W[name + "/moving_variance"] = rng.uniform(0.6, 1.4, c).astype(np.float32)
+
+    def conv(name, cin, cout):
+        W[name + "/kernel"] = (rng.standard_normal((1, 1, cin, cout)) * np.sqrt(1.0 / cin)).astype(np.float32)
+        W[name + "/bias"] = (rng.standard_normal(cout) * 0.05).astype(np.float32)
+
+    def sep(name, c, cout, gain=1.6, bias_std=0.05):
+        W[name + "/depthwise_kernel"] = (rng.standard_normal((3, 3, c, 1)) * np.sqrt(1.0 / 9)).astype(np.float32)
+        W[name + "/pointwise_kernel"] = (rng.standard_normal((1, 1, c, cout)) * np.sqrt(gain / c)).astype(np.float32)
+        W[name + "/bias"] = (rng.standard_normal(cout) * bias_std).astype(np.float32)
+
+    c5 = cfg.backbone_channels[2]
+    if c5 != F_:
+        conv("resample_p6/conv2d", c5, F_)
+        bn("resample_p6/bn", F_)
+    chans = list(cfg.backbone_channels) + [F_, F_]
+    for rep in range(cfg.fpn_cell_repeats):
+        cur = list(chans) if rep == 0 else [F_] * 5
+        for i, (lvl, offsets) in enumerate(BIFPN_NODES):
+            pre = "fpn_cells/cell_%d/fnode%d" % (rep, i)
+            for idx, o in enumerate(offsets):
+                if cur[o] != F_:
+                    nm = "%s/resample_%d_%d_%d" % (pre, idx, o, len(cur))
+                    conv(nm + "/conv2d", cur[o], F_)
+                    bn(nm + "/bn", F_)
+                if cfg.fpn_weight_method == "fastattn":
+                    W["%s/WSM%s" % (pre, "" if idx == 0 else "_%d" % idx)] = np.float32(rng.uniform(0.5, 1.5))
+            op = "%s/op_after_combine%d" % (pre, len(cur))
+            sep(op + "/conv", F_, F_, gain=1.0)
+            bn(op + "/bn", F_)
+            cur.append(F_)
+    na = cfg.num_scales * len(cfg.aspect_ratios)
+    for kind, nout in (("class", cfg.num_classes * na), ("box", 4 * na)):
+        for i in range(cfg.box_class_repeats):
+            sep("%s_net/%s-%d" % (kind, kind, i), F_, F_)
+            for level in range(cfg.min_level, cfg.max_level + 1):
+                bn("%s_net/%s-%d-bn-%d" % (kind, kind, i, level), F_)
+        sep("%s_net/%s-predict" % (kind, kind), F_, nout, gain=1.0 if kind == "class" else 0.05,
+            bias_std=1.0 if kind == "class" else 0.02)
+    if "class_net/class-predict/bias" in W:
+        W["class_net/class-predict/bias"] -= np.float32(3.0)     # mostly-negative logits, like a trained detector
+    return W
