@@ -114,6 +114,37 @@ int b2_reid_num_launches(b2_reid* ctx);
 /* Stage-addressable activation of the last pass as fp32 NHWC (parity tests): "conv1", "maxpool", "conv2.0", ... */
 int b2_reid_get_activation(b2_reid* ctx, const char* name, float* dst_host, int64_t capacity_bytes, int64_t shape[4]);
 
+/* ---- EfficientDet (config 3): BiFPN feature network + class/box nets + detection post-processing.
+ * Replaces the TF graph of efficientdet/efficientdet_arch.py build_feature_network (:440-505), build_bifpn_layer
+ * (:594-682), build_class_and_box_outputs (:343-393) and the wrapper's add_metric_fn_inputs / get_results_tf /
+ * own-level ROIAlign box feature (efficientdet_wrapper.py:265-474; anchors.py:399-487). */
+typedef struct b2_effdet_config {
+  int image_h, image_w;            /* network input size (multiple of 128) */
+  int min_level, max_level;        /* 3, 7 */
+  int fpn_num_filters, fpn_cell_repeats, box_class_repeats;
+  int num_classes, num_scales, num_aspects;
+  float aspect_ratios[3][2];       /* (x, y) multipliers, anchors.py:216-257 */
+  float anchor_scale;
+  int fpn_weight_method;           /* 0 "sum", 1 "fastattn" */
+  int backbone_channels[3];        /* channels of the backbone's level 3, 4, 5 endpoints */
+  int max_detection_topk;          /* 5000 */
+  int result_per_im;               /* 100 */
+  float nms_iou_threshold, result_score_thres;
+  int precision;                   /* 0 fp16, 1 split (fp32-class) */
+} b2_effdet_config;
+typedef struct b2_effdet b2_effdet;
+int b2_effdet_create(b2_effdet** out, const b2_effdet_config* cfg, int device);
+void b2_effdet_destroy(b2_effdet* ctx);
+/* TF checkpoint variables (names as efficientdet_arch.py creates them, kernels HWIO, fp32) */
+int b2_effdet_load_weights(b2_effdet* ctx, const char* const* names, const float* const* data, const int64_t* numel, int n);
+/* Backbone endpoints C3/C4/C5 (host NHWC fp32) -> detections: boxes [max][4] x1 y1 x2 y2 scaled by image_scale,
+ * scores, classes (1-based), levels, box_feat [max][fpn_num_filters]; *count = number of valid rows. */
+int b2_effdet_run_features(b2_effdet* ctx, const float* c3, const float* c4, const float* c5, float image_scale,
+                           float* boxes, float* scores, int32_t* classes, int32_t* levels, float* box_feat, int32_t* count);
+/* Stage tensors of the last pass (parity tests): "fpn3".."fpn7", "cls3".."cls7", "box3".."box7" as fp32 NHWC */
+int b2_effdet_get_stage(b2_effdet* ctx, const char* name, float* dst_host, int64_t capacity_bytes, int64_t shape[4]);
+int b2_effdet_num_launches(b2_effdet* ctx);
+
 /* Distance matrix of torchreid/distance.py:6-80 on the tensor cores: a [na,D], b [nb,D] (host) -> out [na,nb].
  * metric 0 = cosine (1 - a^.b^), 1 = squared euclidean (|a|^2 + |b|^2 - 2 a.b). */
 int b2_distance_matrix(int device, const float* a, int na, const float* b, int nb, int D, int metric, int precision,

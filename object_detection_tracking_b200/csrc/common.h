@@ -58,7 +58,7 @@ struct ConvDesc {
   int Cout = 0;
   // output placement: conv output (Ho x Wo) written at (off_h, off_w) inside an out_H x out_W buffer
   int out_H = 0, out_W = 0, off_h = 0, off_w = 0, ldc = 0;
-  int relu = 0;
+  int relu = 0;        // 0 none, 1 ReLU, 2 swish (x * sigmoid(x))
   int res_shift = 0;   // residual pixel = (p >> shift, q >> shift) in a res_H x res_W buffer
   int res_H = 0, res_W = 0, ldr = 0;
   int Ho() const { return (in_H + pad_t + pad_b - ((R - 1) * dil + 1)) / stride + 1; }

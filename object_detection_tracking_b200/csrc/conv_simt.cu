@@ -59,7 +59,8 @@ __global__ void conv_simt_kernel(ConvDesc d, ConvWeights w, ConvIO io, int Ho, i
         v += __half2float(io.res_hi[rpix * d.ldr + n]);
         if (SPLIT && io.res_lo) v = fmaf(__half2float(io.res_lo[rpix * d.ldr + n]), kLoInv, v);
       }
-      if (d.relu) v = fmaxf(v, 0.f);
+      if (d.relu == 1) v = fmaxf(v, 0.f);
+      else if (d.relu == 2) v = __fmul_rn(v, 1.f / (1.f + expf(-v)));
       if (io.out_f32) {
         io.out_f32[opix * d.ldc + n] = v;
       } else {

@@ -121,9 +121,12 @@ __device__ __forceinline__ void epilogue_chunk16(const ConvTcParams& p, const ui
       }
     }
   }
-  if (p.relu) {
+  if (p.relu == 1) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+  } else if (p.relu == 2) {   // swish: x * sigmoid(x)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], 1.f / (1.f + expf(-v[j])));
   }
   if (p.out_f32 != nullptr) {
     float4* o = reinterpret_cast<float4*>(p.out_f32 + opix * p.ldc + n);
@@ -202,9 +205,12 @@ __device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, con
       }
     }
   }
-  if (p.relu) {
+  if (p.relu == 1) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+  } else if (p.relu == 2) {   // swish: x * sigmoid(x)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], 1.f / (1.f + expf(-v[j])));
   }
   uint32_t hi[8];
 #pragma unroll

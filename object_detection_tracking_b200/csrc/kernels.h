@@ -82,6 +82,73 @@ int gated_sum4_launch(const __half* const hi[4], const __half* const lo[4], cons
 int avgpool2_launch(const __half* in_hi, const __half* in_lo, int B, int H, int W, int C, __half* out_hi,
                     __half* out_lo, cudaStream_t s);
 
+// effdet.cu -- EfficientDet feature network, heads' depthwise halves, post-processing
+struct BifpnInput {
+  const __half* hi;
+  const __half* lo;
+  int H, W;               // source map size
+  int mode;               // 0 same size, 1 max-pool 3x3/2 SAME from a 2x finer map, 2 nearest 2x upsampling
+  int pad_t, pad_l;       // SAME padding of mode 1
+  float weight;           // fast-attention edge weight relu(w_i)
+};
+struct BifpnCombineParams {
+  BifpnInput in[3];
+  int n_in;
+  int B, Ho, Wo, C;
+  int weighted;           // 1: node = sum_i x_i * w_i / denom (fastattn); 0: plain sum
+  float denom;            // sum_i relu(w_i) + 1e-4
+  int swish;              // apply x * sigmoid(x) to the combined node (op_after_combine input)
+  __half* out_hi;
+  __half* out_lo;
+};
+int bifpn_combine_launch(const BifpnCombineParams& p, cudaStream_t s);
+int dw3x3_plain_launch(const __half* in_hi, const __half* in_lo, int B, int H, int W, int C, const float* w, __half* out_hi,
+                       __half* out_lo, cudaStream_t s);
+
+struct EffdetPostParams {
+  const float* logits[5];   // per level [h*w][ld]: anchor-major, class-minor (A * num_classes real columns)
+  const float* boxes[5];    // per level [h*w][ldb]: A * 4 (ty, tx, th, tw)
+  int ld[5], ldb[5], w[5];
+  unsigned long long level_off[6];   // flat logit index where each level starts
+  unsigned long long total;
+  int n_levels, anchors, num_classes, min_level;
+  double stride_y[5], stride_x[5], half_y[5][9], half_x[5][9];   // anchor grid (anchors.py:216-257), float64 like numpy
+  int k, max_out;
+  float score_thresh, nms_thr;
+  unsigned int* hist;       // [256]
+  uint32_t* state;          // [8]: prefix, mask, need, n_selected (> k-th), n_ties (== k-th), n_candidates
+  unsigned long long* cand; // [k]
+  unsigned long long* ties; // [k] lowest-index ties of the k-th value
+  unsigned int* tie_cnt;    // [effdet_topk_blocks()] ties per block (blocks own contiguous index ranges)
+  unsigned int* tie_off;    // exclusive prefix of tie_cnt
+  float4* cand_box;         // [k] (ymin, xmin, ymax, xmax), score order
+  float* cand_score;
+  int* cand_cls;
+  int* cand_lvl;
+  unsigned long long* mask; // [k][ceil(k/64)]
+  float4* out_boxes;        // [max_out] x1 y1 x2 y2, scaled back to the original frame
+  float* out_scores;
+  int* out_classes;
+  int* out_levels;
+  int* out_count;
+};
+int effdet_topk_blocks();
+int effdet_post_launch(const EffdetPostParams& p, const float* image_scale_dev, cudaStream_t s);
+
+// roialign.cu -- ROIAlign 7x7 on the detection's own level + mean over the 49 bins (efficientdet_wrapper.py:265-301)
+struct LevelRoiFeatParams {
+  const __half* feat_hi[5];
+  const __half* feat_lo[5];
+  int H[5], W[5];
+  float inv_stride[5];
+  int C, Creal, min_level, max_out;
+  const float4* boxes;      // x1 y1 x2 y2
+  const int* levels;
+  const int* count;
+  float* out;               // [max_out][Creal]
+};
+int level_roi_feat_launch(const LevelRoiFeatParams& p, cudaStream_t s);
+
 // cosine.cu
 int cosine_normalize_rows(const float* src, int rows, int D, __half* hi, __half* lo, int ld, cudaStream_t s);
 int rows_to_planes(const float* src, int rows, int D, __half* hi, __half* lo, int ld, float* sqnorm, cudaStream_t s);

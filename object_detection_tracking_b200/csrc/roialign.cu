@@ -140,7 +140,74 @@ __global__ void __launch_bounds__(256) roialign_kernel(const __grid_constant__ R
   }
 }
 
+// EfficientDet box feature: ROIAlign 7x7 on the detection's own pyramid level, then the mean of the 49 bins.
+// One block per detection, one thread per channel octet.
+__global__ void level_roi_feat_kernel(const __grid_constant__ LevelRoiFeatParams p) {
+  const int roi = blockIdx.x;
+  const int cvec = p.C / 8;
+  const bool live = roi < p.count[0];
+  float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+  int lvl = 0;
+  if (live) {
+    bx = __ldg(p.boxes + roi);
+    lvl = p.levels[roi] - p.min_level;
+  }
+  for (int cv = threadIdx.x; cv < cvec; cv += blockDim.x) {
+    float sum[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) sum[t] = 0.f;
+    if (live) {
+      const float is = p.inv_stride[lvl];
+      const int H = p.H[lvl], W = p.W[lvl];
+      const __half* fh = p.feat_hi[lvl];
+      const __half* fl = p.feat_lo[lvl];
+      for (int bin = 0; bin < kOut * kOut; ++bin) {
+        const int oy = bin / kOut, ox = bin % kOut;
+        const Axis ay = make_axis(__fmul_rn(bx.y, is), __fmul_rn(bx.w, is), H, oy);
+        const Axis ax = make_axis(__fmul_rn(bx.x, is), __fmul_rn(bx.z, is), W, ox);
+        float acc[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            if (!(ay.ok[dy] && ax.ok[dx])) continue;
+            float tl[8], tr[8], bl[8], br[8];
+            const size_t r0 = static_cast<size_t>(ay.lo[dy]) * W, r1 = static_cast<size_t>(ay.hi[dy]) * W;
+            load8(fh, fl, (r0 + ax.lo[dx]) * p.C + cv * 8, tl);
+            load8(fh, fl, (r0 + ax.hi[dx]) * p.C + cv * 8, tr);
+            load8(fh, fl, (r1 + ax.lo[dx]) * p.C + cv * 8, bl);
+            load8(fh, fl, (r1 + ax.hi[dx]) * p.C + cv * 8, br);
+            const float xl = ax.lerp[dx], yl = ay.lerp[dy];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const float top = __fadd_rn(tl[t], __fmul_rn(__fsub_rn(tr[t], tl[t]), xl));
+              const float bot = __fadd_rn(bl[t], __fmul_rn(__fsub_rn(br[t], bl[t]), xl));
+              acc[t] = __fadd_rn(acc[t], __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), yl)));
+            }
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) sum[t] = __fadd_rn(sum[t], __fdiv_rn(acc[t], 4.f));
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int ch = cv * 8 + t;
+      if (ch < p.Creal) p.out[static_cast<size_t>(roi) * p.Creal + ch] = __fdiv_rn(sum[t], 49.f);
+    }
+  }
+}
+
 }  // namespace
+
+int level_roi_feat_launch(const LevelRoiFeatParams& p, cudaStream_t s) {
+  B2_CHECK(p.C % 8 == 0 && p.max_out >= 1, "level_roi_feat: bad parameters");
+  level_roi_feat_kernel<<<p.max_out, 64, 0, s>>>(p);
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int roialign_launch(const RoiAlignParams& p, cudaStream_t s) {
   B2_CHECK(p.C == 256, "roialign: C must be 256 (one 16-byte vector per lane)");

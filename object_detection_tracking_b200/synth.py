@@ -206,6 +206,7 @@ def synth_effdet_weights(cfg, seed: int = 99) -> dict:
         W[name + "/pointwise_kernel"] = (rng.standard_normal((1, 1, c, cout)) * np.sqrt(gain / c)).astype(np.float32)
         W[name + "/bias"] = (rng.standard_normal(cout) * bias_std).astype(np.float32)
 
+    node_gain_sum = 0.55     # un-normalised "sum" nodes add 2-3 maps: smaller pointwise gain keeps 8 cells O(1)
     c5 = cfg.backbone_channels[2]
     if c5 != F_:
         conv("resample_p6/conv2d", c5, F_)
@@ -223,17 +224,17 @@ def synth_effdet_weights(cfg, seed: int = 99) -> dict:
                 if cfg.fpn_weight_method == "fastattn":
                     W["%s/WSM%s" % (pre, "" if idx == 0 else "_%d" % idx)] = np.float32(rng.uniform(0.5, 1.5))
             op = "%s/op_after_combine%d" % (pre, len(cur))
-            sep(op + "/conv", F_, F_, gain=1.0)
+            sep(op + "/conv", F_, F_, gain=3.0 if cfg.fpn_weight_method == "fastattn" else node_gain_sum)
             bn(op + "/bn", F_)
             cur.append(F_)
     na = cfg.num_scales * len(cfg.aspect_ratios)
     for kind, nout in (("class", cfg.num_classes * na), ("box", 4 * na)):
         for i in range(cfg.box_class_repeats):
-            sep("%s_net/%s-%d" % (kind, kind, i), F_, F_)
+            sep("%s_net/%s-%d" % (kind, kind, i), F_, F_, gain=3.0)
             for level in range(cfg.min_level, cfg.max_level + 1):
                 bn("%s_net/%s-%d-bn-%d" % (kind, kind, i, level), F_)
-        sep("%s_net/%s-predict" % (kind, kind), F_, nout, gain=1.0 if kind == "class" else 0.05,
-            bias_std=1.0 if kind == "class" else 0.02)
+        sep("%s_net/%s-predict" % (kind, kind), F_, nout, gain=6.0 if kind == "class" else 0.05,
+            bias_std=0.5 if kind == "class" else 0.02)
     if "class_net/class-predict/bias" in W:
         W["class_net/class-predict/bias"] -= np.float32(3.0)     # mostly-negative logits, like a trained detector
     return W

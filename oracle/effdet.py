@@ -158,6 +158,25 @@ def anchor_boxes(cfg, fsizes):
     return np.vstack(out).astype(np.float32)
 
 
+def sigmoid(logits):
+    """anchors.py:51-53 in float32 (tf.sigmoid of float32 logits at :443)."""
+    f32 = np.float32
+    return (f32(1) / (f32(1) + np.exp(-np.asarray(logits, f32)))).astype(f32)
+
+
+def decode_boxes(rel_codes, anchors):
+    """decode_box_outputs_tf (anchors.py:369-396; numpy twin :56-84): [N,4] (ty,tx,th,tw) x anchors [N,4]
+    (ymin,xmin,ymax,xmax) -> [N,4] (ymin,xmin,ymax,xmax), float32 op by op."""
+    f32 = np.float32
+    t = np.asarray(rel_codes, f32)
+    anchors = np.asarray(anchors, f32)
+    yca = ((anchors[:, 0] + anchors[:, 2]) / f32(2)).astype(f32); xca = ((anchors[:, 1] + anchors[:, 3]) / f32(2)).astype(f32)
+    ha = (anchors[:, 2] - anchors[:, 0]).astype(f32); wa = (anchors[:, 3] - anchors[:, 1]).astype(f32)
+    w = (np.exp(t[:, 3]).astype(f32) * wa).astype(f32); h = (np.exp(t[:, 2]).astype(f32) * ha).astype(f32)
+    yc = ((t[:, 0] * ha).astype(f32) + yca).astype(f32); xc = ((t[:, 1] * wa).astype(f32) + xca).astype(f32)
+    return np.stack([yc - h / f32(2), xc - w / f32(2), yc + h / f32(2), xc + w / f32(2)], 1).astype(f32)
+
+
 def postprocess(cls_out, box_out, cfg, fsizes, image_scale):
     """add_metric_fn_inputs (wrapper:367-474) + _generate_detections_tf (anchors.py:399-487).
     cls_out/box_out: {level: [H,W,A*C] / [H,W,A*4]} numpy.  Returns boxes x1y1x2y2 (scaled), scores, classes 1..90,
@@ -175,13 +194,8 @@ def postprocess(cls_out, box_out, cfg, fsizes, image_scale):
     idx, cls = ti // nc, ti % nc
     logits = cls_all[idx, cls]
     anchors = anchor_boxes(cfg, fsizes)[idx]
-    scores = (f32(1) / (f32(1) + np.exp(-logits.astype(f32)))).astype(f32)
-    t = box_all[idx].astype(f32)
-    yca = ((anchors[:, 0] + anchors[:, 2]) / f32(2)).astype(f32); xca = ((anchors[:, 1] + anchors[:, 3]) / f32(2)).astype(f32)
-    ha = (anchors[:, 2] - anchors[:, 0]).astype(f32); wa = (anchors[:, 3] - anchors[:, 1]).astype(f32)
-    w = (np.exp(t[:, 3]).astype(f32) * wa).astype(f32); h = (np.exp(t[:, 2]).astype(f32) * ha).astype(f32)
-    yc = ((t[:, 0] * ha).astype(f32) + yca).astype(f32); xc = ((t[:, 1] * wa).astype(f32) + xca).astype(f32)
-    boxes = np.stack([yc - h / f32(2), xc - w / f32(2), yc + h / f32(2), xc + w / f32(2)], 1).astype(f32)
+    scores = sigmoid(logits)
+    boxes = decode_boxes(box_all[idx], anchors)
     keep = tf_ops.non_max_suppression(boxes, scores, cfg.result_per_im, cfg.nms_iou_threshold,
                                       score_threshold=cfg.result_score_thres)
     b = (boxes[keep] * f32(image_scale)).astype(f32)

@@ -108,9 +108,35 @@ def osnet():
                         **{"crop%d" % i: c for i, c in enumerate(crops)})
 
 
+def effdet_numpy():
+    """The numpy halves of efficientdet/anchors.py (anchor grid, box decode, sigmoid) -- importable once the
+    TensorFlow import at the top of the module is stubbed (TF itself is absent here; only numpy code is executed)."""
+    from unittest.mock import MagicMock
+    for m in ("tensorflow", "tensorflow.compat", "tensorflow.compat.v1", "tensorflow.compat.v2", "tensorflow.python",
+              "tensorflow.python.tpu", "tensorflow.python.tpu.tpu_function", "absl", "absl.logging"):
+        sys.modules.setdefault(m, MagicMock())
+    from efficientdet import anchors as ra
+    out = {}
+    for tag, (h, w, scale) in {"a": (256, 384, 4.0), "b": (512, 640, 5.0)}.items():
+        fs = [{"height": h, "width": w}]
+        for _ in range(7):
+            fs.append({"height": (fs[-1]["height"] - 1) // 2 + 1, "width": (fs[-1]["width"] - 1) // 2 + 1})
+        cfgs = ra._generate_anchor_configs(fs, 3, 7, 3, [(1.0, 1.0), (1.4, 0.7), (0.7, 1.4)])
+        out["anchors_" + tag] = ra._generate_anchor_boxes((h, w), scale, cfgs)       # float64 [N,4]
+    rng = np.random.default_rng(11)
+    anc = out["anchors_a"][rng.integers(0, out["anchors_a"].shape[0], 64)].astype(np.float32)
+    codes = (rng.standard_normal((64, 4)) * 0.3).astype(np.float32)
+    out["dec_anchors"], out["dec_codes"] = anc, codes
+    out["dec_boxes"] = ra.decode_box_outputs(codes.swapaxes(0, 1), anc.swapaxes(0, 1))
+    logits = (rng.standard_normal(64) * 3).astype(np.float32)
+    out["sig_logits"], out["sig_scores"] = logits, ra.sigmoid(logits)
+    np.savez_compressed(os.path.join(HERE, "effdet_numpy.npz"), **out)
+
+
 if __name__ == "__main__":
     anchors()
     cosine()
     tracker_run()
     osnet()
+    effdet_numpy()
     print("golden fixtures written to", HERE)

@@ -1,0 +1,142 @@
+"""EfficientDet BiFPN + class/box nets + post-processing on the GPU (b2_effdet_* C ABI) vs oracle/effdet.py.
+Tolerances: stage tensors fp32-class (split precision); integer outputs (labels, levels, count) exact; boxes within
+1e-3 px; scores 1e-6."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _features(cfg, seed=5):
+    from object_detection_tracking_b200.effdet_config import feat_sizes
+    rng = np.random.default_rng(seed)
+    fs = feat_sizes(cfg)
+    return {l: np.abs(rng.standard_normal((cfg.backbone_channels[l - 3],) + fs[l])).astype(np.float32) for l in (3, 4, 5)}
+
+
+def _case(name, h, w, precision="split", **over):
+    from object_detection_tracking_b200.effdet import EffdetEngine
+    from object_detection_tracking_b200.effdet_config import make_effdet_config
+    from object_detection_tracking_b200.synth import synth_effdet_weights
+    from oracle import effdet as oe
+    cfg = make_effdet_config(name, h, w, **over)
+    W = synth_effdet_weights(cfg)
+    feats = _features(cfg)
+    ref = oe.forward_from_features(cfg, W, feats, image_scale=1.25, stages=True)
+    eng = EffdetEngine(cfg, W, precision=precision)
+    out = eng.run_features(feats, image_scale=1.25)
+    return cfg, eng, out, ref, feats
+
+
+@pytest.fixture(scope="module")
+def d0():
+    c = _case("efficientdet-d0", 256, 384, fpn_cell_repeats=2, box_class_repeats=2)
+    yield c
+    c[1].close()
+
+
+def test_bifpn_levels_match_oracle(d0):
+    cfg, eng, out, ref, _ = d0
+    for l in range(3, 8):
+        g, r = eng.stage("fpn%d" % l), ref["fpn"][l].transpose(1, 2, 0)
+        assert g.shape == r.shape
+        assert np.abs(g - r).max() <= 2e-5 * max(1.0, np.abs(r).max())
+
+
+def test_class_and_box_outputs_match_oracle(d0):
+    cfg, eng, out, ref, _ = d0
+    for l in range(3, 8):
+        for k, key in (("cls", "cls_out"), ("box", "box_out")):
+            g, r = eng.stage("%s%d" % (k, l)), ref[key][l]
+            assert g.shape == r.shape
+            assert np.abs(g - r).max() <= 2e-5 * max(1.0, np.abs(r).max())
+
+
+def test_detections_match_oracle(d0):
+    cfg, eng, out, ref, _ = d0
+    assert len(out["final_probs"]) == len(ref["final_probs"]) > 0
+    np.testing.assert_array_equal(out["final_labels"], ref["final_labels"])
+    np.testing.assert_array_equal(out["levels"], ref["levels"])
+    assert np.abs(out["final_boxes"] - ref["final_boxes"]).max() <= 1e-3
+    assert np.abs(out["final_probs"] - ref["final_probs"]).max() <= 1e-6
+    assert np.abs(out["fpn_box_feat"] - ref["fpn_box_feat"]).max() <= 2e-5 * max(1.0, np.abs(ref["fpn_box_feat"]).max())
+
+
+def test_graph_replay_is_deterministic_and_scale_is_live(d0):
+    cfg, eng, out, ref, feats = d0
+    again = eng.run_features(feats, image_scale=1.25)
+    for k in out:
+        np.testing.assert_array_equal(again[k], out[k])
+    other = eng.run_features(feats, image_scale=2.0)            # image_scale is read on the device, not baked in
+    np.testing.assert_array_equal(other["final_labels"], out["final_labels"])
+    np.testing.assert_allclose(other["final_boxes"], out["final_boxes"] * np.float32(2.0 / 1.25), rtol=1e-6)
+    assert eng.num_launches > 100
+
+
+def test_sum_method_and_padded_filters():
+    # D1 width (88 filters -> padded to 128 operand channels), un-normalised "sum" combine (the D6/D7 setting)
+    cfg, eng, out, ref, _ = _case("efficientdet-d1", 256, 256, fpn_cell_repeats=2, box_class_repeats=1,
+                                  fpn_weight_method="sum")
+    for l in range(3, 8):
+        g, r = eng.stage("fpn%d" % l), ref["fpn"][l].transpose(1, 2, 0)
+        assert np.abs(g - r).max() <= 2e-5 * max(1.0, np.abs(r).max())
+    np.testing.assert_array_equal(out["final_labels"], ref["final_labels"])
+    np.testing.assert_array_equal(out["levels"], ref["levels"])
+    assert np.abs(out["final_boxes"] - ref["final_boxes"]).max() <= 1e-3
+    eng.close()
+
+
+def test_d7_width_small_frame():
+    # the headline family's width (384 filters, 8 cells, 5 head repeats, anchor_scale 5, "sum") on a small frame
+    cfg, eng, out, ref, _ = _case("efficientdet-d7", 128, 256)
+    np.testing.assert_array_equal(out["final_labels"], ref["final_labels"])
+    np.testing.assert_array_equal(out["levels"], ref["levels"])
+    assert np.abs(out["final_boxes"] - ref["final_boxes"]).max() <= 1e-3
+    assert np.abs(out["fpn_box_feat"] - ref["fpn_box_feat"]).max() <= 5e-5 * max(1.0, np.abs(ref["fpn_box_feat"]).max())
+    eng.close()
+
+
+def test_fp16_precision_is_close():
+    cfg, eng, out, ref, _ = _case("efficientdet-d0", 256, 384, precision="fp16", fpn_cell_repeats=2, box_class_repeats=2)
+    for l in range(3, 8):
+        g, r = eng.stage("cls%d" % l), ref["cls_out"][l]
+        assert np.abs(g - r).max() <= 2e-2 * max(1.0, np.abs(r).max())
+    # set-based: near-tied candidates may swap order at fp16 accuracy
+    hits = 0
+    for b, lab in zip(out["final_boxes"], out["final_labels"]):
+        d = np.abs(ref["final_boxes"] - b).max(axis=1)
+        j = int(np.argmin(d))
+        hits += int(d[j] < 0.5 and ref["final_labels"][j] == lab)
+    assert hits >= 0.9 * len(ref["final_labels"])
+    eng.close()
+
+
+def test_ties_resolve_to_lowest_index():
+    # all class logits equal (zero pointwise kernel, constant bias): tf.nn.top_k keeps the lowest flat indices
+    from object_detection_tracking_b200.effdet import EffdetEngine
+    from object_detection_tracking_b200.effdet_config import make_effdet_config
+    from object_detection_tracking_b200.synth import synth_effdet_weights
+    from oracle import effdet as oe
+    cfg = make_effdet_config("efficientdet-d0", 128, 128, fpn_cell_repeats=1, box_class_repeats=1, max_detection_topk=700)
+    W = synth_effdet_weights(cfg)
+    W["class_net/class-predict/pointwise_kernel"] = np.zeros_like(W["class_net/class-predict/pointwise_kernel"])
+    W["class_net/class-predict/bias"] = np.full_like(W["class_net/class-predict/bias"], -1.0)
+    feats = _features(cfg)
+    ref = oe.forward_from_features(cfg, W, feats, image_scale=1.0)
+    eng = EffdetEngine(cfg, W)
+    out = eng.run_features(feats, image_scale=1.0)
+    np.testing.assert_array_equal(out["final_labels"], ref["final_labels"])
+    np.testing.assert_array_equal(out["levels"], ref["levels"])
+    assert np.abs(out["final_boxes"] - ref["final_boxes"]).max() <= 1e-3
+    eng.close()
+
+
+def test_missing_weight_fails_loudly():
+    from object_detection_tracking_b200.effdet import EffdetEngine
+    from object_detection_tracking_b200.effdet_config import make_effdet_config
+    from object_detection_tracking_b200.synth import synth_effdet_weights
+    cfg = make_effdet_config("efficientdet-d0", 128, 128, fpn_cell_repeats=1, box_class_repeats=1)
+    W = synth_effdet_weights(cfg)
+    del W["box_net/box-predict/bias"]
+    with pytest.raises(RuntimeError, match="missing weight"):
+        EffdetEngine(cfg, W)
