@@ -131,6 +131,8 @@ typedef struct b2_effdet_config {
   int result_per_im;               /* 100 */
   float nms_iou_threshold, result_score_thres;
   int precision;                   /* 0 fp16, 1 split (fp32-class) */
+  int backbone;                    /* -1: none (b2_effdet_run_features only); 0..7: EfficientNet-b0..b7 trunk
+                                    * (efficientdet_arch.py:396-437, backbone/efficientnet_model.py:504-704) */
 } b2_effdet_config;
 typedef struct b2_effdet b2_effdet;
 int b2_effdet_create(b2_effdet** out, const b2_effdet_config* cfg, int device);
@@ -141,7 +143,12 @@ int b2_effdet_load_weights(b2_effdet* ctx, const char* const* names, const float
  * scores, classes (1-based), levels, box_feat [max][fpn_num_filters]; *count = number of valid rows. */
 int b2_effdet_run_features(b2_effdet* ctx, const float* c3, const float* c4, const float* c5, float image_scale,
                            float* boxes, float* scores, int32_t* classes, int32_t* levels, float* box_feat, int32_t* count);
-/* Stage tensors of the last pass (parity tests): "fpn3".."fpn7", "cls3".."cls7", "box3".."box7" as fp32 NHWC */
+/* The wrapper's whole per-frame path (efficientdet_wrapper.py:40-111): host BGR uint8 frame [h,w,3] -> build_preprocess
+ * (RGB, /255, mean/std, bilinear resize to fit image_h x image_w, zero-pad) -> backbone -> BiFPN -> heads -> detections
+ * in frame pixels.  *image_scale_out = image_scale_to_original.  Needs cfg.backbone >= 0. */
+int b2_effdet_detect(b2_effdet* ctx, const uint8_t* frame_bgr, int h, int w, float* boxes, float* scores,
+                     int32_t* classes, int32_t* levels, float* box_feat, int32_t* count, float* image_scale_out);
+/* Stage tensors of the last pass (parity tests): "image", "stem", "block_<i>", "c3".."c5", "fpn3".."fpn7", "cls3".."cls7", "box3".."box7" as fp32 NHWC */
 int b2_effdet_get_stage(b2_effdet* ctx, const char* name, float* dst_host, int64_t capacity_bytes, int64_t shape[4]);
 int b2_effdet_num_launches(b2_effdet* ctx);
 

@@ -138,6 +138,88 @@ class Mask_RCNN_FPN_multi(Mask_RCNN_FPN):
     is_multi = True
 
 
+class EfficientDet:
+    """EfficientDet model object (reference: efficientdet_wrapper.py:12-111 `EfficientDet`): same five attributes and
+    `get_feed_dict_forward` as Mask_RCNN_FPN; the whole graph -- build_preprocess (uint8 BGR frame -> RGB, /255,
+    mean/std, bilinear fit to (short_edge_size, max_size), zero pad), EfficientNet backbone, BiFPN, class/box nets,
+    top-k + class-agnostic NMS, own-level ROIAlign feature -- runs in libb200det (b2_effdet_*).
+    Outputs: boxes x1,y1,x2,y2 in the pixels of the frame that was fed (the graph multiplies by
+    image_scale_to_original itself, wrapper :350-353), labels int32 in 1..num_classes (1..len(partial_classes) with
+    use_partial_classes), probs float32, fpn_box_feat [R, fpn_num_filters]."""
+
+    is_multi = False
+
+    def __init__(self, config, gpuid=0, precision="split"):
+        from .effdet_config import BACKBONE_OF, make_effdet_config
+        self.config = config
+        self.gpuid = gpuid
+        self.precision = precision
+        name = getattr(config, "efficientdet_modelname", "efficientdet-d0")
+        over = dict(min_level=int(getattr(config, "efficientdet_min_level", 3)),
+                    max_level=int(getattr(config, "efficientdet_max_level", 7)),
+                    max_detection_topk=int(getattr(config, "efficientdet_max_detection_topk", 5000)),
+                    result_score_thres=float(getattr(config, "result_score_thres", 1e-4)),
+                    result_per_im=int(getattr(config, "result_per_im", 100)))
+        # get_efficientdet_config (wrapper :160-252): image_size = (short_edge_size, max_size)
+        self.eff_config = make_effdet_config(name, int(config.short_edge_size), int(config.max_size), **over)
+        self.backbone_name = BACKBONE_OF[name]
+        self.partial_class_idxs = []
+        if getattr(config, "use_partial_classes", False):
+            from .class_ids import coco_id_mapping_reverse
+            self.partial_class_idxs = [coco_id_mapping_reverse[c] - 1 for c in config.partial_classes]
+            self.eff_config.num_classes = len(self.partial_class_idxs)
+        self.image = TensorHandle(self, "image:0")
+        self.final_boxes = TensorHandle(self, "final_boxes:0")          # wrapper :31-35
+        self.final_labels = TensorHandle(self, "final_labels:0")
+        self.final_probs = TensorHandle(self, "final_probs:0")
+        self.fpn_box_feat = TensorHandle(self, "fpn_box_feat:0")
+        self._engine = None
+        self._weights = None
+
+    def set_weights(self, weights: dict):
+        """TF checkpoint variables (efficientdet_arch.py / efficientnet_model.py names, kernels HWIO).  With
+        use_partial_classes the class-predict columns are gathered here, which is what the graph's tf.gather on the
+        class logits (wrapper :398-404) computes."""
+        w = {k: np.asarray(v, dtype=np.float32) for k, v in weights.items()}
+        if self.partial_class_idxs:
+            na = self.eff_config.num_scales * len(self.eff_config.aspect_ratios)
+            full = w["class_net/class-predict/bias"].shape[0] // na
+            cols = np.concatenate([a * full + np.asarray(self.partial_class_idxs) for a in range(na)])
+            w["class_net/class-predict/pointwise_kernel"] = w["class_net/class-predict/pointwise_kernel"][..., cols]
+            w["class_net/class-predict/bias"] = w["class_net/class-predict/bias"][cols]
+        self._weights = w
+        if self._engine is not None:
+            self._engine.load_weights(w)
+
+    def load_npz(self, path: str):
+        with np.load(path) as z:
+            self.set_weights({(k[:-2] if k.endswith(":0") else k): z[k] for k in z.files})
+
+    def get_feed_dict_forward(self, imgdata):
+        """wrapper :105-111: {image placeholder (uint8 [h,w,3] BGR): frame}."""
+        return {self.image: imgdata}
+
+    def _run(self, fetches, feed_dict):
+        from .effdet import EffdetEngine
+        if self._engine is None:
+            if self._weights is None:
+                raise RuntimeError("model has no weights: call set_weights()/load_npz() first")
+            self._engine = EffdetEngine(self.eff_config, self._weights, device=self.gpuid, precision=self.precision,
+                                        backbone=self.backbone_name)
+        frame = np.asarray(feed_dict[self.image])
+        if frame.dtype != np.uint8:
+            frame = frame.astype(np.uint8)          # the placeholder is uint8 (wrapper :19-21)
+        out = self._engine.detect(frame)
+        table = {id(self.final_boxes): out["final_boxes"], id(self.final_labels): out["final_labels"],
+                 id(self.final_probs): out["final_probs"], id(self.fpn_box_feat): out["fpn_box_feat"]}
+        res = []
+        for f in fetches:
+            if id(f) not in table:
+                raise KeyError("unknown fetch %r" % (f,))
+            res.append(table[id(f)].copy())
+        return res
+
+
 class Session:
     """`sess.run(fetches, feed_dict=...)` for fetches that all belong to one model object."""
 
@@ -162,6 +244,6 @@ def get_model(config, gpuid=0, task=0, controller="/cpu:0", is_multi=False, **kw
     """models.get_model (models.py:97-119).  `controller`/`task` are TF device-placement arguments with
     no meaning here; kept for signature compatibility."""
     if getattr(config, "is_efficientdet", False):
-        raise NotImplementedError("EfficientDet path (efficientdet_wrapper.py) is not built yet")
+        return EfficientDet(config, gpuid=gpuid, **kw)                  # models.py:112-113
     cls = Mask_RCNN_FPN_multi if is_multi else Mask_RCNN_FPN
     return cls(config, gpuid=gpuid, **kw)

@@ -43,6 +43,7 @@ struct EConv {
   ConvIO io;
   ConvPlan* plan = nullptr;
   int cin_real = 0, cout_real = 0;
+  float* w_master = nullptr;   // fp32 copy of the packed weights (projection convs re-scaled by the SE gate per frame)
 };
 
 struct EDw {
@@ -56,7 +57,26 @@ struct ECombine {
   std::string wnames[3];  // fast-attention scalars
 };
 
-struct EStep { int kind, idx; };   // 0 conv, 1 depthwise, 2 combine
+// backbone: depthwise KxK + BN + swish
+struct EDwBn {
+  std::string wname, bnname;
+  DwConvParams p;
+  float* w = nullptr;
+  float* bias = nullptr;
+  int creal = 0;
+};
+
+// backbone: squeeze-excite whose gate is folded into the projection conv's weights every frame
+struct ESe {
+  std::string pre;          // ".../blocks_i/se"
+  EPlanes x;
+  int creal = 0, nr = 0;
+  float *partial = nullptr, *gate = nullptr, *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
+  float* w_master = nullptr;   // BN-folded projection weights [Cout_pad][K] fp32
+  EConv* proj = nullptr;
+};
+
+struct EStep { int kind, idx; };   // 0 conv, 1 depthwise, 2 combine, 3 backbone depthwise, 4 squeeze-excite, 5 stem im2col
 
 struct F32Out { float* p = nullptr; int H = 0, W = 0, ld = 0, creal = 0; };
 
@@ -77,7 +97,16 @@ struct b2_effdet {
   std::vector<std::unique_ptr<EDw>> dws;
   std::vector<std::unique_ptr<ECombine>> combines;
   std::map<std::string, float*> dw_shared;    // depthwise kernels shared across levels
-  std::vector<EStep> steps;
+  std::vector<std::unique_ptr<EDwBn>> dwbns;
+  std::vector<std::unique_ptr<ESe>> ses;
+  std::vector<EStep> steps;          // feature network + heads
+  std::vector<EStep> bb_steps;       // backbone (only when cfg.backbone >= 0)
+  std::string bb_name;
+  float* image = nullptr;            // [H][W][3] fp32, pre-processed network input
+  uint8_t* frame = nullptr;          // device copy of the caller's BGR frame
+  size_t frame_cap = 0;
+  EPlanes stem_cols;
+  cudaGraphExec_t graph_full = nullptr;
   std::map<std::string, EPlanes> named;
   std::map<std::string, F32Out> named_f32;
   EPlanes backbone[3];
@@ -92,6 +121,7 @@ struct b2_effdet {
   float* out_feat = nullptr;
   cudaGraphExec_t graph = nullptr;
   bool loaded = false;
+  bool building_backbone = false;
 
   template <typename T>
   T* alloc(size_t n) {
@@ -129,7 +159,7 @@ EConv* add_pw(b2_effdet* c, const std::string& wname, const std::string& biasnam
   L->w.bias = c->alloc<float>(L->w.Cout_pad);
   L->io.in_hi = in.hi; L->io.in_lo = in.lo; L->io.out_hi = out.hi; L->io.out_lo = out.lo; L->io.out_f32 = out_f32;
   EConv* raw = L.get();
-  c->steps.push_back({0, static_cast<int>(c->convs.size())});
+  (c->building_backbone ? c->bb_steps : c->steps).push_back({0, static_cast<int>(c->convs.size())});
   c->convs.push_back(std::move(L));
   return raw;
 }
@@ -185,6 +215,111 @@ int add_pool(b2_effdet* c, const EPlanes& src, const EPlanes& dst) {
   return 0;
 }
 
+
+struct BlockSpec { int kernel, stride, expand, cin, cout; };
+
+int round_filters(double filters, double width) {
+  filters *= width;
+  int nf = static_cast<int>(filters + 4.0) / 8 * 8;      // efficientnet_model.py:137-151, divisor 8
+  if (nf < 8) nf = 8;
+  if (nf < 0.9 * filters) nf += 8;
+  return nf;
+}
+
+void same_pad(int n, int k, int s, int* out, int* before) {
+  *out = (n + s - 1) / s;
+  const int total = (*out - 1) * s + k - n;
+  *before = (total > 0 ? total : 0) / 2;
+}
+
+// EfficientNet-b{0..7} trunk up to reduction_5 (efficientnet_model.py:504-704); endpoints land in c->backbone[0..2]
+int build_backbone(b2_effdet* c) {
+  static const double kWidth[8] = {1.0, 1.0, 1.1, 1.2, 1.4, 1.6, 1.8, 2.0};
+  static const double kDepth[8] = {1.0, 1.1, 1.2, 1.4, 1.8, 2.2, 2.6, 3.1};
+  static const int kStage[7][6] = {{1, 3, 1, 1, 32, 16}, {2, 3, 2, 6, 16, 24}, {2, 5, 2, 6, 24, 40}, {3, 3, 2, 6, 40, 80},
+                                   {3, 5, 1, 6, 80, 112}, {4, 5, 2, 6, 112, 192}, {1, 3, 1, 6, 192, 320}};
+  const b2_effdet_config& g = c->cfg;
+  B2_CHECK(g.backbone >= 0 && g.backbone <= 7, "effdet: backbone must be efficientnet-b0..b7");
+  const double width = kWidth[g.backbone], depth = kDepth[g.backbone];
+  c->bb_name = "efficientnet-b" + std::to_string(g.backbone);
+  std::vector<BlockSpec> blocks;
+  for (const auto& st : kStage) {
+    const int rep = static_cast<int>(ceil(depth * st[0])), ci = round_filters(st[4], width), co = round_filters(st[5], width);
+    blocks.push_back({st[1], st[2], st[3], ci, co});
+    for (int r = 1; r < rep; ++r) blocks.push_back({st[1], 1, st[3], co, co});
+  }
+  c->building_backbone = true;
+  const int H = g.image_h, W = g.image_w;
+  c->image = c->alloc<float>(static_cast<size_t>(H) * W * 3);
+  // stem: 3x3/2 SAME as a 1x1 conv over im2col-packed pixels (27 live of 64 operand channels)
+  int h = 0, w = 0, pt = 0, pl = 0;
+  same_pad(H, 3, 2, &h, &pt);
+  same_pad(W, 3, 2, &w, &pl);
+  c->stem_cols = c->planes(h, w, 64, 27);
+  c->bb_steps.push_back({5, pt * 65536 + pl});
+  const int stem_c = round_filters(32, width);
+  EPlanes x = c->planes(h, w, pad64(stem_c), stem_c);
+  add_pw(c, c->bb_name + "/stem/conv2d/kernel", "", c->bb_name + "/stem/tpu_batch_normalization", c->stem_cols, x, stem_c, 2);
+  c->named["stem"] = x;
+  int reduction = 0;   // reduction_k closes when the next block strides or at the last block (Model.call :644-668)
+  for (size_t i = 0; i < blocks.size(); ++i) {
+    const BlockSpec& b = blocks[i];
+    const std::string pre = c->bb_name + "/blocks_" + std::to_string(i);
+    B2_CHECK(x.creal == b.cin, "effdet backbone: channel bookkeeping mismatch");
+    const int mid = b.cin * b.expand;
+    EPlanes e = x;
+    std::string proj = "conv2d";
+    if (b.expand != 1) {
+      e = c->planes(x.H, x.W, pad64(mid), mid);
+      add_pw(c, pre + "/conv2d/kernel", "", pre + "/tpu_batch_normalization", x, e, mid, 2);
+      proj = "conv2d_1";
+    }
+    std::unique_ptr<EDwBn> D(new EDwBn());
+    int ho = 0, wo = 0, dpt = 0, dpl = 0;
+    same_pad(e.H, b.kernel, b.stride, &ho, &dpt);
+    same_pad(e.W, b.kernel, b.stride, &wo, &dpl);
+    EPlanes d = c->planes(ho, wo, e.C, mid);
+    D->wname = pre + "/depthwise_conv2d/depthwise_kernel"; D->bnname = pre + "/tpu_batch_normalization_1"; D->creal = mid;
+    D->w = c->alloc<float>(static_cast<size_t>(b.kernel) * b.kernel * e.C);
+    D->bias = c->alloc<float>(e.C);
+    D->p = DwConvParams{e.hi, e.lo, e.H, e.W, e.C, b.kernel, b.stride, dpt, dpl, ho, wo, D->w, D->bias, d.hi, d.lo};
+    c->bb_steps.push_back({3, static_cast<int>(c->dwbns.size())});
+    c->dwbns.push_back(std::move(D));
+    // squeeze-excite (se_ratio 0.25 of the block's input filters)
+    std::unique_ptr<ESe> S(new ESe());
+    S->pre = pre + "/se"; S->x = d; S->creal = mid; S->nr = b.cin / 4 > 1 ? b.cin / 4 : 1;
+    S->partial = c->alloc<float>(static_cast<size_t>(se_chunks(ho * wo)) * d.C);
+    S->gate = c->alloc<float>(d.C);
+    S->w1 = c->alloc<float>(static_cast<size_t>(mid) * S->nr); S->b1 = c->alloc<float>(S->nr);
+    S->w2 = c->alloc<float>(static_cast<size_t>(S->nr) * mid); S->b2 = c->alloc<float>(mid);
+    ESe* se = S.get();
+    c->bb_steps.push_back({4, static_cast<int>(c->ses.size())});
+    c->ses.push_back(std::move(S));
+    // projection (+ identity skip when the block keeps shape, efficientnet_model.py:381-390)
+    EPlanes y = c->planes(ho, wo, pad64(b.cout), b.cout);
+    EConv* P = add_pw(c, pre + "/" + proj + "/kernel", "", pre + "/tpu_batch_normalization_2", d, y, b.cout, 0);
+    if (b.stride == 1 && b.cin == b.cout) {
+      P->d.res_H = x.H; P->d.res_W = x.W; P->d.ldr = x.C;
+      P->io.res_hi = x.hi; P->io.res_lo = x.lo;
+    }
+    se->proj = P;
+    se->w_master = c->alloc<float>(static_cast<size_t>(P->w.Cout_pad) * P->w.K);
+    P->w_master = se->w_master;
+    x = y;
+    c->named["block_" + std::to_string(i)] = x;
+    if (i + 1 == blocks.size() || blocks[i + 1].stride > 1) {
+      const int lvl = ++reduction;
+      if (lvl >= 3 && lvl <= 5) {
+        B2_CHECK(x.creal == g.backbone_channels[lvl - 3], "effdet: backbone_channels do not match the backbone's endpoints");
+        B2_CHECK(x.H == c->fh[lvl] && x.W == c->fw[lvl], "effdet: backbone endpoint size mismatch");
+        c->backbone[lvl - 3] = x;
+      }
+    }
+  }
+  c->building_backbone = false;
+  return 0;
+}
+
 int build(b2_effdet* c) {
   const b2_effdet_config& g = c->cfg;
   B2_CHECK(g.min_level == 3 && g.max_level == 7, "effdet: levels 3..7 only (the reference's configuration)");
@@ -200,10 +335,12 @@ int build(b2_effdet* c) {
     }
   }
   std::vector<EPlanes> feats;
+  if (g.backbone >= 0 && build_backbone(c)) return -1;
   for (int i = 0; i < 3; ++i) {
     const int cr = g.backbone_channels[i];
-    c->backbone[i] = c->planes(c->fh[3 + i], c->fw[3 + i], pad64(cr), cr);
+    if (g.backbone < 0) c->backbone[i] = c->planes(c->fh[3 + i], c->fw[3 + i], pad64(cr), cr);
     feats.push_back(c->backbone[i]);
+    c->named["c" + std::to_string(3 + i)] = c->backbone[i];
   }
   // P6, P7 (arch.py:464-480): resample_p6 = [conv1x1 + BN] + max-pool, resample_p7 = max-pool
   for (int level = 6; level <= 7; ++level) {
@@ -347,17 +484,36 @@ int build(b2_effdet* c) {
   return 0;
 }
 
-int enqueue(b2_effdet* c) {
+int run_step(b2_effdet* c, const EStep& s) {
   cudaStream_t st = c->stream;
-  for (const EStep& s : c->steps) {
-    int rc = -1;
-    if (s.kind == 0) rc = conv_tc_launch(c->convs[s.idx]->plan, st);
-    else if (s.kind == 1) {
+  switch (s.kind) {
+    case 0: return conv_tc_launch(c->convs[s.idx]->plan, st);
+    case 1: {
       const EDw* d = c->dws[s.idx].get();
-      rc = dw3x3_plain_launch(d->in.hi, d->in.lo, 1, d->in.H, d->in.W, d->in.C, d->w, d->out.hi, d->out.lo, st);
-    } else rc = bifpn_combine_launch(c->combines[s.idx]->p, st);
-    if (rc) return -1;
+      return dw3x3_plain_launch(d->in.hi, d->in.lo, 1, d->in.H, d->in.W, d->in.C, d->w, d->out.hi, d->out.lo, st);
+    }
+    case 2: return bifpn_combine_launch(c->combines[s.idx]->p, st);
+    case 3: return dwconv_bn_swish_launch(c->dwbns[s.idx]->p, st);
+    case 4: {
+      const ESe* e = c->ses[s.idx].get();
+      if (se_gate_launch(e->x.hi, e->x.lo, e->x.H * e->x.W, e->x.C, e->creal, e->nr, e->partial, e->w1, e->b1, e->w2, e->b2,
+                         e->gate, st)) return -1;
+      return se_scale_weights_launch(e->w_master, e->gate, e->proj->w.Cout_pad, e->proj->w.K, e->proj->w.w_hi, e->proj->w.w_lo, st);
+    }
+    case 5:
+      return stem_im2col_launch(c->image, c->cfg.image_h, c->cfg.image_w, c->stem_cols.H, c->stem_cols.W, s.idx / 65536,
+                                s.idx % 65536, c->stem_cols.hi, c->stem_cols.lo, st);
   }
+  return -1;
+}
+
+int enqueue(b2_effdet* c, bool with_backbone) {
+  cudaStream_t st = c->stream;
+  if (with_backbone)
+    for (const EStep& s : c->bb_steps)
+      if (run_step(c, s)) return -1;
+  for (const EStep& s : c->steps)
+    if (run_step(c, s)) return -1;
   if (effdet_post_launch(c->post, c->scale_dev, st)) return -1;
   return level_roi_feat_launch(c->roi, st);
 }
@@ -374,6 +530,39 @@ struct WS {
     return it->second.first;
   }
 };
+
+
+int launch_and_fetch(b2_effdet* c, bool full, float image_scale, float* boxes, float* scores, int* classes, int* levels,
+                     float* box_feat, int* count) {
+  B2_CUDA(cudaMemcpyAsync(c->scale_dev, &image_scale, 4, cudaMemcpyHostToDevice, c->stream));
+  cudaGraphExec_t& graph = full ? c->graph_full : c->graph;
+  if (getenv("B2_EFFDET_NO_GRAPH") != nullptr) {
+    if (enqueue(c, full)) return -1;
+  } else {
+    if (!graph) {
+      if (enqueue(c, full)) return -1;           // eager warm-up before the capture
+      B2_CUDA(cudaStreamSynchronize(c->stream));
+      cudaGraph_t g = nullptr;
+      B2_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = enqueue(c, full);
+      cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+      if (rc) return -1;
+      B2_CUDA(e);
+      B2_CUDA(cudaGraphInstantiate(&graph, g, 0));
+      B2_CUDA(cudaGraphDestroy(g));
+    }
+    B2_CUDA(cudaGraphLaunch(graph, c->stream));
+  }
+  const int m = c->post.max_out;
+  B2_CUDA(cudaMemcpyAsync(boxes, c->out_boxes, sizeof(float) * 4 * m, cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaMemcpyAsync(scores, c->out_scores, sizeof(float) * m, cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaMemcpyAsync(classes, c->out_classes, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
+  if (levels) B2_CUDA(cudaMemcpyAsync(levels, c->out_levels, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
+  if (box_feat) B2_CUDA(cudaMemcpyAsync(box_feat, c->out_feat, sizeof(float) * m * c->F, cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaMemcpyAsync(count, c->out_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
 
 }  // namespace
 
@@ -402,8 +591,10 @@ void b2_effdet_destroy(b2_effdet* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   if (c->graph) cudaGraphExecDestroy(c->graph);
+  if (c->graph_full) cudaGraphExecDestroy(c->graph_full);
   for (auto& L : c->convs) if (L->plan) conv_tc_plan_destroy(L->plan);
   for (void* p : c->allocs) cudaFree(p);
+  if (c->frame) cudaFree(c->frame);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -417,8 +608,8 @@ int b2_effdet_load_weights(b2_effdet* c, const char* const* names, const float* 
   for (auto& L : c->convs) {
     const int K = L->w.K, Cp = L->w.Cout_pad, co = L->cout_real, ci = L->cin_real;
     const float* w = ws.get(L->wname, static_cast<int64_t>(ci) * co);
-    const float* b = ws.get(L->biasname, co);
-    if (!w || !b) return -1;
+    const float* b = L->biasname.empty() ? nullptr : ws.get(L->biasname, co);   // backbone convs have no bias
+    if (!w || (!b && !L->biasname.empty())) return -1;
     std::vector<double> scale(co, 1.0), shift(co, 0.0);
     if (!L->bnname.empty()) {
       const float* ga = ws.get(L->bnname + "/gamma", co);
@@ -434,12 +625,13 @@ int b2_effdet_load_weights(b2_effdet* c, const char* const* names, const float* 
     std::vector<float> packed(static_cast<size_t>(Cp) * K, 0.f), bias(Cp, 0.f);
     for (int o = 0; o < co; ++o) {
       for (int i = 0; i < ci; ++i) packed[static_cast<size_t>(o) * K + i] = static_cast<float>(w[static_cast<size_t>(i) * co + o] * scale[o]);
-      bias[o] = static_cast<float>(static_cast<double>(b[o]) * scale[o] + shift[o]);
+      bias[o] = static_cast<float>((b ? static_cast<double>(b[o]) : 0.0) * scale[o] + shift[o]);
     }
     float* tmp = nullptr;
     B2_CUDA(cudaMalloc(&tmp, packed.size() * 4));
     B2_CUDA(cudaMemcpyAsync(tmp, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, c->stream));
     if (f32_to_planes(tmp, L->w.w_hi, L->w.w_lo, packed.size(), c->stream)) return -1;
+    if (L->w_master) B2_CUDA(cudaMemcpyAsync(L->w_master, tmp, packed.size() * 4, cudaMemcpyDeviceToDevice, c->stream));
     B2_CUDA(cudaMemcpyAsync(L->w.bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     B2_CUDA(cudaFree(tmp));
@@ -452,6 +644,37 @@ int b2_effdet_load_weights(b2_effdet* c, const char* const* names, const float* 
     for (int t = 0; t < 9; ++t)
       for (int ch = 0; ch < cr; ++ch) pw[static_cast<size_t>(t) * C + ch] = w[t * cr + ch];
     B2_CUDA(cudaMemcpyAsync(kv.second, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  for (auto& D : c->dwbns) {
+    const int C = D->p.C, cr = D->creal, kk = D->p.K * D->p.K;
+    const float* w = ws.get(D->wname, static_cast<int64_t>(kk) * cr);   // [K,K,C,1]
+    const float* ga = ws.get(D->bnname + "/gamma", cr);
+    const float* be = ws.get(D->bnname + "/beta", cr);
+    const float* mm = ws.get(D->bnname + "/moving_mean", cr);
+    const float* mv = ws.get(D->bnname + "/moving_variance", cr);
+    if (!w || !ga || !be || !mm || !mv) return -1;
+    std::vector<float> pw(static_cast<size_t>(kk) * C, 0.f), pb(C, 0.f);
+    for (int ch = 0; ch < cr; ++ch) {
+      const double sc = static_cast<double>(ga[ch]) / sqrt(static_cast<double>(mv[ch]) + 1e-3);
+      for (int t = 0; t < kk; ++t) pw[static_cast<size_t>(t) * C + ch] = static_cast<float>(w[t * cr + ch] * sc);
+      pb[ch] = static_cast<float>(static_cast<double>(be[ch]) - static_cast<double>(mm[ch]) * sc);
+    }
+    B2_CUDA(cudaMemcpyAsync(D->w, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(D->bias, pb.data(), pb.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  for (auto& S : c->ses) {
+    const int m = S->creal, r = S->nr;
+    const float* w1 = ws.get(S->pre + "/conv2d/kernel", static_cast<int64_t>(m) * r);
+    const float* b1 = ws.get(S->pre + "/conv2d/bias", r);
+    const float* w2 = ws.get(S->pre + "/conv2d_1/kernel", static_cast<int64_t>(r) * m);
+    const float* b2 = ws.get(S->pre + "/conv2d_1/bias", m);
+    if (!w1 || !b1 || !w2 || !b2) return -1;
+    B2_CUDA(cudaMemcpyAsync(S->w1, w1, sizeof(float) * m * r, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(S->b1, b1, sizeof(float) * r, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(S->w2, w2, sizeof(float) * r * m, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(S->b2, b2, sizeof(float) * m, cudaMemcpyHostToDevice, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
   }
   if (c->cfg.fpn_weight_method == 1) {
@@ -473,6 +696,7 @@ int b2_effdet_load_weights(b2_effdet* c, const char* const* names, const float* 
   }
   c->loaded = true;
   if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
+  if (c->graph_full) { cudaGraphExecDestroy(c->graph_full); c->graph_full = nullptr; }
   return 0;
 }
 
@@ -497,33 +721,38 @@ int b2_effdet_run_features(b2_effdet* c, const float* c3, const float* c4, const
     B2_CUDA(cudaStreamSynchronize(c->stream));
     B2_CUDA(cudaFree(tmp));
   }
-  B2_CUDA(cudaMemcpyAsync(c->scale_dev, &image_scale, 4, cudaMemcpyHostToDevice, c->stream));
-  if (getenv("B2_EFFDET_NO_GRAPH") != nullptr) {
-    if (enqueue(c)) return -1;
-  } else {
-    if (!c->graph) {
-      if (enqueue(c)) return -1;                 // eager warm-up before the capture
-      B2_CUDA(cudaStreamSynchronize(c->stream));
-      cudaGraph_t g = nullptr;
-      B2_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-      const int rc = enqueue(c);
-      cudaError_t e = cudaStreamEndCapture(c->stream, &g);
-      if (rc) return -1;
-      B2_CUDA(e);
-      B2_CUDA(cudaGraphInstantiate(&c->graph, g, 0));
-      B2_CUDA(cudaGraphDestroy(g));
-    }
-    B2_CUDA(cudaGraphLaunch(c->graph, c->stream));
+  return launch_and_fetch(c, false, image_scale, boxes, scores, classes, levels, box_feat, count);
+}
+
+// Full per-frame path of the reference wrapper (EfficientDet.build_preprocess + build_model): host BGR uint8 frame
+// [h,w,3] -> pre-process (RGB, /255, mean/std, bilinear resize to fit, zero-pad) -> backbone -> BiFPN -> heads ->
+// detections scaled back to the frame.  *image_scale_out = image_scale_to_original.
+int b2_effdet_detect(b2_effdet* c, const uint8_t* frame_bgr, int h, int w, float* boxes, float* scores, int* classes,
+                     int* levels, float* box_feat, int* count, float* image_scale_out) {
+  B2_CHECK(c && frame_bgr && boxes && scores && classes && count, "b2_effdet_detect: null argument");
+  B2_CHECK(h >= 1 && w >= 1, "b2_effdet_detect: empty frame");
+  B2_CUDA(cudaSetDevice(c->device));
+  B2_CHECK(c->loaded, "b2_effdet_detect: weights not loaded");
+  B2_CHECK(c->cfg.backbone >= 0, "b2_effdet_detect: the context was created without a backbone (use b2_effdet_run_features)");
+  const size_t bytes = static_cast<size_t>(h) * w * 3;
+  if (bytes > c->frame_cap) {
+    if (c->frame) B2_CUDA(cudaFree(c->frame));
+    c->frame = nullptr; c->frame_cap = 0;
+    B2_CUDA(cudaMalloc(&c->frame, bytes));
+    c->frame_cap = bytes;
   }
-  const int m = c->post.max_out;
-  B2_CUDA(cudaMemcpyAsync(boxes, c->out_boxes, sizeof(float) * 4 * m, cudaMemcpyDeviceToHost, c->stream));
-  B2_CUDA(cudaMemcpyAsync(scores, c->out_scores, sizeof(float) * m, cudaMemcpyDeviceToHost, c->stream));
-  B2_CUDA(cudaMemcpyAsync(classes, c->out_classes, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
-  if (levels) B2_CUDA(cudaMemcpyAsync(levels, c->out_levels, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
-  if (box_feat) B2_CUDA(cudaMemcpyAsync(box_feat, c->out_feat, sizeof(float) * m * c->F, cudaMemcpyDeviceToHost, c->stream));
-  B2_CUDA(cudaMemcpyAsync(count, c->out_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  B2_CUDA(cudaStreamSynchronize(c->stream));
-  return 0;
+  // set_scale_factors_to_output_size (dataloader.py:101-113), float32 like the TF graph
+  const float sy = static_cast<float>(c->cfg.image_h) / static_cast<float>(h);
+  const float sx = static_cast<float>(c->cfg.image_w) / static_cast<float>(w);
+  const float scale = sx < sy ? sx : sy;
+  int sh = static_cast<int>(static_cast<float>(h) * scale), sw = static_cast<int>(static_cast<float>(w) * scale);
+  if (sh > c->cfg.image_h) sh = c->cfg.image_h;
+  if (sw > c->cfg.image_w) sw = c->cfg.image_w;
+  const float image_scale = 1.0f / scale;
+  if (image_scale_out) *image_scale_out = image_scale;
+  B2_CUDA(cudaMemcpyAsync(c->frame, frame_bgr, bytes, cudaMemcpyHostToDevice, c->stream));
+  if (effnet_preprocess_launch(c->frame, h, w, sh, sw, c->image, c->cfg.image_h, c->cfg.image_w, c->stream)) return -1;
+  return launch_and_fetch(c, true, image_scale, boxes, scores, classes, levels, box_feat, count);
 }
 
 // Stage-addressable tensors of the last pass as fp32 NHWC: "fpn3".."fpn7" (BiFPN outputs, channel-padded),
@@ -539,6 +768,14 @@ int b2_effdet_get_stage(b2_effdet* c, const char* name, float* dst, int64_t capa
     const int64_t n = static_cast<int64_t>(o.H) * o.W * o.ld;
     B2_CHECK(capacity >= n * 4, "b2_effdet_get_stage: buffer too small");
     B2_CUDA(cudaMemcpyAsync(dst, o.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+  }
+  if (std::string(name) == "image" && c->image) {
+    shape[0] = 1; shape[1] = c->cfg.image_h; shape[2] = c->cfg.image_w; shape[3] = 3;
+    const int64_t n = static_cast<int64_t>(c->cfg.image_h) * c->cfg.image_w * 3;
+    B2_CHECK(capacity >= n * 4, "b2_effdet_get_stage: buffer too small");
+    B2_CUDA(cudaMemcpyAsync(dst, c->image, n * 4, cudaMemcpyDeviceToHost, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
   }
@@ -559,7 +796,10 @@ int b2_effdet_get_stage(b2_effdet* c, const char* name, float* dst, int64_t capa
 
 int b2_effdet_num_launches(b2_effdet* c) {
   if (!c) return -1;
-  return static_cast<int>(c->steps.size()) + 15;   // + seed, 4 x (hist, pick), collect, tie scan, tie write, prepare, mask, scan, roi feature
+  int bb = 0;
+  for (const EStep& s : c->bb_steps) bb += s.kind == 4 ? 3 : 1;
+  if (bb) bb += 1;   // pre-processing
+  return bb + static_cast<int>(c->steps.size()) + 15;   // + seed, 4 x (hist, pick), collect, tie scan, tie write, prepare, mask, scan, roi feature
 }
 
 }  // extern "C"

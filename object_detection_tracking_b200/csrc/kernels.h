@@ -135,6 +135,27 @@ struct EffdetPostParams {
 int effdet_topk_blocks();
 int effdet_post_launch(const EffdetPostParams& p, const float* image_scale_dev, cudaStream_t s);
 
+// effnet.cu -- EfficientNet backbone pieces + EfficientDet input pre-processing
+int effnet_preprocess_launch(const uint8_t* img_bgr, int h, int w, int sh, int sw, float* out, int H, int W, cudaStream_t s);
+int stem_im2col_launch(const float* img, int H, int W, int Ho, int Wo, int pad_t, int pad_l, __half* out_hi, __half* out_lo,
+                       cudaStream_t s);
+struct DwConvParams {
+  const __half* in_hi;
+  const __half* in_lo;
+  int H, W, C;              // input map (batch 1), C multiple of 8
+  int K, stride, pad_t, pad_l;
+  int Ho, Wo;
+  const float* w;           // [K*K][C], BatchNorm scale folded in
+  const float* bias;        // [C], BatchNorm shift
+  __half* out_hi;
+  __half* out_lo;
+};
+int dwconv_bn_swish_launch(const DwConvParams& p, cudaStream_t s);
+int se_chunks(int HW);      // rows of the partial-sum buffer se_gate_launch needs
+int se_gate_launch(const __half* in_hi, const __half* in_lo, int HW, int Cpad, int C, int nr, float* partial, const float* w1,
+                   const float* b1, const float* w2, const float* b2, float* gate, cudaStream_t s);
+int se_scale_weights_launch(const float* w, const float* gate, int rows, int K, __half* hi, __half* lo, cudaStream_t s);
+
 // roialign.cu -- ROIAlign 7x7 on the detection's own level + mean over the 49 bins (efficientdet_wrapper.py:265-301)
 struct LevelRoiFeatParams {
   const __half* feat_hi[5];

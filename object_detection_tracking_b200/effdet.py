@@ -10,8 +10,9 @@ from . import _lib
 from .effdet_config import make_effdet_config  # noqa: F401  (re-export)
 
 
-def _c_config(cfg, precision: str) -> _lib.B2EffdetConfig:
+def _c_config(cfg, precision: str, backbone) -> _lib.B2EffdetConfig:
     c = _lib.B2EffdetConfig()
+    c.backbone = -1 if backbone is None else int(str(backbone)[-1])
     c.image_h, c.image_w = int(cfg.image_size[0]), int(cfg.image_size[1])
     c.min_level, c.max_level = int(cfg.min_level), int(cfg.max_level)
     c.fpn_num_filters = int(cfg.fpn_num_filters)
@@ -35,11 +36,12 @@ def _c_config(cfg, precision: str) -> _lib.B2EffdetConfig:
 class EffdetEngine:
     """Feature network + heads + post-processing of one EfficientDet configuration on one GPU."""
 
-    def __init__(self, cfg, weights: dict, device: int = 0, precision: str = "split"):
+    def __init__(self, cfg, weights: dict, device: int = 0, precision: str = "split", backbone=None):
+        """backbone: None (features in, run_features only) or "efficientnet-b0".."efficientnet-b7" (detect())."""
         self.cfg = cfg
         self._lib = _lib.load()
         self._h = ctypes.c_void_p()
-        cc = _c_config(cfg, precision)
+        cc = _c_config(cfg, precision, backbone)
         _lib.check(self._lib.b2_effdet_create(ctypes.byref(self._h), ctypes.byref(cc), int(device)), "b2_effdet_create")
         self.load_weights(weights)
 
@@ -71,21 +73,46 @@ class EffdetEngine:
         return dict(final_boxes=boxes[:n], final_probs=scores[:n], final_labels=classes[:n], levels=levels[:n],
                     fpn_box_feat=feat[:n])
 
-    def stage(self, name: str) -> np.ndarray:
-        """'fpn3'..'fpn7' -> [H,W,F]; 'cls3'.. -> [H,W,A*num_classes]; 'box3'.. -> [H,W,A*4] (fp32)."""
-        lvl = int(name[-1])
-        fs_h, fs_w = self.cfg.image_size
-        for _ in range(lvl):
-            fs_h, fs_w = (fs_h - 1) // 2 + 1, (fs_w - 1) // 2 + 1
+    def detect(self, frame_bgr: np.ndarray) -> dict:
+        """One BGR uint8 frame [h,w,3] -> detections in frame pixels (efficientdet_wrapper.py:40-111)."""
+        frame = np.ascontiguousarray(frame_bgr, np.uint8)
+        if frame.ndim != 3 or frame.shape[2] != 3:
+            raise ValueError("frame must be [h, w, 3] uint8 BGR")
+        m, f = int(self.cfg.result_per_im), int(self.cfg.fpn_num_filters)
+        boxes = np.zeros((m, 4), np.float32)
+        scores = np.zeros(m, np.float32)
+        classes = np.zeros(m, np.int32)
+        levels = np.zeros(m, np.int32)
+        feat = np.zeros((m, f), np.float32)
+        count = np.zeros(1, np.int32)
+        scale = np.zeros(1, np.float32)
+        _lib.check(self._lib.b2_effdet_detect(
+            self._h, frame.ctypes.data, int(frame.shape[0]), int(frame.shape[1]), boxes.ctypes.data, scores.ctypes.data,
+            classes.ctypes.data, levels.ctypes.data, feat.ctypes.data, count.ctypes.data, scale.ctypes.data),
+            "b2_effdet_detect")
+        n = int(count[0])
+        return dict(final_boxes=boxes[:n], final_probs=scores[:n], final_labels=classes[:n], levels=levels[:n],
+                    fpn_box_feat=feat[:n], image_scale=float(scale[0]))
+
+    def stage(self, name: str, real: int = None) -> np.ndarray:
+        """'fpn3'..'fpn7' -> [H,W,F]; 'cls3'.. -> [H,W,A*num_classes]; 'box3'.. -> [H,W,A*4]; 'image' -> [H,W,3];
+        'stem' / 'block_<i>' / 'c3'..'c5' -> [h,w,C] (pass `real` to drop the operand channel padding)."""
         na = self.cfg.num_scales * len(self.cfg.aspect_ratios)
-        real = {"fpn": self.cfg.fpn_num_filters, "cls": na * self.cfg.num_classes, "box": na * 4}[name[:3]]
-        cap = fs_h * fs_w * (real + 64)
+        if real is None:
+            real = {"fpn": self.cfg.fpn_num_filters, "cls": na * self.cfg.num_classes, "box": na * 4,
+                    "ima": 3}.get(name[:3])
+            if name in ("c3", "c4", "c5"):
+                real = self.cfg.backbone_channels[int(name[1]) - 3]
+        cap = int(self.cfg.image_size[0]) * int(self.cfg.image_size[1]) * 64      # stride-2 maps have <= 64 channels
+        if name[:3] in ("cls", "box", "fpn") or name in ("c3", "c4", "c5"):
+            cap //= 4
         buf = np.zeros(cap, np.float32)
         shape = (ctypes.c_int64 * 4)()
         _lib.check(self._lib.b2_effdet_get_stage(self._h, name.encode(), buf.ctypes.data, buf.nbytes, shape),
                    "b2_effdet_get_stage")
         _, h, w, c = [int(v) for v in shape]
-        return buf[: h * w * c].reshape(h, w, c)[:, :, :real].copy()
+        out = buf[: h * w * c].reshape(h, w, c)
+        return (out if real is None else out[:, :, :real]).copy()
 
     @property
     def num_launches(self) -> int:

@@ -45,3 +45,38 @@ def feat_sizes(cfg):
         h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
         out.append((h, w))
     return out
+
+
+# EfficientNet backbone geometry (efficientnet_builder.py:37-52,172-178; efficientnet_model.py:137-159,535-584)
+_EFFNET = {"efficientnet-b0": (1.0, 1.0), "efficientnet-b1": (1.0, 1.1), "efficientnet-b2": (1.1, 1.2),
+           "efficientnet-b3": (1.2, 1.4), "efficientnet-b4": (1.4, 1.8), "efficientnet-b5": (1.6, 2.2),
+           "efficientnet-b6": (1.8, 2.6), "efficientnet-b7": (2.0, 3.1)}
+# (repeats, kernel, stride, expand, in, out, se_ratio)
+_EFFNET_STAGES = ((1, 3, 1, 1, 32, 16, 0.25), (2, 3, 2, 6, 16, 24, 0.25), (2, 5, 2, 6, 24, 40, 0.25),
+                  (3, 3, 2, 6, 40, 80, 0.25), (3, 5, 1, 6, 80, 112, 0.25), (4, 5, 2, 6, 112, 192, 0.25),
+                  (1, 3, 1, 6, 192, 320, 0.25))
+# efficientdet_wrapper.py:511-587: detector -> backbone
+BACKBONE_OF = {"efficientdet-d0": "efficientnet-b0", "efficientdet-d1": "efficientnet-b1", "efficientdet-d2": "efficientnet-b2",
+               "efficientdet-d3": "efficientnet-b3", "efficientdet-d4": "efficientnet-b4", "efficientdet-d5": "efficientnet-b5",
+               "efficientdet-d6": "efficientnet-b6", "efficientdet-d7": "efficientnet-b6"}
+
+
+def _round_filters(filters, width, divisor=8):
+    filters *= width
+    new = max(divisor, int(filters + divisor / 2) // divisor * divisor)
+    if new < 0.9 * filters:
+        new += divisor
+    return int(new)
+
+
+def efficientnet_blocks(name):
+    """-> (stem channels, [block(kernel, stride, expand, cin, cout, se)]) after width / depth scaling."""
+    import math
+    width, depth = _EFFNET[name]
+    out = []
+    for rep, k, s, e, ci, co, se in _EFFNET_STAGES:
+        ci, co, rep = _round_filters(ci, width), _round_filters(co, width), int(math.ceil(depth * rep))
+        out.append(SimpleNamespace(kernel=k, stride=s, expand=e, cin=ci, cout=co, se=se))
+        for _ in range(rep - 1):
+            out.append(SimpleNamespace(kernel=k, stride=1, expand=e, cin=co, cout=co, se=se))
+    return _round_filters(32, width), out

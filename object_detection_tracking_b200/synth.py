@@ -238,3 +238,44 @@ def synth_effdet_weights(cfg, seed: int = 99) -> dict:
     if "class_net/class-predict/bias" in W:
         W["class_net/class-predict/bias"] -= np.float32(3.0)     # mostly-negative logits, like a trained detector
     return W
+
+
+
+def synth_efficientnet_weights(name: str, seed: int = 77) -> dict:
+    """Seeded EfficientNet backbone weights in the keras variable naming of the reference graph
+    (efficientnet_model.py:162-392, 504-704); gains chosen so that activations stay O(1) through all blocks."""
+    from .effdet_config import efficientnet_blocks
+    rng = np.random.default_rng(seed)
+    stem_c, blocks = efficientnet_blocks(name)
+    W = {}
+
+    def bn(pre, c, g_lo=0.8, g_hi=1.2):
+        W[pre + "/gamma"] = rng.uniform(g_lo, g_hi, c).astype(np.float32)
+        W[pre + "/beta"] = (rng.standard_normal(c) * 0.1).astype(np.float32)
+        W[pre + "/moving_mean"] = (rng.standard_normal(c) * 0.1).astype(np.float32)
+        W[pre + "/moving_variance"] = rng.uniform(0.6, 1.4, c).astype(np.float32)
+
+    def conv(pre, k, cin, cout, gain, bias=None):
+        W[pre + "/kernel"] = (rng.standard_normal((k, k, cin, cout)) * np.sqrt(gain / (k * k * cin))).astype(np.float32)
+        if bias is not None:
+            W[pre + "/bias"] = (rng.standard_normal(cout) * 0.1 + bias).astype(np.float32)
+
+    conv(name + "/stem/conv2d", 3, 3, stem_c, 1.0)
+    bn(name + "/stem/tpu_batch_normalization", stem_c)
+    for i, b in enumerate(blocks):
+        pre = "%s/blocks_%d" % (name, i)
+        mid = b.cin * b.expand
+        proj = "conv2d"
+        if b.expand != 1:
+            conv(pre + "/conv2d", 1, b.cin, mid, 2.5)
+            bn(pre + "/tpu_batch_normalization", mid)
+            proj = "conv2d_1"
+        W[pre + "/depthwise_conv2d/depthwise_kernel"] = (
+            rng.standard_normal((b.kernel, b.kernel, mid, 1)) * np.sqrt(2.5 / (b.kernel ** 2))).astype(np.float32)
+        bn(pre + "/tpu_batch_normalization_1", mid)
+        nr = max(1, int(b.cin * b.se))
+        conv(pre + "/se/conv2d", 1, mid, nr, 1.0, bias=0.0)
+        conv(pre + "/se/conv2d_1", 1, nr, mid, 1.0, bias=0.5)
+        conv(pre + "/" + proj, 1, mid, b.cout, 2.0)
+        bn(pre + "/tpu_batch_normalization_2", b.cout, 0.45, 0.75)
+    return W

@@ -177,7 +177,7 @@ def decode_boxes(rel_codes, anchors):
     return np.stack([yc - h / f32(2), xc - w / f32(2), yc + h / f32(2), xc + w / f32(2)], 1).astype(f32)
 
 
-def postprocess(cls_out, box_out, cfg, fsizes, image_scale):
+def postprocess(cls_out, box_out, cfg, fsizes, image_scale, partial_class_idxs=None):
     """add_metric_fn_inputs (wrapper:367-474) + _generate_detections_tf (anchors.py:399-487).
     cls_out/box_out: {level: [H,W,A*C] / [H,W,A*4]} numpy.  Returns boxes x1y1x2y2 (scaled), scores, classes 1..90,
     level indexes -- canonical order = NMS selection order."""
@@ -185,6 +185,9 @@ def postprocess(cls_out, box_out, cfg, fsizes, image_scale):
     nc = cfg.num_classes
     na = cfg.num_scales * len(cfg.aspect_ratios)
     cls_all = np.concatenate([cls_out[l].reshape(-1, nc) for l in range(cfg.min_level, cfg.max_level + 1)], 0)
+    if partial_class_idxs:                                            # wrapper :398-411: tf.gather on the class axis
+        cls_all = np.ascontiguousarray(cls_all[:, list(partial_class_idxs)])
+        nc = len(partial_class_idxs)
     box_all = np.concatenate([box_out[l].reshape(-1, 4) for l in range(cfg.min_level, cfg.max_level + 1)], 0)
     lvl_all = np.concatenate([np.full(fsizes[l][0] * fsizes[l][1] * na, l, np.int32)
                               for l in range(cfg.min_level, cfg.max_level + 1)])
@@ -214,7 +217,7 @@ def box_features(fpn_feats, boxes, levels, cfg):
     return out
 
 
-def forward_from_features(cfg, W, features, image_scale=1.0, stages=False):
+def forward_from_features(cfg, W, features, image_scale=1.0, stages=False, partial_class_idxs=None):
     """BiFPN + heads + post-processing from backbone features {3,4,5: numpy [C,H,W]}."""
     from object_detection_tracking_b200.effdet_config import BIFPN_NODES, feat_sizes
     fs = feat_sizes(cfg)
@@ -222,7 +225,7 @@ def forward_from_features(cfg, W, features, image_scale=1.0, stages=False):
         feats = build_feature_network({l: _t(features[l])[None] for l in (3, 4, 5)}, W, cfg, BIFPN_NODES, fs)
         cls_out = {l: head_net(feats[l], W, l, cfg, "class")[0].permute(1, 2, 0).contiguous().numpy() for l in feats}
         box_out = {l: head_net(feats[l], W, l, cfg, "box")[0].permute(1, 2, 0).contiguous().numpy() for l in feats}
-    boxes, scores, classes, levels = postprocess(cls_out, box_out, cfg, fs, image_scale)
+    boxes, scores, classes, levels = postprocess(cls_out, box_out, cfg, fs, image_scale, partial_class_idxs)
     res = dict(final_boxes=boxes, final_probs=scores, final_labels=classes, levels=levels,
                fpn_box_feat=box_features(feats, boxes, levels, cfg))
     if stages:

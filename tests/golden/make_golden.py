@@ -130,6 +130,24 @@ def effdet_numpy():
     out["dec_boxes"] = ra.decode_box_outputs(codes.swapaxes(0, 1), anc.swapaxes(0, 1))
     logits = (rng.standard_normal(64) * 3).astype(np.float32)
     out["sig_logits"], out["sig_scores"] = logits, ra.sigmoid(logits)
+    # filter / repeat rounding of the backbone (efficientnet_model.py:137-159) for b0..b7
+    from types import SimpleNamespace
+    from efficientdet.backbone import efficientnet_model as em
+    table = {"b0": (1.0, 1.0), "b1": (1.0, 1.1), "b2": (1.1, 1.2), "b3": (1.2, 1.4), "b4": (1.4, 1.8), "b5": (1.6, 2.2),
+             "b6": (1.8, 2.6), "b7": (2.0, 3.1)}
+    base_f, base_r = [32, 16, 24, 40, 80, 112, 192, 320, 1280], [1, 2, 3, 4]
+    rf, rr = [], []
+    for k in sorted(table):
+        gp = SimpleNamespace(width_coefficient=table[k][0], depth_coefficient=table[k][1], depth_divisor=8, min_depth=None)
+        rf.append([em.round_filters(f, gp) for f in base_f])
+        rr.append([em.round_repeats(r, gp) for r in base_r])
+    out["round_filters"], out["round_repeats"] = np.array(rf, np.int64), np.array(rr, np.int64)
+    # COCO category table (class_ids.py:526-549)
+    import class_ids as rc
+    ids = sorted(rc.coco_id_mapping)
+    out["coco_ids"] = np.array(ids, np.int64)
+    out["coco_names"] = np.array([rc.coco_id_mapping[i] for i in ids])
+    out["coco_dense"] = np.array([rc.coco_obj_class_to_id[rc.coco_id_mapping[i]] for i in ids], np.int64)
     np.savez_compressed(os.path.join(HERE, "effdet_numpy.npz"), **out)
 
 

@@ -25,22 +25,27 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.b2_version() == 1
 
 
-def test_config_struct_matches_header_size():
-    # 15 int32 + 4 (resnet_blocks is 4 -> counted) ... computed from the header text
+def _header_struct_words(name):
     src = open(os.path.join(ROOT, "include", "b200det.h")).read()
-    body = src[src.index("typedef struct b2_config {") + len("typedef struct b2_config {"):src.index("} b2_config;")]
+    head = "typedef struct %s {" % name
+    body = src[src.index(head) + len(head):src.index("} %s;" % name)]
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     n = 0
     for decl in body.split(";"):
         decl = decl.strip()
-        m = re.match(r"(int32_t|float)\s+(.*)", decl)
+        m = re.match(r"(int32_t|int|float)\s+(.*)", decl)
         if not m:
             continue
         for var in m.group(2).split(","):
-            k = re.search(r"\[(\d+)\]", var)
-            n += int(k.group(1)) if k else 1
+            dims = [int(k) for k in re.findall(r"\[(\d+)\]", var)]
+            n += int(__import__("numpy").prod(dims)) if dims else 1
+    return n
+
+
+def test_config_structs_match_header_size():
     import ctypes
-    assert ctypes.sizeof(_lib.B2Config) == 4 * n
+    assert ctypes.sizeof(_lib.B2Config) == 4 * _header_struct_words("b2_config")
+    assert ctypes.sizeof(_lib.B2EffdetConfig) == 4 * _header_struct_words("b2_effdet_config")
 
 
 def test_compute_entry_points_fail_loudly_without_gpu():

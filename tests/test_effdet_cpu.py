@@ -93,3 +93,71 @@ def test_fast_attention_weights_are_used(tiny):
     W2["fpn_cells/cell_0/fnode0/WSM"] = np.float32(-1.0)         # relu -> 0: the first edge drops out of the node
     r2 = oe.forward_from_features(cfg, W2, feats, image_scale=1.5, stages=True)
     assert np.abs(r2["fpn"][6] - r["fpn"][6]).max() > 1e-3
+
+
+# ---- EfficientNet backbone geometry + pre-processing oracle -----------------------------------------------------------
+def test_filter_and_repeat_rounding_match_reference(golden):
+    from oracle import efficientnet as on
+    names = sorted(on.PARAMS)
+    base_f, base_r = [32, 16, 24, 40, 80, 112, 192, 320, 1280], [1, 2, 3, 4]
+    for row, name in enumerate(names):
+        width, depth = on.PARAMS[name]
+        assert [on.round_filters(f, width) for f in base_f] == list(golden["round_filters"][row])
+        assert [on.round_repeats(r, depth) for r in base_r] == list(golden["round_repeats"][row])
+
+
+def test_backbone_endpoints_match_the_detector_table():
+    from object_detection_tracking_b200.effdet_config import _TABLE, BACKBONE_OF, efficientnet_blocks
+    from oracle import efficientnet as on
+    for det, bb in BACKBONE_OF.items():
+        stem, blocks = on.block_specs(bb)
+        red = on.endpoint_blocks(blocks)
+        assert len(red) == 5
+        assert tuple(blocks[red[k]].cout for k in (2, 3, 4)) == _TABLE[det][5]
+        s2, b2 = efficientnet_blocks(bb)                              # the product package's own copy of the geometry
+        assert s2 == stem and [(b.kernel, b.stride, b.expand, b.cin, b.cout) for b in b2] == \
+            [(b.kernel, b.stride, b.expand, b.cin, b.cout) for b in blocks]
+    assert len(on.block_specs("efficientnet-b6")[1]) == 45
+
+
+def test_preprocess_resize_pad_and_scale():
+    from oracle import efficientnet as on
+    rng = np.random.default_rng(0)
+    frame = rng.integers(0, 256, (300, 500, 3)).astype(np.uint8)
+    img, scale = on.preprocess(frame, 256, 384)
+    assert img.shape == (256, 384, 3) and img.dtype == np.float32
+    assert abs(scale - 500 / 384) < 1e-6                              # width-limited: image_scale_to_original
+    sh = int(np.float32(300) * (np.float32(384) / np.float32(500)))
+    assert not img[sh:].any() and img[:sh].any()                      # zero padding below the resized frame
+    # pixel (0,0) maps to source (0,0): RGB order, /255, mean/std
+    exp = (frame[0, 0, ::-1].astype(np.float32) * np.float32(1 / 255.0) - np.array([0.485, 0.456, 0.406], np.float32)) \
+        / np.array([0.229, 0.224, 0.225], np.float32)
+    np.testing.assert_allclose(img[0, 0], exp, rtol=1e-6)
+    same, s1 = on.preprocess(frame[:256, :384], 256, 384)             # identity size: no interpolation
+    assert s1 == 1.0
+    np.testing.assert_allclose(same[5, 7], (frame[5, 7, ::-1].astype(np.float32) * np.float32(1 / 255.0)
+                               - np.array([0.485, 0.456, 0.406], np.float32)) / np.array([0.229, 0.224, 0.225], np.float32), rtol=1e-6)
+
+
+def test_same_padding_and_backbone_shapes():
+    from object_detection_tracking_b200.synth import synth_efficientnet_weights
+    from oracle import efficientnet as on
+    x = torch.zeros(1, 1, 7, 10)
+    assert tuple(on.same_pad(x, 3, 2).shape) == (1, 1, 9, 11)         # 7 -> out 4: total 2 (1,1); 10 -> out 5: total 1 (0,1)
+    assert tuple(on.same_pad(x, 5, 1).shape) == (1, 1, 11, 14)
+    W = synth_efficientnet_weights("efficientnet-b0")
+    img = np.random.default_rng(1).standard_normal((128, 256, 3)).astype(np.float32)
+    r = on.forward(img, W, "efficientnet-b0")
+    assert r[3].shape == (40, 16, 32) and r[4].shape == (112, 8, 16) and r[5].shape == (320, 4, 8)
+    assert all(np.isfinite(r[l]).all() for l in (3, 4, 5))
+
+
+def test_coco_tables(golden):
+    from object_detection_tracking_b200 import class_ids as c
+    assert sorted(c.coco_id_mapping) == list(golden["coco_ids"])
+    assert [c.coco_id_mapping[i] for i in golden["coco_ids"]] == [str(n) for n in golden["coco_names"]]
+    assert c.effdet_labels_to_coco80(golden["coco_ids"]) == list(golden["coco_dense"])
+    assert c.coco_id_mapping[1] == "person" and c.coco_id_mapping[90] == "toothbrush" and 12 not in c.coco_id_mapping
+    assert c.coco_id_mapping[13] == "stop sign" and c.coco_id_mapping[67] == "dining table"
+    assert c.effdet_labels_to_coco80([1, 3, 90]) == [1, 3, 80]
+    assert c.coco_id_mapping_reverse["car"] == 3

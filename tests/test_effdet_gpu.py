@@ -140,3 +140,124 @@ def test_missing_weight_fails_loudly():
     del W["box_net/box-predict/bias"]
     with pytest.raises(RuntimeError, match="missing weight"):
         EffdetEngine(cfg, W)
+
+
+# ---- pre-processing + EfficientNet backbone + whole-frame detect (a16, a17) ------------------------------------------
+def _frame(h, w, seed=3):
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (h // 8 + 1, w // 8 + 1, 3)).astype(np.float32)
+    img = np.kron(base, np.ones((8, 8, 1), np.float32))[:h, :w]
+    return np.clip(img + rng.standard_normal((h, w, 3)) * 12, 0, 255).astype(np.uint8)
+
+
+def _full_case(det, H, W, fh, fw, precision="split", **over):
+    from object_detection_tracking_b200.effdet import EffdetEngine
+    from object_detection_tracking_b200.effdet_config import BACKBONE_OF, make_effdet_config
+    from object_detection_tracking_b200.synth import synth_effdet_weights, synth_efficientnet_weights
+    from oracle import effdet as oe
+    from oracle import efficientnet as on
+    bb = BACKBONE_OF[det]
+    cfg = make_effdet_config(det, H, W, **over)
+    Wt = dict(synth_effdet_weights(cfg))
+    Wt.update(synth_efficientnet_weights(bb))
+    frame = _frame(fh, fw)
+    img, scale = on.preprocess(frame, H, W)
+    feats = on.forward(img, Wt, bb, stages=True)
+    ref = oe.forward_from_features(cfg, Wt, {l: feats[l] for l in (3, 4, 5)}, image_scale=scale, stages=True)
+    eng = EffdetEngine(cfg, Wt, precision=precision, backbone=bb)
+    out = eng.detect(frame)
+    return cfg, eng, out, ref, feats, img, scale, frame, Wt
+
+
+@pytest.fixture(scope="module")
+def full_d0():
+    c = _full_case("efficientdet-d0", 256, 384, 300, 500, fpn_cell_repeats=2, box_class_repeats=2)
+    yield c
+    c[1].close()
+
+
+def test_preprocess_is_bit_exact(full_d0):
+    cfg, eng, out, ref, feats, img, scale, frame, _ = full_d0
+    np.testing.assert_array_equal(eng.stage("image"), img)
+    assert out["image_scale"] == pytest.approx(float(scale), rel=1e-7)
+
+
+def test_backbone_blocks_and_endpoints_match_oracle(full_d0):
+    cfg, eng, out, ref, feats, img, scale, frame, _ = full_d0
+    st = feats["stages"]
+    g = eng.stage("stem", real=st["stem"].shape[0])
+    assert np.abs(g - st["stem"].transpose(1, 2, 0)).max() <= 2e-5 * max(1.0, np.abs(st["stem"]).max())
+    for i in range(len(st) - 1):
+        r = st["block_%d" % i].transpose(1, 2, 0)
+        g = eng.stage("block_%d" % i, real=r.shape[2])
+        assert g.shape == r.shape
+        assert np.abs(g - r).max() <= 2e-5 * max(1.0, np.abs(r).max()), "block_%d" % i
+    for l in (3, 4, 5):
+        r = feats[l].transpose(1, 2, 0)
+        assert np.abs(eng.stage("c%d" % l) - r).max() <= 2e-5 * max(1.0, np.abs(r).max())
+
+
+def test_whole_frame_detections_match_oracle(full_d0):
+    cfg, eng, out, ref, feats, img, scale, frame, _ = full_d0
+    assert len(out["final_probs"]) == len(ref["final_probs"]) > 0
+    np.testing.assert_array_equal(out["final_labels"], ref["final_labels"])
+    np.testing.assert_array_equal(out["levels"], ref["levels"])
+    assert np.abs(out["final_boxes"] - ref["final_boxes"]).max() <= 1e-3
+    assert np.abs(out["final_probs"] - ref["final_probs"]).max() <= 5e-6
+    assert np.abs(out["fpn_box_feat"] - ref["fpn_box_feat"]).max() <= 2e-5 * max(1.0, np.abs(ref["fpn_box_feat"]).max())
+    again = eng.detect(frame)                                        # CUDA-graph replay, SE-scaled weights rewritten per frame
+    for k in ("final_boxes", "final_probs", "final_labels", "fpn_box_feat"):
+        np.testing.assert_array_equal(again[k], out[k])
+    other = eng.detect(_frame(240, 320, seed=9))                     # a different frame size through the same context
+    assert other["image_scale"] != out["image_scale"]
+    back = eng.detect(frame)
+    np.testing.assert_array_equal(back["final_boxes"], out["final_boxes"])
+
+
+def test_backbone_5x5_stride2_and_wider_trunk():
+    # b1 trunk (23 blocks) on a square input whose frame is taller than wide (height-limited scale)
+    cfg, eng, out, ref, feats, img, scale, frame, _ = _full_case("efficientdet-d1", 256, 256, 200, 190,
+                                                                 fpn_cell_repeats=1, box_class_repeats=1)
+    np.testing.assert_array_equal(eng.stage("image"), img)
+    for l in (3, 4, 5):
+        r = feats[l].transpose(1, 2, 0)
+        assert np.abs(eng.stage("c%d" % l) - r).max() <= 2e-5 * max(1.0, np.abs(r).max())
+    np.testing.assert_array_equal(out["final_labels"], ref["final_labels"])
+    assert np.abs(out["final_boxes"] - ref["final_boxes"]).max() <= 1e-3
+    eng.close()
+
+
+def test_efficientdet_model_object_drop_in():
+    # the reference call surface: models.get_model(config) -> EfficientDet; sess.run(fetches, feed_dict)
+    from types import SimpleNamespace
+    from object_detection_tracking_b200.backend import EfficientDet, Session, get_model
+    from object_detection_tracking_b200.effdet_config import make_effdet_config
+    from object_detection_tracking_b200.synth import synth_effdet_weights, synth_efficientnet_weights
+    from oracle import effdet as oe
+    from oracle import efficientnet as on
+    config = SimpleNamespace(is_efficientdet=True, efficientdet_modelname="efficientdet-d0", short_edge_size=256, max_size=384,
+                             efficientdet_min_level=3, efficientdet_max_level=7, efficientdet_max_detection_topk=5000,
+                             result_score_thres=1e-4, result_per_im=100, use_partial_classes=True,
+                             partial_classes=["person", "car", "bus", "truck", "bicycle"], is_load_from_pb=False)
+    model = get_model(config, gpuid=0, controller="/cpu:0")
+    assert isinstance(model, EfficientDet)
+    cfg_full = make_effdet_config("efficientdet-d0", 256, 384)
+    Wt = dict(synth_effdet_weights(cfg_full))
+    Wt.update(synth_efficientnet_weights("efficientnet-b0"))
+    with pytest.raises(RuntimeError):
+        Session().run([model.final_boxes], feed_dict=model.get_feed_dict_forward(_frame(300, 500)))   # no weights yet
+    model.set_weights(Wt)
+    frame = _frame(300, 500).astype(np.float32)                      # the drivers feed the float32 resized frame
+    sess = Session()
+    boxes, labels, probs, feat = sess.run([model.final_boxes, model.final_labels, model.final_probs, model.fpn_box_feat],
+                                          feed_dict=model.get_feed_dict_forward(frame))
+    assert boxes.shape[1] == 4 and len(boxes) == len(labels) == len(probs) == len(feat) > 0
+    assert labels.min() >= 1 and labels.max() <= 5                   # 1..len(partial_classes)
+    # oracle with the same class gather (wrapper :398-404)
+    idx = model.partial_class_idxs
+    img, scale = on.preprocess(frame.astype(np.uint8), 256, 384)
+    feats = on.forward(img, Wt, "efficientnet-b0")
+    ref = oe.forward_from_features(cfg_full, Wt, feats, image_scale=scale, partial_class_idxs=idx)
+    np.testing.assert_array_equal(labels, ref["final_labels"])
+    assert np.abs(boxes - ref["final_boxes"]).max() <= 1e-3
+    assert np.abs(probs - ref["final_probs"]).max() <= 5e-6
