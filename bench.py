@@ -34,8 +34,8 @@ def workload_config(n_gpus, precision):
                         "(BASELINE configs[1]); one stream per GPU, no data-path collective",
             "frame": [H, W, 3], "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "num_class": 15,
             "rpn_topk": 300, "precision": precision, "weights": "seeded synthetic (synth.py, seed 1234)",
-            "l2": "inputs rotate over 4 distinct batches (4 x 88 MB f32 > 126 MB L2) and the per-step "
-                  "activation footprint (> 2 GB) exceeds L2",
+            "l2": "inputs rotate over distinct batches larger than the 126 MB L2 (4 x 88 MB float32 / 8 x 22 MB uint8) "
+                  "and the per-step activation footprint (> 2 GB) exceeds L2",
             "parallelism": "replicas x%d" % n_gpus}
 
 
@@ -198,6 +198,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="split", choices=["split", "fp16"])
+    ap.add_argument("--input-dtype", default="float32", choices=["float32", "uint8"],
+                    help="frame dtype at the boundary: float32 = the reference placeholder (models.py:283), uint8 = decoder output")
     ap.add_argument("--cpu-frames", type=int, default=5, help="frames in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default="", help="write the per-layer roofline table here")
@@ -229,13 +231,14 @@ def main():
         torch.cuda.synchronize()
 
     cfg = make_config()
-    det = Detector(cfg, BATCH, H, W, device=local_rank, input_dtype="float32", precision=args.precision,
+    det = Detector(cfg, BATCH, H, W, device=local_rank, input_dtype=args.input_dtype, precision=args.precision,
                    use_cuda_graph=True)
     det.load_weights(synth_weights(cfg, 1234))
     # 4 distinct batches of synthetic frames (seeded per rank), resident on device and in pinned host memory
-    nb = 4
+    np_dt = np.float32 if args.input_dtype == "float32" else np.uint8
+    nb = 4 if args.input_dtype == "float32" else 8            # rotating input set larger than the 126 MB L2
     host = [torch.from_numpy(np.stack([synth_frame(H, W, seed=1000 * rank + 8 * j + i) for i in range(BATCH)])
-                             .astype(np.float32)).pin_memory() for j in range(nb)]
+                             .astype(np_dt)).pin_memory() for j in range(nb)]
     dev = [h.cuda(local_rank) for h in host]
     outs = det.alloc_outputs(feat_mode=0, pinned=True)
 
@@ -258,7 +261,8 @@ def main():
     det.run_phases(255)
     phase_ms = det.phase_times()
 
-    # ---------------- end to end through the host-buffer C-ABI call ----------------
+    # ---------------- end to end through the host-buffer C-ABI calls ----------------
+    # (a) one synchronous b2_detect_host per step (what Session.run does): upload, pass, download back to back
     for i in range(2):
         det.detect_host(host[i % nb], outs)
     barrier()
@@ -266,14 +270,30 @@ def main():
     for i in range(args.steps):
         det.detect_host(host[i % nb], outs)
     torch.cuda.synchronize()
+    dt_sync = time.perf_counter() - t1
+    barrier()
+    # (b) the streaming pair b2_submit_host / b2_wait with two slots (queue-fed drivers): every step still uploads its
+    # frames from pinned host memory and downloads all outputs inside the timed region; the upload of step i+1 overlaps
+    # the pass of step i
+    outs2 = [outs, det.alloc_outputs(feat_mode=0, pinned=True)]
+    det.submit_host(host[0], outs2[0], 0)
+    det.wait(0)
+    barrier()
+    t1 = time.perf_counter()
+    det.submit_host(host[0], outs2[0], 0)
+    for i in range(1, args.steps):
+        det.submit_host(host[i % nb], outs2[i & 1], i & 1)
+        det.wait((i - 1) & 1)
+    det.wait((args.steps - 1) & 1)
+    torch.cuda.synchronize()
     dt_e2e = time.perf_counter() - t1
     barrier()
 
     from object_detection_tracking_b200 import replicas
-    dt, dt_e2e = replicas.max_over_ranks([dt, dt_e2e], device="cuda")     # slowest rank bounds the job
+    dt, dt_e2e, dt_sync = replicas.max_over_ranks([dt, dt_e2e, dt_sync], device="cuda")     # slowest rank bounds the job
     value = replicas.aggregate_fps(args.steps * BATCH, dt, world)
     e2e_value = replicas.aggregate_fps(args.steps * BATCH, dt_e2e, world)
-    h2d = host[0].numel() * 4
+    h2d = host[0].numel() * host[0].element_size()
     d2h = sum(v.numel() * v.element_size() for v in outs.values())
 
     if rank == 0:
@@ -308,9 +328,11 @@ def main():
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16x2-split (fp32-equivalent products, fp32 accumulate)" if args.precision == "split"
                 else "f16 (fp32 accumulate)",
-                "data": "synthetic", "config": workload_config(world, args.precision),
+                "data": "synthetic", "config": dict(workload_config(world, args.precision), input_dtype=args.input_dtype),
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": dt_e2e / args.steps * 1e3},
+                        "ms_per_step": dt_e2e / args.steps * 1e3,
+                        "api": "b2_submit_host/b2_wait (2 slots, pinned %s frames in, all outputs out, every step)" % args.input_dtype,
+                        "sync_call_value": replicas.aggregate_fps(args.steps * BATCH, dt_sync, world)},
                 "gpu_launches": det.kernel_launches() * args.steps,
                 "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
                 "phase_ms": phase_ms}

@@ -77,6 +77,14 @@ int b2_detect(b2_ctx* ctx, const void* frames_dev, float* boxes, float* probs, i
 int b2_detect_host(b2_ctx* ctx, const void* frames_host, float* boxes, float* probs, int32_t* labels,
                    int32_t* valid, float* box_feat, int feat_mode);
 
+/* Pipelined ingest for streaming drivers (the queue-fed loop of obj_detect_tracking_multi_queuer.py:386-480):
+ * b2_submit_host returns as soon as the upload, the pass and the download of the results are enqueued; b2_wait(slot)
+ * blocks until that slot's results are in the caller's buffers.  Two slots: the upload of batch i+1 overlaps the pass
+ * of batch i.  Host buffers must stay valid (page-locked for real overlap) until b2_wait returns. */
+int b2_submit_host(b2_ctx* ctx, const void* frames_host, float* boxes, float* probs, int32_t* labels, int32_t* valid,
+                   float* box_feat, int feat_mode, int slot);
+int b2_wait(b2_ctx* ctx, int slot);
+
 /* Stage-addressable access for parity tests.  Activations are returned as fp32. */
 int b2_stage_shape(b2_ctx* ctx, const char* name, int64_t shape[4], int32_t* dtype /*0 f32, 1 i32*/);
 int b2_get_stage(b2_ctx* ctx, const char* name, void* dst_host, int64_t capacity_bytes);
@@ -151,6 +159,9 @@ int b2_effdet_detect(b2_effdet* ctx, const uint8_t* frame_bgr, int h, int w, flo
 /* Stage tensors of the last pass (parity tests): "image", "stem", "block_<i>", "c3".."c5", "fpn3".."fpn7", "cls3".."cls7", "box3".."box7" as fp32 NHWC */
 int b2_effdet_get_stage(b2_effdet* ctx, const char* name, float* dst_host, int64_t capacity_bytes, int64_t shape[4]);
 int b2_effdet_num_launches(b2_effdet* ctx);
+/* Per-step CUDA-event timing / description of the pass (same contract as b2_profile_steps / b2_step_info). */
+int b2_effdet_profile_steps(b2_effdet* ctx, int reps, float* ms_out, int cap, int* n_out);
+int b2_effdet_step_info(b2_effdet* ctx, int idx, char* name, int name_cap, double* flops, double* bytes, int* kind);
 
 /* Distance matrix of torchreid/distance.py:6-80 on the tensor cores: a [na,D], b [nb,D] (host) -> out [na,nb].
  * metric 0 = cosine (1 - a^.b^), 1 = squared euclidean (|a|^2 + |b|^2 - 2 a.b). */

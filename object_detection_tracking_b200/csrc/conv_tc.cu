@@ -126,7 +126,7 @@ __device__ __forceinline__ void epilogue_chunk16(const ConvTcParams& p, const ui
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
   } else if (p.relu == 2) {   // swish: x * sigmoid(x)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], 1.f / (1.f + expf(-v[j])));
+    for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], __frcp_rn(1.f + __expf(-v[j])));   // MUFU ex2 + rcp: ~2 ulp
   }
   if (p.out_f32 != nullptr) {
     float4* o = reinterpret_cast<float4*>(p.out_f32 + opix * p.ldc + n);
@@ -210,7 +210,7 @@ __device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, con
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
   } else if (p.relu == 2) {   // swish: x * sigmoid(x)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], 1.f / (1.f + expf(-v[j])));
+    for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], __frcp_rn(1.f + __expf(-v[j])));   // MUFU ex2 + rcp: ~2 ulp
   }
   uint32_t hi[8];
 #pragma unroll
@@ -489,19 +489,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const uint32_t lane_off = static_cast<uint32_t>(ew * 32) << 16;
         const uint32_t tacc = tmem_base + lane_off + as * acc_stage_cols;
         const uint32_t tacc1 = ACC ? tmem_base + lane_off + 256 + as * 128 : tacc + 128;
-#pragma unroll
-        for (int c = 0; c < (ACC ? 8 : 16); ++c) {
-          if (c >= nch) continue;
+        // one 16-column chunk: TMEM -> registers -> (+bias, +residual, activation, fp16 pair) -> swizzled smem -> TMA store
+        auto finish_chunk = [&](int c, uint32_t (&a0)[16], uint32_t (&a1)[16]) {
           const uint32_t j = g & (kEpiBufs - 1);
           uint8_t* buf = epi + j * buf_bytes;
-          uint32_t a0[16], a1[16];
-          if (ACC) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) a0[i] = __float_as_uint(sums[(ACC ? c : 0) * 16 + (ACC ? i : 0)]);
-          } else {
-            tmem_ld_32x32b_x16(tacc + c * 16, a0);
-          }
-          if (SPLIT) tmem_ld_32x32b_x16(tacc1 + c * 16, a1);
           if (has_res) {
             mbar_wait(&res_full[j], (rph >> j) & 1u);
             rph ^= 1u << j;
@@ -509,7 +500,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           tmem_ld_wait();
           epilogue_chunk16_smem<SPLIT>(p, a0, a1, buf, row, n0 + c * 16, has_res);
           fence_proxy_async();
-          if (elected && g >= 1) bulk_wait_read<1>();     // store(g-2) done reading -> buffer (g+2)&3 is free
+          if (elected && g >= 1) {
+            // with a residual the look-ahead load refills buffer (g+2)&3 right away: store(g-2) must be done reading;
+            // without one the next writer of a buffer is chunk g+1 into (g+1)&3: store(g-3) done is enough
+            if (has_res) bulk_wait_read<1>();
+            else bulk_wait_read<2>();
+          }
           named_bar_sync(1, 128);
           if (elected) {
             tma_store_2d(&tmO_hi, buf, n0 + c * 16, m_blk * kBlockM);
@@ -518,6 +514,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             if (has_res) issue_res(g + 2);
           }
           ++g;
+        };
+        if (ACC) {
+          // fully unrolled: the chunk sums live in registers and need compile-time indices
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (c >= nch) continue;
+            uint32_t a0[16], a1[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a0[i] = __float_as_uint(sums[(ACC ? c : 0) * 16 + (ACC ? i : 0)]);
+            if (SPLIT) tmem_ld_32x32b_x16(tacc1 + c * 16, a1);
+            finish_chunk(c, a0, a1);
+          }
+        } else {
+          // rolled (x2): 16 unrolled copies of the chunk body overflow the instruction cache (ncu: "no instructions" +
+          // "branch resolving" stalls on the K = 64 EfficientNet expansions)
+#pragma unroll 2
+          for (int c = 0; c < nch; ++c) {
+            uint32_t a0[16], a1[16];
+            tmem_ld_32x32b_x16(tacc + c * 16, a0);
+            if (SPLIT) tmem_ld_32x32b_x16(tacc1 + c * 16, a1);
+            finish_chunk(c, a0, a1);
+          }
         }
         tc_fence_before();
         __syncwarp();

@@ -106,44 +106,6 @@ __global__ void bifpn_combine_kernel(const __grid_constant__ BifpnCombineParams 
   }
 }
 
-// depthwise 3x3, stride 1, SAME, no bias / activation: w [9][C] fp32
-__global__ void dw3x3_plain_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, int B, int H, int W,
-                                   int C, const float* __restrict__ w, __half* __restrict__ out_hi,
-                                   __half* __restrict__ out_lo) {
-  const int cvec = C / 8;
-  const size_t total = static_cast<size_t>(B) * H * W * cvec;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int cv = static_cast<int>(idx % cvec);
-    const size_t pix = idx / cvec;
-    const int b = static_cast<int>(pix / (static_cast<size_t>(H) * W));
-    const int rem = static_cast<int>(pix % (static_cast<size_t>(H) * W));
-    const int y = rem / W, x = rem % W;
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int iy = y + r - 1;
-      if (iy < 0 || iy >= H) continue;
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int ix = x + s - 1;
-        if (ix < 0 || ix >= W) continue;
-        float v[8];
-        ld8(in_hi, in_lo, ((static_cast<size_t>(b) * H + iy) * W + ix) * C + cv * 8, v);
-        const float4* wp = reinterpret_cast<const float4*>(w + static_cast<size_t>(r * 3 + s) * C + cv * 8);
-        const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
-        acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]);
-        acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
-        acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]);
-        acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
-      }
-    }
-    st8(out_hi, out_lo, pix * C + cv * 8, acc);
-  }
-}
-
 // ---- global top-k over all class logits: multi-block radix select on order-preserving keys ----------
 __device__ __forceinline__ int level_of(const EffdetPostParams& p, unsigned long long i) {
   int l = 0;
@@ -408,10 +370,9 @@ int bifpn_combine_launch(const BifpnCombineParams& p, cudaStream_t s) {
 
 int dw3x3_plain_launch(const __half* in_hi, const __half* in_lo, int B, int H, int W, int C, const float* w, __half* out_hi,
                        __half* out_lo, cudaStream_t s) {
-  const size_t total = static_cast<size_t>(B) * H * W * (C / 8);
-  dw3x3_plain_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, s>>>(in_hi, in_lo, B, H, W, C, w, out_hi, out_lo);
-  B2_CUDA(cudaGetLastError());
-  return 0;
+  B2_CHECK(B == 1, "dw3x3_plain: batch 1 only");
+  DwConvParams p{in_hi, in_lo, H, W, C, 3, 1, 1, 1, H, W, w, nullptr, out_hi, out_lo};
+  return dwconv_launch(p, 0, s);
 }
 
 int effdet_topk_blocks() { return static_cast<int>(kTopkMaxBlocks); }

@@ -11,6 +11,7 @@
 // folded BatchNorm (eps 1e-3) and swish in the epilogue.  The class/box nets share conv weights across levels but
 // not BatchNorm statistics, so each level gets its own folded copy of the pointwise weights.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -71,7 +72,7 @@ struct ESe {
   std::string pre;          // ".../blocks_i/se"
   EPlanes x;
   int creal = 0, nr = 0;
-  float *partial = nullptr, *gate = nullptr, *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
+  float *partial = nullptr, *r_part = nullptr, *gate = nullptr, *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
   float* w_master = nullptr;   // BN-folded projection weights [Cout_pad][K] fp32
   EConv* proj = nullptr;
 };
@@ -290,6 +291,7 @@ int build_backbone(b2_effdet* c) {
     S->pre = pre + "/se"; S->x = d; S->creal = mid; S->nr = b.cin / 4 > 1 ? b.cin / 4 : 1;
     S->partial = c->alloc<float>(static_cast<size_t>(se_chunks(ho * wo)) * d.C);
     S->gate = c->alloc<float>(d.C);
+    S->r_part = c->alloc<float>(static_cast<size_t>(se_fc1_parts()) * se_max_nr());
     S->w1 = c->alloc<float>(static_cast<size_t>(mid) * S->nr); S->b1 = c->alloc<float>(S->nr);
     S->w2 = c->alloc<float>(static_cast<size_t>(S->nr) * mid); S->b2 = c->alloc<float>(mid);
     ESe* se = S.get();
@@ -496,9 +498,8 @@ int run_step(b2_effdet* c, const EStep& s) {
     case 3: return dwconv_bn_swish_launch(c->dwbns[s.idx]->p, st);
     case 4: {
       const ESe* e = c->ses[s.idx].get();
-      if (se_gate_launch(e->x.hi, e->x.lo, e->x.H * e->x.W, e->x.C, e->creal, e->nr, e->partial, e->w1, e->b1, e->w2, e->b2,
-                         e->gate, st)) return -1;
-      return se_scale_weights_launch(e->w_master, e->gate, e->proj->w.Cout_pad, e->proj->w.K, e->proj->w.w_hi, e->proj->w.w_lo, st);
+      return se_gate_launch(e->x.hi, e->x.lo, e->x.H * e->x.W, e->x.C, e->creal, e->nr, e->partial, e->r_part, e->w1, e->b1,
+                            e->w2, e->b2, e->gate, e->w_master, e->proj->w.Cout_pad, e->proj->w.w_hi, e->proj->w.w_lo, st);
     }
     case 5:
       return stem_im2col_launch(c->image, c->cfg.image_h, c->cfg.image_w, c->stem_cols.H, c->stem_cols.W, s.idx / 65536,
@@ -791,6 +792,98 @@ int b2_effdet_get_stage(b2_effdet* c, const char* name, float* dst, int64_t capa
   B2_CUDA(cudaMemcpyAsync(dst, tmp, n * 4, cudaMemcpyDeviceToHost, c->stream));
   B2_CUDA(cudaStreamSynchronize(c->stream));
   B2_CUDA(cudaFree(tmp));
+  return 0;
+}
+
+// Per-step CUDA-event timing of the whole pass (backbone when present, feature network, heads, post-processing, box
+// feature), eager launches on the context stream.  ms_out[i] = mean over `reps` of step i; *n_out = number of steps.
+int b2_effdet_profile_steps(b2_effdet* c, int reps, float* ms_out, int cap, int* n_out) {
+  B2_CHECK(c && ms_out && n_out && reps >= 1, "b2_effdet_profile_steps: bad argument");
+  B2_CUDA(cudaSetDevice(c->device));
+  B2_CHECK(c->loaded, "b2_effdet_profile_steps: weights not loaded");
+  std::vector<EStep> all(c->bb_steps);
+  all.insert(all.end(), c->steps.begin(), c->steps.end());
+  const int n = static_cast<int>(all.size()) + 2;
+  B2_CHECK(cap >= n, "b2_effdet_profile_steps: buffer too small");
+  std::vector<cudaEvent_t> ev(2 * n);
+  for (auto& e : ev) B2_CUDA(cudaEventCreate(&e));
+  std::vector<double> acc(n, 0.0);
+  for (int r = 0; r < reps; ++r) {
+    for (int i = 0; i < n; ++i) {
+      B2_CUDA(cudaEventRecord(ev[2 * i], c->stream));
+      int rc = 0;
+      if (i < n - 2) rc = run_step(c, all[i]);
+      else if (i == n - 2) rc = effdet_post_launch(c->post, c->scale_dev, c->stream);
+      else rc = level_roi_feat_launch(c->roi, c->stream);
+      if (rc) return -1;
+      B2_CUDA(cudaEventRecord(ev[2 * i + 1], c->stream));
+    }
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; ++i) {
+      float ms = 0.f;
+      B2_CUDA(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]));
+      acc[i] += ms;
+    }
+  }
+  for (int i = 0; i < n; ++i) ms_out[i] = static_cast<float>(acc[i] / reps);
+  for (auto& e : ev) cudaEventDestroy(e);
+  *n_out = n;
+  return 0;
+}
+
+// Step `idx` of b2_effdet_profile_steps: kind (0 pointwise conv on the tensor cores, 1 head/BiFPN depthwise, 2 BiFPN
+// combine / max-pool, 3 backbone depthwise, 4 squeeze-excite, 5 stem im2col, 6 post-processing, 7 box feature), a
+// name, algorithmic FLOPs and HBM bytes (operands once, at the stored precision).
+int b2_effdet_step_info(b2_effdet* c, int idx, char* name, int name_cap, double* flops, double* bytes, int* kind) {
+  B2_CHECK(c && name && flops && bytes && kind, "b2_effdet_step_info: null argument");
+  std::vector<EStep> all(c->bb_steps);
+  all.insert(all.end(), c->steps.begin(), c->steps.end());
+  const int n = static_cast<int>(all.size()) + 2;
+  B2_CHECK(idx >= 0 && idx < n, "b2_effdet_step_info: index out of range");
+  const double esz = c->split ? 4.0 : 2.0;
+  std::string nm;
+  *flops = 0; *bytes = 0;
+  if (idx == n - 2) { *kind = 6; nm = "post"; *bytes = static_cast<double>(c->post.total) * 4.0 * 6.0; }
+  else if (idx == n - 1) { *kind = 7; nm = "box_feat"; }
+  else {
+    const EStep& s = all[idx];
+    *kind = s.kind;
+    if (s.kind == 0) {
+      const EConv* L = c->convs[s.idx].get();
+      const ConvDesc& d = L->d;
+      const double M = static_cast<double>(d.in_H) * d.in_W;
+      *flops = 2.0 * M * L->cin_real * L->cout_real;
+      *bytes = M * d.Cin * esz + static_cast<double>(L->w.K) * L->w.Cout_pad * esz +
+               M * (L->io.out_f32 ? L->w.Cout_pad * 4.0 : d.ldc * esz) + (L->io.res_hi ? M * d.ldr * esz : 0.0);
+      nm = L->wname + " [" + std::to_string(d.in_H) + "x" + std::to_string(d.in_W) + "x" + std::to_string(L->cin_real) + "->" +
+           std::to_string(L->cout_real) + "]";
+    } else if (s.kind == 1) {
+      const EDw* D = c->dws[s.idx].get();
+      *bytes = 2.0 * static_cast<double>(D->in.elems()) * esz;
+      *flops = 18.0 * static_cast<double>(D->in.H) * D->in.W * D->in.creal;
+      nm = D->wname;
+    } else if (s.kind == 2) {
+      const BifpnCombineParams& p = c->combines[s.idx]->p;
+      double in = 0;
+      for (int i = 0; i < p.n_in; ++i) in += static_cast<double>(p.in[i].H) * p.in[i].W * p.C;
+      *bytes = (in + static_cast<double>(p.Ho) * p.Wo * p.C) * esz;
+      nm = "combine x" + std::to_string(p.n_in) + " [" + std::to_string(p.Ho) + "x" + std::to_string(p.Wo) + "]";
+    } else if (s.kind == 3) {
+      const EDwBn* D = c->dwbns[s.idx].get();
+      *bytes = (static_cast<double>(D->p.H) * D->p.W + static_cast<double>(D->p.Ho) * D->p.Wo) * D->p.C * esz;
+      *flops = 2.0 * D->p.K * D->p.K * static_cast<double>(D->p.Ho) * D->p.Wo * D->creal;
+      nm = D->wname + " [" + std::to_string(D->p.H) + "x" + std::to_string(D->p.W) + "x" + std::to_string(D->creal) + " k" +
+           std::to_string(D->p.K) + "/" + std::to_string(D->p.stride) + "]";
+    } else if (s.kind == 4) {
+      const ESe* e = c->ses[s.idx].get();
+      *bytes = static_cast<double>(e->x.elems()) * esz + 2.0 * e->proj->w.Cout_pad * e->proj->w.K * 4.0;
+      nm = e->pre;
+    } else {
+      *bytes = static_cast<double>(c->cfg.image_h) * c->cfg.image_w * 3 * 4 + static_cast<double>(c->stem_cols.elems()) * esz;
+      nm = "stem_im2col";
+    }
+  }
+  snprintf(name, name_cap, "%s", nm.c_str());
   return 0;
 }
 

@@ -99,6 +99,11 @@ struct b2_ctx {
   // buffers
   void* img = nullptr;
   size_t img_bytes = 0;
+  // pipelined ingest (b2_submit_host / b2_wait): two staging buffers fed by a copy stream
+  cudaStream_t copy_stream = nullptr;
+  void* stage_in[2] = {nullptr, nullptr};
+  cudaEvent_t h2d_done[2] = {nullptr, nullptr}, staged_free[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
+  bool slot_busy[2] = {false, false};
   Planes stem_u, c1, pool, cfeat[4], lat[4], pfeat[5], rpn_h[5];
   float* rpn_out[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   RpnParams rpn;
@@ -704,6 +709,12 @@ void b2_destroy(b2_ctx* c) {
   for (void* p : c->allocs) cudaFree(p);
   for (int i = 0; i <= NPHASE; ++i)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 2; ++i) {
+    if (c->h2d_done[i]) cudaEventDestroy(c->h2d_done[i]);
+    if (c->staged_free[i]) cudaEventDestroy(c->staged_free[i]);
+    if (c->out_done[i]) cudaEventDestroy(c->out_done[i]);
+  }
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -874,6 +885,52 @@ int b2_detect_host(b2_ctx* c, const void* frames_host, float* boxes, float* prob
   if (run_all(c)) return -1;
   if (copy_outputs(c, boxes, probs, labels, valid, box_feat, feat_mode, cudaMemcpyDeviceToHost)) return -1;
   B2_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// Pipelined ingest for streaming drivers (the reference's queue-fed loop, obj_detect_tracking_multi_queuer.py:386-480):
+// b2_submit_host enqueues  H2D(frames -> staging[slot]) on a copy stream, then on the compute stream
+// staging[slot] -> image, the pass, and the D2H of the results into the caller's (pinned) buffers, and returns without
+// waiting; b2_wait(slot) blocks until that slot's results have landed.  With two slots the upload of batch i+1 overlaps
+// the pass of batch i.  Host buffers must stay valid (and should be page-locked) until b2_wait returns.
+int b2_submit_host(b2_ctx* c, const void* frames_host, float* boxes, float* probs, int32_t* labels, int32_t* valid,
+                   float* box_feat, int feat_mode, int slot) {
+  B2_CHECK(c && frames_host, "b2_submit_host: null argument");
+  B2_CHECK(slot == 0 || slot == 1, "b2_submit_host: slot must be 0 or 1");
+  B2_CUDA(cudaSetDevice(c->device));
+  B2_CHECK(c->weights_loaded, "b2_submit_host: weights not loaded");
+  B2_CHECK(!c->slot_busy[slot], "b2_submit_host: slot still in flight (call b2_wait first)");
+  if (!c->copy_stream) {
+    B2_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      B2_CUDA(cudaMalloc(&c->stage_in[i], c->img_bytes));
+      c->allocs.push_back(c->stage_in[i]);
+      B2_CUDA(cudaEventCreateWithFlags(&c->h2d_done[i], cudaEventDisableTiming));
+      B2_CUDA(cudaEventCreateWithFlags(&c->staged_free[i], cudaEventDisableTiming));
+      B2_CUDA(cudaEventCreateWithFlags(&c->out_done[i], cudaEventDisableTiming));
+      B2_CUDA(cudaEventRecord(c->staged_free[i], c->stream));
+    }
+    if (c->cfg.use_cuda_graph && ensure_graph(c)) return -1;   // capture before anything is in flight
+  }
+  B2_CUDA(cudaStreamWaitEvent(c->copy_stream, c->staged_free[slot], 0));      // the previous use of this staging buffer
+  B2_CUDA(cudaMemcpyAsync(c->stage_in[slot], frames_host, c->img_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+  B2_CUDA(cudaEventRecord(c->h2d_done[slot], c->copy_stream));
+  B2_CUDA(cudaStreamWaitEvent(c->stream, c->h2d_done[slot], 0));
+  B2_CUDA(cudaMemcpyAsync(c->img, c->stage_in[slot], c->img_bytes, cudaMemcpyDeviceToDevice, c->stream));
+  B2_CUDA(cudaEventRecord(c->staged_free[slot], c->stream));
+  if (run_all(c)) return -1;
+  if (copy_outputs(c, boxes, probs, labels, valid, box_feat, feat_mode, cudaMemcpyDeviceToHost)) return -1;
+  B2_CUDA(cudaEventRecord(c->out_done[slot], c->stream));
+  c->slot_busy[slot] = true;
+  return 0;
+}
+
+int b2_wait(b2_ctx* c, int slot) {
+  B2_CHECK(c && (slot == 0 || slot == 1), "b2_wait: bad argument");
+  B2_CUDA(cudaSetDevice(c->device));
+  B2_CHECK(c->slot_busy[slot], "b2_wait: nothing was submitted on this slot");
+  B2_CUDA(cudaEventSynchronize(c->out_done[slot]));
+  c->slot_busy[slot] = false;
   return 0;
 }
 

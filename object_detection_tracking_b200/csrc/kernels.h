@@ -151,10 +151,13 @@ struct DwConvParams {
   __half* out_lo;
 };
 int dwconv_bn_swish_launch(const DwConvParams& p, cudaStream_t s);
+int dwconv_launch(const DwConvParams& p, int act, cudaStream_t s);   // act 0 none / 2 swish; p.bias may be null
 int se_chunks(int HW);      // rows of the partial-sum buffer se_gate_launch needs
-int se_gate_launch(const __half* in_hi, const __half* in_lo, int HW, int Cpad, int C, int nr, float* partial, const float* w1,
-                   const float* b1, const float* w2, const float* b2, float* gate, cudaStream_t s);
-int se_scale_weights_launch(const float* w, const float* gate, int rows, int K, __half* hi, __half* lo, cudaStream_t s);
+int se_fc1_parts();         // rows of the r_part buffer (row stride se_max_nr())
+int se_max_nr();
+int se_gate_launch(const __half* in_hi, const __half* in_lo, int HW, int Cpad, int C, int nr, float* partial, float* r_part,
+                   const float* w1, const float* b1, const float* w2, const float* b2, float* gate, const float* w, int rows,
+                   __half* w_hi, __half* w_lo, cudaStream_t s);
 
 // roialign.cu -- ROIAlign 7x7 on the detection's own level + mean over the 49 bins (efficientdet_wrapper.py:265-301)
 struct LevelRoiFeatParams {

@@ -114,6 +114,21 @@ class EffdetEngine:
         out = buf[: h * w * c].reshape(h, w, c)
         return (out if real is None else out[:, :, :real]).copy()
 
+    def profile_steps(self, reps: int = 5):
+        """[(name, kind, ms, flops, bytes)] per launch group of the last pass (CUDA events, eager launches)."""
+        cap = 4096
+        ms = (ctypes.c_float * cap)()
+        n = ctypes.c_int()
+        _lib.check(self._lib.b2_effdet_profile_steps(self._h, int(reps), ms, cap, ctypes.byref(n)), "b2_effdet_profile_steps")
+        out = []
+        for i in range(n.value):
+            name = ctypes.create_string_buffer(256)
+            fl, by, kind = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+            _lib.check(self._lib.b2_effdet_step_info(self._h, i, name, 256, ctypes.byref(fl), ctypes.byref(by),
+                                                     ctypes.byref(kind)), "b2_effdet_step_info")
+            out.append((name.value.decode(), kind.value, float(ms[i]), fl.value, by.value))
+        return out
+
     @property
     def num_launches(self) -> int:
         return int(self._lib.b2_effdet_num_launches(self._h))

@@ -81,6 +81,21 @@ class Detector:
                    "b2_detect_host")
         return out
 
+    def submit_host(self, frames, out: dict, slot: int, feat_mode: int = 0, want_feat: bool = True):
+        """Asynchronous detect_host: enqueue upload + pass + download for `slot` (0/1) and return; `frames` and the
+        arrays of `out` must stay alive (pinned for real overlap) until wait(slot).  Streaming drivers alternate slots
+        so that the upload of the next batch overlaps the pass of the current one."""
+        if isinstance(frames, np.ndarray):
+            assert frames.dtype == self._np_dtype() and frames.flags["C_CONTIGUOUS"], "submit_host needs a contiguous array"
+            assert frames.shape == (self.batch, self.height, self.width, 3), frames.shape
+        _lib.check(self.lib.b2_submit_host(self._ctx, _lib.ptr(frames), _lib.ptr(out["boxes"]), _lib.ptr(out["probs"]),
+                                           _lib.ptr(out["labels"]), _lib.ptr(out["valid"]),
+                                           _lib.ptr(out["feat"]) if want_feat else c_void_p(0), feat_mode, int(slot)),
+                   "b2_submit_host")
+
+    def wait(self, slot: int):
+        _lib.check(self.lib.b2_wait(self._ctx, int(slot)), "b2_wait")
+
     def detect_device(self, frames_dev, out_dev: dict | None = None, feat_mode: int = 0, sync: bool = True):
         """frames_dev / out_dev: torch CUDA tensors (or None to leave results in the context)."""
         o = out_dev or {}

@@ -193,6 +193,34 @@ def test_cuda_graph_replay_equals_eager_and_outputs_are_fresh(small):
     dg.close(); du.close()
 
 
+def test_pipelined_submit_wait_equals_synchronous_calls(small):
+    # b2_submit_host / b2_wait (two slots, upload of batch i+1 overlapping the pass of batch i) must return exactly what
+    # the synchronous b2_detect_host returns for each batch, in order
+    from object_detection_tracking_b200.engine import Detector
+    from object_detection_tracking_b200.synth import synth_frame
+    cfg, Wt, frames, det, ref = small
+    dg = Detector(cfg, 2, 192, 256, precision="split", use_cuda_graph=True)
+    dg.load_weights(Wt)
+    batches = [frames] + [np.stack([synth_frame(192, 256, seed=50 + 2 * j + i) for i in range(2)]).astype(np.float32)
+                          for j in range(4)]
+    sync = [dg.detect_host(b) for b in batches]
+    outs = [dg.alloc_outputs(feat_mode=0), dg.alloc_outputs(feat_mode=0)]
+    got = []
+    dg.submit_host(batches[0], outs[0], 0)
+    for i in range(1, len(batches)):
+        dg.submit_host(batches[i], outs[i & 1], i & 1)
+        dg.wait((i - 1) & 1)
+        got.append({k: v.copy() for k, v in outs[(i - 1) & 1].items()})
+    dg.wait((len(batches) - 1) & 1)
+    got.append({k: v.copy() for k, v in outs[(len(batches) - 1) & 1].items()})
+    for a, b in zip(sync, got):
+        for k in a:
+            np.testing.assert_array_equal(a[k], b[k])
+    with pytest.raises(RuntimeError):
+        dg.wait(0)                                   # nothing in flight on that slot
+    dg.close()
+
+
 def test_batch_graph_semantics_match_oracle_multi():
     """multi_semantics=1 (Mask_RCNN_FPN_multi: combined_non_max_suppression) vs oracle.forward_multi."""
     from object_detection_tracking_b200.config import make_config
