@@ -126,7 +126,7 @@ __device__ __forceinline__ void epilogue_chunk16(const ConvTcParams& p, const ui
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
   } else if (p.relu == 2) {   // swish: x * sigmoid(x)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], __frcp_rn(1.f + __expf(-v[j])));   // MUFU ex2 + rcp: ~2 ulp
+    for (int j = 0; j < 16; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));   // MUFU ex2 + rcp: ~2 ulp
   }
   if (p.out_f32 != nullptr) {
     float4* o = reinterpret_cast<float4*>(p.out_f32 + opix * p.ldc + n);
@@ -210,7 +210,7 @@ __device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, con
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
   } else if (p.relu == 2) {   // swish: x * sigmoid(x)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], __frcp_rn(1.f + __expf(-v[j])));   // MUFU ex2 + rcp: ~2 ulp
+    for (int j = 0; j < 16; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));   // MUFU ex2 + rcp: ~2 ulp
   }
   uint32_t hi[8];
 #pragma unroll

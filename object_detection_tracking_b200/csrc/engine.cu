@@ -100,8 +100,10 @@ struct b2_ctx {
   void* img = nullptr;
   size_t img_bytes = 0;
   // pipelined ingest (b2_submit_host / b2_wait): two staging buffers fed by a copy stream
-  cudaStream_t copy_stream = nullptr;
+  cudaStream_t copy_stream = nullptr, down_stream = nullptr;
   void* stage_in[2] = {nullptr, nullptr};
+  uint8_t* stage_out[2] = {nullptr, nullptr};     // boxes | probs | labels | count | feat, device copies per slot
+  cudaEvent_t pass_done[2] = {nullptr, nullptr};
   cudaEvent_t h2d_done[2] = {nullptr, nullptr}, staged_free[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
   bool slot_busy[2] = {false, false};
   Planes stem_u, c1, pool, cfeat[4], lat[4], pfeat[5], rpn_h[5];
@@ -713,8 +715,10 @@ void b2_destroy(b2_ctx* c) {
     if (c->h2d_done[i]) cudaEventDestroy(c->h2d_done[i]);
     if (c->staged_free[i]) cudaEventDestroy(c->staged_free[i]);
     if (c->out_done[i]) cudaEventDestroy(c->out_done[i]);
+    if (c->pass_done[i]) cudaEventDestroy(c->pass_done[i]);
   }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->down_stream) cudaStreamDestroy(c->down_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -900,14 +904,21 @@ int b2_submit_host(b2_ctx* c, const void* frames_host, float* boxes, float* prob
   B2_CUDA(cudaSetDevice(c->device));
   B2_CHECK(c->weights_loaded, "b2_submit_host: weights not loaded");
   B2_CHECK(!c->slot_busy[slot], "b2_submit_host: slot still in flight (call b2_wait first)");
+  const int B = c->cfg.batch, R = c->cfg.result_per_im, C = c->cfg.fpn_num_channel;
+  const size_t nb_boxes = sizeof(float) * B * R * 4, nb_probs = sizeof(float) * B * R, nb_labels = sizeof(int32_t) * B * R;
+  const size_t nb_valid = (sizeof(int32_t) * B + 255) / 256 * 256, nb_feat = sizeof(float) * B * R * C * 49;
   if (!c->copy_stream) {
     B2_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    B2_CUDA(cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
       B2_CUDA(cudaMalloc(&c->stage_in[i], c->img_bytes));
       c->allocs.push_back(c->stage_in[i]);
+      B2_CUDA(cudaMalloc(&c->stage_out[i], nb_boxes + nb_probs + nb_labels + nb_valid + nb_feat));
+      c->allocs.push_back(c->stage_out[i]);
       B2_CUDA(cudaEventCreateWithFlags(&c->h2d_done[i], cudaEventDisableTiming));
       B2_CUDA(cudaEventCreateWithFlags(&c->staged_free[i], cudaEventDisableTiming));
       B2_CUDA(cudaEventCreateWithFlags(&c->out_done[i], cudaEventDisableTiming));
+      B2_CUDA(cudaEventCreateWithFlags(&c->pass_done[i], cudaEventDisableTiming));
       B2_CUDA(cudaEventRecord(c->staged_free[i], c->stream));
     }
     if (c->cfg.use_cuda_graph && ensure_graph(c)) return -1;   // capture before anything is in flight
@@ -919,8 +930,27 @@ int b2_submit_host(b2_ctx* c, const void* frames_host, float* boxes, float* prob
   B2_CUDA(cudaMemcpyAsync(c->img, c->stage_in[slot], c->img_bytes, cudaMemcpyDeviceToDevice, c->stream));
   B2_CUDA(cudaEventRecord(c->staged_free[slot], c->stream));
   if (run_all(c)) return -1;
-  if (copy_outputs(c, boxes, probs, labels, valid, box_feat, feat_mode, cudaMemcpyDeviceToHost)) return -1;
-  B2_CUDA(cudaEventRecord(c->out_done[slot], c->stream));
+  // results -> this slot's device staging (a few tens of microseconds), then off the compute stream: the download runs
+  // on its own stream while the next pass is already executing
+  uint8_t* so = c->stage_out[slot];
+  uint8_t* d_boxes = so;
+  uint8_t* d_probs = d_boxes + nb_boxes;
+  uint8_t* d_labels = d_probs + nb_probs;
+  uint8_t* d_valid = d_labels + nb_labels;
+  uint8_t* d_feat = d_valid + nb_valid;
+  const size_t feat_bytes = feat_mode == 1 ? sizeof(float) * B * R * C : nb_feat;
+  if (copy_outputs(c, boxes ? reinterpret_cast<float*>(d_boxes) : nullptr, probs ? reinterpret_cast<float*>(d_probs) : nullptr,
+                   labels ? reinterpret_cast<int32_t*>(d_labels) : nullptr, valid ? reinterpret_cast<int32_t*>(d_valid) : nullptr,
+                   box_feat ? reinterpret_cast<float*>(d_feat) : nullptr, feat_mode, cudaMemcpyDeviceToDevice)) return -1;
+  B2_CUDA(cudaEventRecord(c->pass_done[slot], c->stream));
+  cudaStream_t ds = c->down_stream;
+  B2_CUDA(cudaStreamWaitEvent(ds, c->pass_done[slot], 0));
+  if (boxes) B2_CUDA(cudaMemcpyAsync(boxes, d_boxes, nb_boxes, cudaMemcpyDeviceToHost, ds));
+  if (probs) B2_CUDA(cudaMemcpyAsync(probs, d_probs, nb_probs, cudaMemcpyDeviceToHost, ds));
+  if (labels) B2_CUDA(cudaMemcpyAsync(labels, d_labels, nb_labels, cudaMemcpyDeviceToHost, ds));
+  if (valid) B2_CUDA(cudaMemcpyAsync(valid, d_valid, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, ds));
+  if (box_feat) B2_CUDA(cudaMemcpyAsync(box_feat, d_feat, feat_bytes, cudaMemcpyDeviceToHost, ds));
+  B2_CUDA(cudaEventRecord(c->out_done[slot], ds));
   c->slot_busy[slot] = true;
   return 0;
 }

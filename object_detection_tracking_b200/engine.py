@@ -86,8 +86,11 @@ class Detector:
         arrays of `out` must stay alive (pinned for real overlap) until wait(slot).  Streaming drivers alternate slots
         so that the upload of the next batch overlaps the pass of the current one."""
         if isinstance(frames, np.ndarray):
-            assert frames.dtype == self._np_dtype() and frames.flags["C_CONTIGUOUS"], "submit_host needs a contiguous array"
+            frames = np.ascontiguousarray(frames, dtype=self._np_dtype())     # a copy only when the caller's array needs one
             assert frames.shape == (self.batch, self.height, self.width, 3), frames.shape
+        if not hasattr(self, "_inflight"):
+            self._inflight = {}
+        self._inflight[int(slot)] = (frames, out)                             # keep the buffers alive until wait()
         _lib.check(self.lib.b2_submit_host(self._ctx, _lib.ptr(frames), _lib.ptr(out["boxes"]), _lib.ptr(out["probs"]),
                                            _lib.ptr(out["labels"]), _lib.ptr(out["valid"]),
                                            _lib.ptr(out["feat"]) if want_feat else c_void_p(0), feat_mode, int(slot)),
@@ -95,6 +98,7 @@ class Detector:
 
     def wait(self, slot: int):
         _lib.check(self.lib.b2_wait(self._ctx, int(slot)), "b2_wait")
+        getattr(self, "_inflight", {}).pop(int(slot), None)
 
     def detect_device(self, frames_dev, out_dev: dict | None = None, feat_mode: int = 0, sync: bool = True):
         """frames_dev / out_dev: torch CUDA tensors (or None to leave results in the context)."""
