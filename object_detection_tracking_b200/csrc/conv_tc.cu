@@ -529,12 +529,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         } else {
           // rolled (x2): 16 unrolled copies of the chunk body overflow the instruction cache (ncu: "no instructions" +
           // "branch resolving" stalls on the K = 64 EfficientNet expansions)
+          if (!has_res && (nch & 1) == 0) {
+            // two chunks per fence / barrier / store group: the per-chunk membar + named barrier + TMA issue chain is what
+            // bounds short-K layers (ncu: MMA issuer spinning on tmem_empty, epilogue warps never waiting on tmem_full)
+            for (int c = 0; c < nch; c += 2) {
+              uint32_t a0[16], a1[16], b0[16], b1[16];
+              tmem_ld_32x32b_x16(tacc + c * 16, a0);
+              if (SPLIT) tmem_ld_32x32b_x16(tacc1 + c * 16, a1);
+              tmem_ld_32x32b_x16(tacc + c * 16 + 16, b0);
+              if (SPLIT) tmem_ld_32x32b_x16(tacc1 + c * 16 + 16, b1);
+              uint8_t* bufa = epi + (g & (kEpiBufs - 1)) * buf_bytes;
+              uint8_t* bufb = epi + ((g + 1) & (kEpiBufs - 1)) * buf_bytes;
+              tmem_ld_wait();
+              epilogue_chunk16_smem<SPLIT>(p, a0, a1, bufa, row, n0 + c * 16, false);
+              epilogue_chunk16_smem<SPLIT>(p, b0, b1, bufb, row, n0 + c * 16 + 16, false);
+              fence_proxy_async();
+              // the next pair overwrites the buffers of the previous pair: its store (one pair-time old) must be done reading
+              if (elected && g >= 2) bulk_wait_read<0>();
+              named_bar_sync(1, 128);
+              if (elected) {
+                tma_store_2d(&tmO_hi, bufa, n0 + c * 16, m_blk * kBlockM);
+                tma_store_2d(&tmO_hi, bufb, n0 + c * 16 + 16, m_blk * kBlockM);
+                if (SPLIT && p.out_lo != nullptr) {
+                  tma_store_2d(&tmO_lo, bufa + kEpiPlaneBytes, n0 + c * 16, m_blk * kBlockM);
+                  tma_store_2d(&tmO_lo, bufb + kEpiPlaneBytes, n0 + c * 16 + 16, m_blk * kBlockM);
+                }
+                bulk_commit();
+              }
+              g += 2;
+            }
+          } else {
 #pragma unroll 2
-          for (int c = 0; c < nch; ++c) {
-            uint32_t a0[16], a1[16];
-            tmem_ld_32x32b_x16(tacc + c * 16, a0);
-            if (SPLIT) tmem_ld_32x32b_x16(tacc1 + c * 16, a1);
-            finish_chunk(c, a0, a1);
+            for (int c = 0; c < nch; ++c) {
+              uint32_t a0[16], a1[16];
+              tmem_ld_32x32b_x16(tacc + c * 16, a0);
+              if (SPLIT) tmem_ld_32x32b_x16(tacc1 + c * 16, a1);
+              finish_chunk(c, a0, a1);
+            }
           }
         }
         tc_fence_before();

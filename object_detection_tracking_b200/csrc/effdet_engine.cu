@@ -152,6 +152,9 @@ EConv* add_pw(b2_effdet* c, const std::string& wname, const std::string& biasnam
   ConvDesc& d = L->d;
   d.B = 1; d.in_H = in.H; d.in_W = in.W; d.Cin = in.C; d.in_pitch_H = in.H; d.in_pitch_W = in.W; d.in_ld = in.C;
   d.Cout = cout_real; d.relu = act;
+  // chunked re-accumulation (conv_tc ACC) only for long reductions: up to K = 512 the truncation bias of the tensor-core
+  // accumulator stays far inside the parity bar and the per-K-block drains would dominate these short-K layers
+  d.acc_kb = in.C <= 512 ? -1 : 0;
   d.out_H = in.H; d.out_W = in.W; d.ldc = out_f32 ? ldc32 : out.C;
   L->w.Cout_pad = pad16(cout_real);
   L->w.K = in.C;
