@@ -61,10 +61,12 @@ struct ConvTcParams {
   int acc_kb;        // ACC: K-blocks per tensor-core accumulation chunk
   int dbg_nodrain;   // perf experiment only (wrong results): skip the TMEM reads of the ACC drain
   int epi_mode;      // 0 = direct global loads/stores per thread, 1 = TMA-staged (residual in, result out)
+  int epi_bufs;      // chunk buffers in the staging ring (4, or 6 = three pairs when a residual is prefetched)
   uint32_t epi_off;  // byte offset of the epilogue staging buffers inside the tile area
 };
 
-constexpr int kEpiBufs = 4;            // ring of 16-column chunk buffers
+constexpr int kEpiBufs = 4;            // ring of 16-column chunk buffers (single-chunk mode; 2 pairs in pair mode)
+constexpr int kEpiBufsMax = 6;         // pair mode with a residual: 3 pairs (the look-ahead load needs one more)
 constexpr int kEpiPlaneBytes = kBlockM * 16 * 2;   // 128 rows x 16 fp16 = 4 KB per plane
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -270,13 +272,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   // 128B swizzle atoms need 1024-byte aligned tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + p.epi_off + kEpiBufs * 2 * kEpiPlaneBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + p.epi_off + p.epi_bufs * 2 * kEpiPlaneBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tmem_full = bars + 2 * kMaxStages;
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;
   uint64_t* res_full = bars + 2 * kMaxStages + 4;                       // [kEpiBufs]
-  uint64_t* c_full = bars + 2 * kMaxStages + 4 + kEpiBufs;              // [2] ACC chunk accumulator ready
+  uint64_t* c_full = bars + 2 * kMaxStages + 4 + kEpiBufsMax;           // [2] ACC chunk accumulator ready
   uint64_t* c_empty = c_full + 2;                                       // [2] ACC chunk accumulator drained
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(c_empty + 2);
   uint8_t* epi = tiles + p.epi_off;
@@ -301,7 +303,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);   // one arrive per epilogue warp
     }
-    for (int i = 0; i < kEpiBufs; ++i) mbar_init(&res_full[i], 1);
+    for (int i = 0; i < kEpiBufsMax; ++i) mbar_init(&res_full[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&c_full[i], 1);
       mbar_init(&c_empty[i], 4);
@@ -461,9 +463,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           la_tile += gridDim.x;
         }
       };
+      // pair mode (block_n a multiple of 32): two chunks per fence / barrier / store group.  Ring = 2 pairs, or 3 pairs when
+      // a residual is prefetched (the load for pair k+2 refills the buffers of pair k-1 while pair k+1 is in flight).
+      const bool pair_mode = (nch & 1) == 0 && (!has_res || p.epi_bufs == kEpiBufsMax);
+      const uint32_t npairs = has_res ? 3u : 2u;
+      uint32_t pidx = 0, la_pidx = 0;
+      auto issue_res_pair = [&]() {
+        if (la_tile >= p.num_tiles) return;
+        const int m_blk = la_tile / p.num_n_blocks;
+        const int n_blk = la_tile - m_blk * p.num_n_blocks;
+        const int col = n_blk * p.block_n + la_c * 16;
+        uint8_t* b = epi + (2 * la_pidx) * buf_bytes;
+        uint64_t* bar = &res_full[la_pidx];
+        mbar_expect_tx(bar, 2 * chunk_bytes);
+        tma_load_2d(b, &tmR_hi, bar, col, m_blk * kBlockM);
+        tma_load_2d(b + buf_bytes, &tmR_hi, bar, col + 16, m_blk * kBlockM);
+        if (SPLIT && p.res_lo != nullptr) {
+          tma_load_2d(b + kEpiPlaneBytes, &tmR_lo, bar, col, m_blk * kBlockM);
+          tma_load_2d(b + buf_bytes + kEpiPlaneBytes, &tmR_lo, bar, col + 16, m_blk * kBlockM);
+        }
+        la_c += 2;
+        if (la_c == nch) {
+          la_c = 0;
+          la_tile += gridDim.x;
+        }
+        if (++la_pidx == npairs) la_pidx = 0;
+      };
       if (elected && has_res) {
-        issue_res(0);
-        issue_res(1);
+        if (pair_mode) {
+          issue_res_pair();
+          issue_res_pair();
+        } else {
+          issue_res(0);
+          issue_res(1);
+        }
       }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int m_blk = tile / p.num_n_blocks;
@@ -515,48 +548,75 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
           ++g;
         };
+        auto finish_pair = [&](int c, uint32_t (&a0)[16], uint32_t (&a1)[16], uint32_t (&b0)[16], uint32_t (&b1)[16]) {
+          uint8_t* bufa = epi + (2 * pidx) * buf_bytes;
+          uint8_t* bufb = bufa + buf_bytes;
+          if (has_res) {
+            mbar_wait(&res_full[pidx], (rph >> pidx) & 1u);
+            rph ^= 1u << pidx;
+          }
+          tmem_ld_wait();
+          epilogue_chunk16_smem<SPLIT>(p, a0, a1, bufa, row, n0 + c * 16, has_res);
+          epilogue_chunk16_smem<SPLIT>(p, b0, b1, bufb, row, n0 + c * 16 + 16, has_res);
+          fence_proxy_async();
+          // every earlier store group must be done reading: the next pair (or the look-ahead residual load issued below)
+          // reuses the buffers of the previous pair, whose store is one pair-time old by now
+          if (elected && g >= 2) bulk_wait_read<0>();
+          named_bar_sync(1, 128);
+          if (elected) {
+            tma_store_2d(&tmO_hi, bufa, n0 + c * 16, m_blk * kBlockM);
+            tma_store_2d(&tmO_hi, bufb, n0 + c * 16 + 16, m_blk * kBlockM);
+            if (SPLIT && p.out_lo != nullptr) {
+              tma_store_2d(&tmO_lo, bufa + kEpiPlaneBytes, n0 + c * 16, m_blk * kBlockM);
+              tma_store_2d(&tmO_lo, bufb + kEpiPlaneBytes, n0 + c * 16 + 16, m_blk * kBlockM);
+            }
+            bulk_commit();
+            if (has_res) issue_res_pair();
+          }
+          g += 2;
+          if (++pidx == npairs) pidx = 0;
+        };
         if (ACC) {
           // fully unrolled: the chunk sums live in registers and need compile-time indices
+          if (pair_mode) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            if (c >= nch) continue;
-            uint32_t a0[16], a1[16];
+            for (int c = 0; c < 8; c += 2) {
+              if (c >= nch) continue;
+              uint32_t a0[16], a1[16], b0[16], b1[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) a0[i] = __float_as_uint(sums[(ACC ? c : 0) * 16 + (ACC ? i : 0)]);
-            if (SPLIT) tmem_ld_32x32b_x16(tacc1 + c * 16, a1);
-            finish_chunk(c, a0, a1);
+              for (int i = 0; i < 16; ++i) {
+                a0[i] = __float_as_uint(sums[(ACC ? c : 0) * 16 + (ACC ? i : 0)]);
+                b0[i] = __float_as_uint(sums[(ACC ? c + 1 : 0) * 16 + (ACC ? i : 0)]);
+              }
+              if (SPLIT) {
+                tmem_ld_32x32b_x16(tacc1 + c * 16, a1);
+                tmem_ld_32x32b_x16(tacc1 + c * 16 + 16, b1);
+              }
+              finish_pair(c, a0, a1, b0, b1);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              if (c >= nch) continue;
+              uint32_t a0[16], a1[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) a0[i] = __float_as_uint(sums[(ACC ? c : 0) * 16 + (ACC ? i : 0)]);
+              if (SPLIT) tmem_ld_32x32b_x16(tacc1 + c * 16, a1);
+              finish_chunk(c, a0, a1);
+            }
           }
         } else {
-          // rolled (x2): 16 unrolled copies of the chunk body overflow the instruction cache (ncu: "no instructions" +
-          // "branch resolving" stalls on the K = 64 EfficientNet expansions)
-          if (!has_res && (nch & 1) == 0) {
-            // two chunks per fence / barrier / store group: the per-chunk membar + named barrier + TMA issue chain is what
-            // bounds short-K layers (ncu: MMA issuer spinning on tmem_empty, epilogue warps never waiting on tmem_full)
+          // rolled: 16 unrolled copies of the chunk body overflow the instruction cache (ncu: "no instructions" +
+          // "branch resolving" stalls on the K = 64 EfficientNet expansions).  The per-chunk membar + named barrier + TMA
+          // issue chain is what bounds short-K layers (ncu: MMA issuer spinning on tmem_empty), hence pairs.
+          if (pair_mode) {
             for (int c = 0; c < nch; c += 2) {
               uint32_t a0[16], a1[16], b0[16], b1[16];
               tmem_ld_32x32b_x16(tacc + c * 16, a0);
               if (SPLIT) tmem_ld_32x32b_x16(tacc1 + c * 16, a1);
               tmem_ld_32x32b_x16(tacc + c * 16 + 16, b0);
               if (SPLIT) tmem_ld_32x32b_x16(tacc1 + c * 16 + 16, b1);
-              uint8_t* bufa = epi + (g & (kEpiBufs - 1)) * buf_bytes;
-              uint8_t* bufb = epi + ((g + 1) & (kEpiBufs - 1)) * buf_bytes;
-              tmem_ld_wait();
-              epilogue_chunk16_smem<SPLIT>(p, a0, a1, bufa, row, n0 + c * 16, false);
-              epilogue_chunk16_smem<SPLIT>(p, b0, b1, bufb, row, n0 + c * 16 + 16, false);
-              fence_proxy_async();
-              // the next pair overwrites the buffers of the previous pair: its store (one pair-time old) must be done reading
-              if (elected && g >= 2) bulk_wait_read<0>();
-              named_bar_sync(1, 128);
-              if (elected) {
-                tma_store_2d(&tmO_hi, bufa, n0 + c * 16, m_blk * kBlockM);
-                tma_store_2d(&tmO_hi, bufb, n0 + c * 16 + 16, m_blk * kBlockM);
-                if (SPLIT && p.out_lo != nullptr) {
-                  tma_store_2d(&tmO_lo, bufa + kEpiPlaneBytes, n0 + c * 16, m_blk * kBlockM);
-                  tma_store_2d(&tmO_lo, bufb + kEpiPlaneBytes, n0 + c * 16 + 16, m_blk * kBlockM);
-                }
-                bulk_commit();
-              }
-              g += 2;
+              finish_pair(c, a0, a1, b0, b1);
             }
           } else {
 #pragma unroll 2
@@ -747,7 +807,17 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   p.idesc = make_idesc_f16(kBlockM, p.block_n);
   p.b_bytes = static_cast<uint32_t>(p.block_n) * kBlockK * 2;
   p.stage_bytes = (kABytes + p.b_bytes) * (split ? 2 : 1);
-  const int epi_bytes = kEpiBufs * 2 * kEpiPlaneBytes;   // 32 KB staging ring (always reserved)
+  // TMA-staged epilogue: fp16 plane output with a 1:1 row mapping (no placement offset, no shifted residual)
+  {
+    const bool one_to_one = d.off_h == 0 && d.off_w == 0 && d.out_H == Ho && d.out_W == Wo;
+    const bool res_ok = io.res_hi == nullptr || (d.res_shift == 0 && d.res_H == d.out_H && d.res_W == d.out_W);
+    p.epi_mode = (io.out_f32 == nullptr && one_to_one && res_ok && d.force_epi_mode != 0) ? 1 : 0;
+    if (getenv("B2_EPI_DIRECT") != nullptr) p.epi_mode = 0;   // test hook: exercise the per-thread epilogue
+  }
+  // staging ring: 4 chunk buffers (32 KB); 6 (48 KB = three pairs) when a residual is prefetched in pair mode
+  p.epi_bufs = (p.epi_mode == 1 && io.res_hi != nullptr && ((p.block_n >> 4) & 1) == 0 && getenv("B2_EPI_RING4") == nullptr)
+                   ? kEpiBufsMax : kEpiBufs;
+  const int epi_bytes = p.epi_bufs * 2 * kEpiPlaneBytes;
   p.num_stages = (kSmemBudget + 24 * 1024 - epi_bytes) / static_cast<int>(p.stage_bytes);
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   B2_CHECK(p.num_stages >= 2, "conv_tc: tile too large for shared memory");
@@ -778,12 +848,6 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   pl->acc = split && d.acc_kb >= 0 && p.num_kb > p.acc_kb && getenv("B2_NO_ACC") == nullptr;
   pl->grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   pl->smem_bytes = static_cast<size_t>(p.num_stages) * p.stage_bytes + epi_bytes + 1024 /*align*/ + 256 /*barriers*/;
-  // TMA-staged epilogue: fp16 plane output with a 1:1 row mapping (no placement offset, no shifted residual)
-  const bool one_to_one = d.off_h == 0 && d.off_w == 0 && d.out_H == Ho && d.out_W == Wo;
-  const bool res_ok = io.res_hi == nullptr || (d.res_shift == 0 && d.res_H == d.out_H && d.res_W == d.out_W);
-  p.epi_mode = (io.out_f32 == nullptr && one_to_one && res_ok && d.force_epi_mode != 0) ? 1 : 0;
-  if (getenv("B2_EPI_DIRECT") != nullptr) p.epi_mode = 0;   // test hook: exercise the per-thread epilogue
-
   const int in_ld = d.in_ld > 0 ? d.in_ld : d.Cin;
   const bool plain = (d.R == 1 && d.S == 1 && d.stride == 1 && d.pad_t == 0 && d.pad_b == 0 && d.pad_l == 0 &&
                       d.pad_r == 0 && d.in_H == d.in_pitch_H && d.in_W == d.in_pitch_W);
