@@ -35,10 +35,18 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                 // fp16 elements = one 128-byte swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 256;
+#ifndef B2_EPI_HALVES
+#define B2_EPI_HALVES 2
+#endif
+#ifndef B2_SETMAXNREG
+#define B2_SETMAXNREG 1
+#endif
+constexpr int kEpiHalves = B2_EPI_HALVES;   // column halves of a tile handled by separate epilogue warp quartets
+constexpr int kEpiWarps = 4 * kEpiHalves;   // warps 4..: TMEM lane quarter = warp & 3, column half = (warp - 4) >> 2
+constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 8;
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kSmemBudget = 224 * 1024;     // pipeline stages + epilogue staging (alignment slack and barriers on top)
 
 struct ConvTcParams {
   int M, Ho, Wo, HoWo;
@@ -61,12 +69,13 @@ struct ConvTcParams {
   int acc_kb;        // ACC: K-blocks per tensor-core accumulation chunk
   int dbg_nodrain;   // perf experiment only (wrong results): skip the TMEM reads of the ACC drain
   int epi_mode;      // 0 = direct global loads/stores per thread, 1 = TMA-staged (residual in, result out)
-  int epi_bufs;      // chunk buffers in the staging ring (4, or 6 = three pairs when a residual is prefetched)
+  int epi_grp;       // staged: 16-column chunks per fence / barrier / store group (1 or 2)
+  int epi_slots;     // staged: group slots in each column half's staging ring (2, or 3 when a residual is prefetched)
+  uint32_t epi_chunk_bytes;   // staged: bytes of one chunk buffer (4 KB hi plane, + 4 KB lo plane in split precision)
   uint32_t epi_off;  // byte offset of the epilogue staging buffers inside the tile area
 };
 
-constexpr int kEpiBufs = 4;            // ring of 16-column chunk buffers (single-chunk mode; 2 pairs in pair mode)
-constexpr int kEpiBufsMax = 6;         // pair mode with a residual: 3 pairs (the look-ahead load needs one more)
+constexpr int kEpiSlotsMax = 3;
 constexpr int kEpiPlaneBytes = kBlockM * 16 * 2;   // 128 rows x 16 fp16 = 4 KB per plane
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -74,18 +83,10 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// 16 consecutive output channels of one pixel: bias, residual, ReLU, store (fp16 hi/lo planes or fp32).
+// 16 consecutive output channels of one pixel (v = accumulator value): bias, residual, activation, store
+// (fp16 hi/lo planes or fp32) straight to global memory.
 template <bool SPLIT>
-__device__ __forceinline__ void epilogue_chunk16(const ConvTcParams& p, const uint32_t (&a0)[16],
-                                                 const uint32_t (&a1)[16], size_t opix, size_t rpix, int n,
-                                                 bool valid) {
-  float v[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    v[j] = __uint_as_float(a0[j]);
-    if (SPLIT) v[j] = fmaf(__uint_as_float(a1[j]), kLoInv, v[j]);
-  }
-  if (!valid) return;
+__device__ __forceinline__ void epilogue_chunk16(const ConvTcParams& p, float (&v)[16], size_t opix, size_t rpix, int n) {
   const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -157,16 +158,10 @@ __device__ __forceinline__ void epilogue_chunk16(const ConvTcParams& p, const ui
 
 // Same math on a chunk whose residual sits in (and whose result goes back to) a 32-byte-swizzled
 // shared-memory buffer [128 rows][16 fp16]: row r, 16-byte half jj lives at r*32 + ((jj ^ ((r>>2)&1)) * 16).
+// The lo plane (split precision) follows the hi plane at +kEpiPlaneBytes.
 template <bool SPLIT>
-__device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, const uint32_t (&a0)[16],
-                                                      const uint32_t (&a1)[16], uint8_t* buf, int row, int n,
-                                                      bool has_res) {
-  float v[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    v[j] = __uint_as_float(a0[j]);
-    if (SPLIT) v[j] = fmaf(__uint_as_float(a1[j]), kLoInv, v[j]);
-  }
+__device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, float (&v)[16], uint8_t* buf, int row, int n,
+                                                      bool has_res, bool has_res_lo) {
   const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -193,7 +188,7 @@ __device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, con
         v[8 * j + 2 * t + 1] += f.y;
       }
     }
-    if (SPLIT) {
+    if (SPLIT && has_res_lo) {
       uint4 l[2] = {*lo0, *lo1};
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -231,35 +226,45 @@ __device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, con
   }
 }
 
-// ACC drain: fold one chunk accumulator (128 TMEM columns of this thread's row) into the per-thread
-// running sums with round-to-nearest adds.  Four 16-column tcgen05.ld are in flight per wait.
-__device__ __forceinline__ void acc_drain(float (&sums)[128], uint32_t tsrc, int nch, bool first) {
-#pragma unroll
-  for (int cc = 0; cc < 8; cc += 4) {
-    if (cc < nch) {
-      uint32_t t[4][16];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (cc + u < nch) tmem_ld_32x32b_x16(tsrc + (cc + u) * 16, t[u]);
-      tmem_ld_wait();
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (cc + u < nch) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            sums[(cc + u) * 16 + i] =
-                first ? __uint_as_float(t[u][i]) : __fadd_rn(sums[(cc + u) * 16 + i], __uint_as_float(t[u][i]));
-        }
-    }
-  }
-}
-
 // ACC (split precision only): the tensor core adds into its fp32 accumulator with truncation (round
 // toward zero), a bias that grows with the number of accumulation steps (K/16) and compounds through 100+
 // layers.  With ACC the hi*hi accumulator is restarted every kAccChunkKb K-blocks in alternating TMEM
 // buffers and the epilogue warps sum the chunk results in registers with round-to-nearest fp32 adds
 // (overlapped with the MMAs of the next chunk), which brings the result to CUDA-core fp32 accuracy.
 constexpr int kAccChunkKb = 1;   // default: restart every K-block (64 K-elements = 4 truncating accumulations)
+constexpr int kAccMaxChunks = 8 / kEpiHalves; // ACC tiles are at most 128 columns wide -> chunks of 16 per column half
+
+// ACC drain: fold this thread's share (my_n chunks of 16 columns of its row) of one chunk accumulator into the
+// running sums with round-to-nearest adds.  All tcgen05.ld are in flight before the single wait; the accumulator is
+// handed back to the MMA issuer as soon as the values sit in registers, before the adds.
+template <bool FMA_LO>
+__device__ __forceinline__ void acc_fold(float (&sums)[kAccMaxChunks * 16], uint32_t tsrc, int my_n, uint64_t* release_bar,
+                                         int lane) {
+  auto release = [&]() {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(release_bar);
+  };
+  auto add = [&](int u, const uint32_t (&t)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      sums[u * 16 + i] = FMA_LO ? fmaf(__uint_as_float(t[i]), kLoInv, sums[u * 16 + i])
+                                : __fadd_rn(sums[u * 16 + i], __uint_as_float(t[i]));
+  };
+  if (my_n == 0) release();
+#pragma unroll
+  for (int u0 = 0; u0 < kAccMaxChunks; u0 += 2) {
+    if (u0 < my_n) {
+      uint32_t t0[16], t1[16];
+      tmem_ld_32x32b_x16(tsrc + u0 * 16, t0);
+      if (u0 + 1 < my_n) tmem_ld_32x32b_x16(tsrc + (u0 + 1) * 16, t1);
+      tmem_ld_wait();
+      if (u0 + 2 >= my_n) release();   // last batch: the accumulator now sits in registers
+      add(u0, t0);
+      if (u0 + 1 < my_n) add(u0 + 1, t1);
+    }
+  }
+}
 
 template <bool SPLIT, bool ACC>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -272,13 +277,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   // 128B swizzle atoms need 1024-byte aligned tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + p.epi_off + p.epi_bufs * 2 * kEpiPlaneBytes);
+  const uint32_t slot_bytes = static_cast<uint32_t>(p.epi_grp) * p.epi_chunk_bytes;
+  const uint32_t ring_bytes = static_cast<uint32_t>(p.epi_slots) * slot_bytes;   // per column half
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + p.epi_off + kEpiHalves * ring_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tmem_full = bars + 2 * kMaxStages;
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;
-  uint64_t* res_full = bars + 2 * kMaxStages + 4;                       // [kEpiBufs]
-  uint64_t* c_full = bars + 2 * kMaxStages + 4 + kEpiBufsMax;           // [2] ACC chunk accumulator ready
+  uint64_t* res_full = bars + 2 * kMaxStages + 4;                       // [2 halves][kEpiSlotsMax]
+  uint64_t* c_full = bars + 2 * kMaxStages + 4 + 2 * kEpiSlotsMax;      // [2] ACC chunk accumulator ready
   uint64_t* c_empty = c_full + 2;                                       // [2] ACC chunk accumulator drained
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(c_empty + 2);
   uint8_t* epi = tiles + p.epi_off;
@@ -301,12 +308,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);   // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], kEpiWarps);   // one arrive per epilogue warp
     }
-    for (int i = 0; i < kEpiBufsMax; ++i) mbar_init(&res_full[i], 1);
+    for (int i = 0; i < 2 * kEpiSlotsMax; ++i) mbar_init(&res_full[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&c_full[i], 1);
-      mbar_init(&c_empty[i], 4);
+      mbar_init(&c_empty[i], kEpiWarps);
     }
     fence_mbar_init();
     fence_proxy_async();
@@ -326,7 +333,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   // accumulator stage s: acc0 at column s*256, acc1 (split) at s*256 + 128
   const uint32_t acc_stage_cols = 256;
 
-  if (warp == 0) {
+  // ACC: the epilogue warps hold 64 running sums per thread on top of the output-stage state; take registers from the
+  // (tiny) producer / MMA warpgroup.  384 threads: 128 x 56 + 256 x 224 = 64512 <= 64K.
+  if (warp < 4) {
+   if (ACC && B2_SETMAXNREG) setmaxnreg_dec<56>();
+   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
@@ -390,6 +401,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (ACC && kq == 0) {
             const uint32_t cbuf = qg & 1;
             mbar_wait(&c_empty[cbuf], ((qg >> 1) & 1) ^ 1);
+            tc_fence_after();
             acc0 = tmem_base + cbuf * 128;
           }
           mbar_wait(&full_bar[stage], phase);
@@ -429,222 +441,77 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
       }
     }
-  } else if (warp >= 4) {
+   }
+  } else if (warp < 4 + kEpiWarps) {
+    if (ACC && B2_SETMAXNREG) setmaxnreg_inc<kEpiHalves == 2 ? 224 : 240>();
     // ===================== epilogue =====================
-    const int ew = warp & 3;                 // TMEM lane quarter this warp may access
+    // Eight warps: warp w reads TMEM lanes 32*(w&3).. (its row quarter of the tile) and owns the column half
+    // hf = (w-4)>>2 of the tile: chunks [c_beg, c_end) of 16 columns.  The two halves run independently (own staging
+    // ring, own named barrier, own elected TMA thread); together they halve the time per tile of the epilogue, which
+    // bounds the short-K layers and -- in ACC mode, where the same warps must keep draining chunk accumulators --
+    // stalls the MMA issuer for as long as a tile's output stage takes.
+    const int ew = warp & 3;
+    const int hf = (warp - 4) >> 2;
     const int row = ew * 32 + lane;
+    const int nch = p.block_n >> 4;
+    const int h0 = kEpiHalves == 2 ? (nch + 1) >> 1 : nch;
+    const int c_beg = hf ? h0 : 0;
+    const int my_n = hf ? nch - h0 : h0;
+    const uint32_t lane_off = static_cast<uint32_t>(ew * 32) << 16;
     int as = 0;
     uint32_t aphase = 0;
     uint32_t qe = 0;     // ACC: running chunk counter (mirrors the MMA issuer's)
-    if (p.epi_mode == 1) {
-      // ---- TMA-staged: residual chunk arrives in a swizzled smem buffer (TMA load, issued two chunks
-      // ahead, also across tile boundaries), the result overwrites it in place and leaves by TMA store.
-      const bool has_res = p.res_hi != nullptr;
-      const bool elected = threadIdx.x == 128;
-      const int nch = p.block_n >> 4;
-      const uint32_t chunk_bytes = kEpiPlaneBytes * ((SPLIT && p.res_lo != nullptr) ? 2 : 1);
-      const uint32_t buf_bytes = 2 * kEpiPlaneBytes;
-      uint32_t g = 0;          // global chunk counter -> buffer g & 3
-      uint32_t rph = 0;        // phase bits of res_full[]
-      // look-ahead cursor (chunk g + 2), advanced only by the elected thread
-      int la_tile = blockIdx.x, la_c = 0;
-      auto issue_res = [&](uint32_t gi) {
-        if (la_tile >= p.num_tiles) return;
-        const int m_blk = la_tile / p.num_n_blocks;
-        const int n_blk = la_tile - m_blk * p.num_n_blocks;
-        const int col = n_blk * p.block_n + la_c * 16;
-        uint8_t* b = epi + (gi & (kEpiBufs - 1)) * buf_bytes;
-        mbar_expect_tx(&res_full[gi & (kEpiBufs - 1)], chunk_bytes);
-        tma_load_2d(b, &tmR_hi, &res_full[gi & (kEpiBufs - 1)], col, m_blk * kBlockM);
-        if (SPLIT && p.res_lo != nullptr)
-          tma_load_2d(b + kEpiPlaneBytes, &tmR_lo, &res_full[gi & (kEpiBufs - 1)], col, m_blk * kBlockM);
-        if (++la_c == nch) {
-          la_c = 0;
-          la_tile += gridDim.x;
-        }
-      };
-      // pair mode (block_n a multiple of 32): two chunks per fence / barrier / store group.  Ring = 2 pairs, or 3 pairs when
-      // a residual is prefetched (the load for pair k+2 refills the buffers of pair k-1 while pair k+1 is in flight).
-      const bool pair_mode = (nch & 1) == 0 && (!has_res || p.epi_bufs == kEpiBufsMax);
-      const uint32_t npairs = has_res ? 3u : 2u;
-      uint32_t pidx = 0, la_pidx = 0;
-      auto issue_res_pair = [&]() {
-        if (la_tile >= p.num_tiles) return;
-        const int m_blk = la_tile / p.num_n_blocks;
-        const int n_blk = la_tile - m_blk * p.num_n_blocks;
-        const int col = n_blk * p.block_n + la_c * 16;
-        uint8_t* b = epi + (2 * la_pidx) * buf_bytes;
-        uint64_t* bar = &res_full[la_pidx];
-        mbar_expect_tx(bar, 2 * chunk_bytes);
-        tma_load_2d(b, &tmR_hi, bar, col, m_blk * kBlockM);
-        tma_load_2d(b + buf_bytes, &tmR_hi, bar, col + 16, m_blk * kBlockM);
-        if (SPLIT && p.res_lo != nullptr) {
-          tma_load_2d(b + kEpiPlaneBytes, &tmR_lo, bar, col, m_blk * kBlockM);
-          tma_load_2d(b + buf_bytes + kEpiPlaneBytes, &tmR_lo, bar, col + 16, m_blk * kBlockM);
-        }
-        la_c += 2;
-        if (la_c == nch) {
-          la_c = 0;
-          la_tile += gridDim.x;
-        }
-        if (++la_pidx == npairs) la_pidx = 0;
-      };
-      if (elected && has_res) {
-        if (pair_mode) {
-          issue_res_pair();
-          issue_res_pair();
-        } else {
-          issue_res(0);
-          issue_res(1);
-        }
+
+    // ---- staged output state (epi_mode 1): residual chunks arrive in swizzled smem buffers (TMA loads issued
+    // epi_slots-1 groups ahead, also across tile boundaries), results overwrite them in place and leave by TMA store.
+    const bool staged = p.epi_mode == 1;
+    const bool has_res = p.res_hi != nullptr;
+    const bool res_lo = SPLIT && p.res_lo != nullptr;
+    const bool elected = threadIdx.x == 128 + hf * 128;
+    const int grp = p.epi_grp;
+    const int nslots = p.epi_slots;
+    // before group k+1 may overwrite its slot, the store of group k+1-nslots must be done reading it; with a residual
+    // the look-ahead load issued right after store k refills the slot of group k-1
+    const bool wait_all_reads = has_res || nslots == 2;
+    uint8_t* ring = epi + hf * ring_bytes;
+    uint64_t* rfull = res_full + hf * kEpiSlotsMax;
+    const int bar_id = 1 + hf;
+    int slot = 0, la_slot = 0;
+    uint32_t rph = 0;        // phase bits of rfull[]
+    int la_tile = blockIdx.x, la_c = 0;   // look-ahead cursor of the residual prefetch (elected thread only)
+    auto issue_res_group = [&]() {
+      if (la_tile >= p.num_tiles || my_n == 0) return;
+      const int m_blk = la_tile / p.num_n_blocks;
+      const int n_blk = la_tile - m_blk * p.num_n_blocks;
+      const int gn = (my_n - la_c) < grp ? (my_n - la_c) : grp;
+      const int col = n_blk * p.block_n + (c_beg + la_c) * 16;
+      uint8_t* b = ring + la_slot * slot_bytes;
+      uint64_t* bar = &rfull[la_slot];
+      mbar_expect_tx(bar, gn * kEpiPlaneBytes * (res_lo ? 2 : 1));
+      for (int u = 0; u < gn; ++u) {
+        tma_load_2d(b + u * p.epi_chunk_bytes, &tmR_hi, bar, col + u * 16, m_blk * kBlockM);
+        if (res_lo) tma_load_2d(b + u * p.epi_chunk_bytes + kEpiPlaneBytes, &tmR_lo, bar, col + u * 16, m_blk * kBlockM);
       }
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.num_n_blocks;
-        const int n_blk = tile - m_blk * p.num_n_blocks;
-        const int n0 = n_blk * p.block_n;
-        float sums[128];
-        if (ACC) {
-          const int nq = (p.num_kb + p.acc_kb - 1) / p.acc_kb;
-          const int nch_acc = p.block_n >> 4;
-          for (int q = 0; q < nq; ++q, ++qe) {
-            const uint32_t cbuf = qe & 1;
-            mbar_wait(&c_full[cbuf], (qe >> 1) & 1);
-            tc_fence_after();
-            const uint32_t tsrc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + cbuf * 128;
-            if (!p.dbg_nodrain) acc_drain(sums, tsrc, nch_acc, q == 0);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&c_empty[cbuf]);
-          }
-        }
-        mbar_wait(&tmem_full[as], aphase);
-        tc_fence_after();
-        const uint32_t lane_off = static_cast<uint32_t>(ew * 32) << 16;
-        const uint32_t tacc = tmem_base + lane_off + as * acc_stage_cols;
-        const uint32_t tacc1 = ACC ? tmem_base + lane_off + 256 + as * 128 : tacc + 128;
-        // one 16-column chunk: TMEM -> registers -> (+bias, +residual, activation, fp16 pair) -> swizzled smem -> TMA store
-        auto finish_chunk = [&](int c, uint32_t (&a0)[16], uint32_t (&a1)[16]) {
-          const uint32_t j = g & (kEpiBufs - 1);
-          uint8_t* buf = epi + j * buf_bytes;
-          if (has_res) {
-            mbar_wait(&res_full[j], (rph >> j) & 1u);
-            rph ^= 1u << j;
-          }
-          tmem_ld_wait();
-          epilogue_chunk16_smem<SPLIT>(p, a0, a1, buf, row, n0 + c * 16, has_res);
-          fence_proxy_async();
-          if (elected && g >= 1) {
-            // with a residual the look-ahead load refills buffer (g+2)&3 right away: store(g-2) must be done reading;
-            // without one the next writer of a buffer is chunk g+1 into (g+1)&3: store(g-3) done is enough
-            if (has_res) bulk_wait_read<1>();
-            else bulk_wait_read<2>();
-          }
-          named_bar_sync(1, 128);
-          if (elected) {
-            tma_store_2d(&tmO_hi, buf, n0 + c * 16, m_blk * kBlockM);
-            if (SPLIT && p.out_lo != nullptr) tma_store_2d(&tmO_lo, buf + kEpiPlaneBytes, n0 + c * 16, m_blk * kBlockM);
-            bulk_commit();
-            if (has_res) issue_res(g + 2);
-          }
-          ++g;
-        };
-        auto finish_pair = [&](int c, uint32_t (&a0)[16], uint32_t (&a1)[16], uint32_t (&b0)[16], uint32_t (&b1)[16]) {
-          uint8_t* bufa = epi + (2 * pidx) * buf_bytes;
-          uint8_t* bufb = bufa + buf_bytes;
-          if (has_res) {
-            mbar_wait(&res_full[pidx], (rph >> pidx) & 1u);
-            rph ^= 1u << pidx;
-          }
-          tmem_ld_wait();
-          epilogue_chunk16_smem<SPLIT>(p, a0, a1, bufa, row, n0 + c * 16, has_res);
-          epilogue_chunk16_smem<SPLIT>(p, b0, b1, bufb, row, n0 + c * 16 + 16, has_res);
-          fence_proxy_async();
-          // every earlier store group must be done reading: the next pair (or the look-ahead residual load issued below)
-          // reuses the buffers of the previous pair, whose store is one pair-time old by now
-          if (elected && g >= 2) bulk_wait_read<0>();
-          named_bar_sync(1, 128);
-          if (elected) {
-            tma_store_2d(&tmO_hi, bufa, n0 + c * 16, m_blk * kBlockM);
-            tma_store_2d(&tmO_hi, bufb, n0 + c * 16 + 16, m_blk * kBlockM);
-            if (SPLIT && p.out_lo != nullptr) {
-              tma_store_2d(&tmO_lo, bufa + kEpiPlaneBytes, n0 + c * 16, m_blk * kBlockM);
-              tma_store_2d(&tmO_lo, bufb + kEpiPlaneBytes, n0 + c * 16 + 16, m_blk * kBlockM);
-            }
-            bulk_commit();
-            if (has_res) issue_res_pair();
-          }
-          g += 2;
-          if (++pidx == npairs) pidx = 0;
-        };
-        if (ACC) {
-          // fully unrolled: the chunk sums live in registers and need compile-time indices
-          if (pair_mode) {
-#pragma unroll
-            for (int c = 0; c < 8; c += 2) {
-              if (c >= nch) continue;
-              uint32_t a0[16], a1[16], b0[16], b1[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                a0[i] = __float_as_uint(sums[(ACC ? c : 0) * 16 + (ACC ? i : 0)]);
-                b0[i] = __float_as_uint(sums[(ACC ? c + 1 : 0) * 16 + (ACC ? i : 0)]);
-              }
-              if (SPLIT) {
-                tmem_ld_32x32b_x16(tacc1 + c * 16, a1);
-                tmem_ld_32x32b_x16(tacc1 + c * 16 + 16, b1);
-              }
-              finish_pair(c, a0, a1, b0, b1);
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              if (c >= nch) continue;
-              uint32_t a0[16], a1[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) a0[i] = __float_as_uint(sums[(ACC ? c : 0) * 16 + (ACC ? i : 0)]);
-              if (SPLIT) tmem_ld_32x32b_x16(tacc1 + c * 16, a1);
-              finish_chunk(c, a0, a1);
-            }
-          }
-        } else {
-          // rolled: 16 unrolled copies of the chunk body overflow the instruction cache (ncu: "no instructions" +
-          // "branch resolving" stalls on the K = 64 EfficientNet expansions).  The per-chunk membar + named barrier + TMA
-          // issue chain is what bounds short-K layers (ncu: MMA issuer spinning on tmem_empty), hence pairs.
-          if (pair_mode) {
-            for (int c = 0; c < nch; c += 2) {
-              uint32_t a0[16], a1[16], b0[16], b1[16];
-              tmem_ld_32x32b_x16(tacc + c * 16, a0);
-              if (SPLIT) tmem_ld_32x32b_x16(tacc1 + c * 16, a1);
-              tmem_ld_32x32b_x16(tacc + c * 16 + 16, b0);
-              if (SPLIT) tmem_ld_32x32b_x16(tacc1 + c * 16 + 16, b1);
-              finish_pair(c, a0, a1, b0, b1);
-            }
-          } else {
-#pragma unroll 2
-            for (int c = 0; c < nch; ++c) {
-              uint32_t a0[16], a1[16];
-              tmem_ld_32x32b_x16(tacc + c * 16, a0);
-              if (SPLIT) tmem_ld_32x32b_x16(tacc1 + c * 16, a1);
-              finish_chunk(c, a0, a1);
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[as]);
-        if (++as == 2) {
-          as = 0;
-          aphase ^= 1;
-        }
+      la_c += gn;
+      if (la_c >= my_n) {
+        la_c = 0;
+        la_tile += gridDim.x;
       }
-      if (elected) bulk_wait_all();   // the output must be globally written before the CTA retires
-    } else {
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.num_n_blocks;
-        const int n_blk = tile - m_blk * p.num_n_blocks;
+      if (++la_slot == nslots) la_slot = 0;
+    };
+    if (staged && elected && has_res)
+      for (int i = 0; i < nslots - 1; ++i) issue_res_group();
+
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.num_n_blocks;
+      const int n_blk = tile - m_blk * p.num_n_blocks;
+      const int n0 = n_blk * p.block_n;
+      // direct mode: this thread's output / residual pixel
+      size_t opix = 0, rpix = 0;
+      bool valid = true;
+      if (!staged) {
         const int m = m_blk * kBlockM + row;
-        const int n0 = n_blk * p.block_n;
-        const bool valid = m < p.M;
-        size_t opix = 0, rpix = 0;
+        valid = m < p.M;
         if (valid) {
           const int img = m / p.HoWo;
           const int rem = m - img * p.HoWo;
@@ -653,50 +520,95 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           opix = (static_cast<size_t>(img) * p.out_H + pp) * p.out_W + qq;
           rpix = (static_cast<size_t>(img) * p.res_H + (pp >> p.res_shift)) * p.res_W + (qq >> p.res_shift);
         }
-        float sums[128];
-        if (ACC) {
-          const int nq = (p.num_kb + p.acc_kb - 1) / p.acc_kb;
-          const int nch_acc = p.block_n >> 4;
-          for (int q = 0; q < nq; ++q, ++qe) {
-            const uint32_t cbuf = qe & 1;
-            mbar_wait(&c_full[cbuf], (qe >> 1) & 1);
-            tc_fence_after();
-            const uint32_t tsrc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + cbuf * 128;
-            if (!p.dbg_nodrain) acc_drain(sums, tsrc, nch_acc, q == 0);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&c_empty[cbuf]);
-          }
+      }
+      // one finished chunk (relative index c in this half): bias / residual / activation, then out
+      auto chunk_out = [&](int c, float (&v)[16]) {
+        const int n = n0 + (c_beg + c) * 16;
+        if (!staged) {
+          if (valid) epilogue_chunk16<SPLIT>(p, v, opix, rpix, n);
+          return;
         }
+        const int u = grp == 2 ? (c & 1) : 0;      // position inside the group
+        uint8_t* sb = ring + slot * slot_bytes;
+        if (u == 0 && has_res) {
+          mbar_wait(&rfull[slot], (rph >> slot) & 1u);
+          rph ^= 1u << slot;
+        }
+        epilogue_chunk16_smem<SPLIT>(p, v, sb + u * p.epi_chunk_bytes, row, n, has_res, res_lo);
+        if (u == grp - 1 || c == my_n - 1) {
+          fence_proxy_async();
+          if (elected) {
+            if (wait_all_reads) bulk_wait_read<0>();
+            else bulk_wait_read<1>();
+          }
+          named_bar_sync(bar_id, 128);
+          if (elected) {
+            const int nb = n - u * 16;
+            for (int t = 0; t <= u; ++t) {
+              tma_store_2d(&tmO_hi, sb + t * p.epi_chunk_bytes, nb + t * 16, m_blk * kBlockM);
+              if (SPLIT && p.out_lo != nullptr)
+                tma_store_2d(&tmO_lo, sb + t * p.epi_chunk_bytes + kEpiPlaneBytes, nb + t * 16, m_blk * kBlockM);
+            }
+            bulk_commit();
+            if (has_res) issue_res_group();
+          }
+          if (++slot == nslots) slot = 0;
+        }
+      };
+
+      if (ACC) {
+        float sums[kAccMaxChunks * 16];
+#pragma unroll
+        for (int i = 0; i < kAccMaxChunks * 16; ++i) sums[i] = 0.0f;
+        const int nq = (p.num_kb + p.acc_kb - 1) / p.acc_kb;
+        for (int q = 0; q < nq; ++q, ++qe) {
+          const uint32_t cbuf = qe & 1;
+          mbar_wait(&c_full[cbuf], (qe >> 1) & 1);
+          tc_fence_after();
+          acc_fold<false>(sums, tmem_base + lane_off + cbuf * 128 + c_beg * 16, p.dbg_nodrain ? 0 : my_n, &c_empty[cbuf], lane);
+        }
+        // the correction accumulator (hi*lo + lo*hi) is folded into the sums right away, which hands the tile's TMEM
+        // stage back before the output stage starts
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
-        const uint32_t lane_off = static_cast<uint32_t>(ew * 32) << 16;
-        const uint32_t tacc = tmem_base + lane_off + as * acc_stage_cols;
-        const uint32_t tacc1 = ACC ? tmem_base + lane_off + 256 + as * 128 : tacc + 128;
-        const int nch = p.block_n >> 4;
+        acc_fold<true>(sums, tmem_base + lane_off + 256 + as * 128 + c_beg * 16, my_n, &tmem_empty[as], lane);
 #pragma unroll
-        for (int c = 0; c < (ACC ? 8 : 16); ++c) {
-          if (c >= nch) continue;
-          uint32_t a0[16], a1[16];
-          if (ACC) {
+        for (int c = 0; c < kAccMaxChunks; ++c) {
+          if (c < my_n) {
+            float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) a0[i] = __float_as_uint(sums[(ACC ? c : 0) * 16 + (ACC ? i : 0)]);
-          } else {
-            tmem_ld_32x32b_x16(tacc + c * 16, a0);
+            for (int i = 0; i < 16; ++i) v[i] = sums[(ACC ? c : 0) * 16 + i];
+            chunk_out(c, v);
           }
+        }
+      } else {
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + lane_off + as * acc_stage_cols + c_beg * 16;
+        const uint32_t tacc1 = tacc + 128;
+        for (int c = 0; c < my_n; ++c) {
+          uint32_t a0[16], a1[16];
+          tmem_ld_32x32b_x16(tacc + c * 16, a0);
           if (SPLIT) tmem_ld_32x32b_x16(tacc1 + c * 16, a1);
           tmem_ld_wait();
-          epilogue_chunk16<SPLIT>(p, a0, a1, opix, rpix, n0 + c * 16, valid);
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v[i] = __uint_as_float(a0[i]);
+            if (SPLIT) v[i] = fmaf(__uint_as_float(a1[i]), kLoInv, v[i]);
+          }
+          chunk_out(c, v);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[as]);
-        if (++as == 2) {
-          as = 0;
-          aphase ^= 1;
-        }
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
       }
     }
+    if (staged && elected) bulk_wait_all();   // the output must be globally written before the CTA retires
   }
   tc_fence_before();
   __syncthreads();
@@ -814,11 +726,31 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
     p.epi_mode = (io.out_f32 == nullptr && one_to_one && res_ok && d.force_epi_mode != 0) ? 1 : 0;
     if (getenv("B2_EPI_DIRECT") != nullptr) p.epi_mode = 0;   // test hook: exercise the per-thread epilogue
   }
-  // staging ring: 4 chunk buffers (32 KB); 6 (48 KB = three pairs) when a residual is prefetched in pair mode
-  p.epi_bufs = (p.epi_mode == 1 && io.res_hi != nullptr && ((p.block_n >> 4) & 1) == 0 && getenv("B2_EPI_RING4") == nullptr)
-                   ? kEpiBufsMax : kEpiBufs;
-  const int epi_bytes = p.epi_bufs * 2 * kEpiPlaneBytes;
-  p.num_stages = (kSmemBudget + 24 * 1024 - epi_bytes) / static_cast<int>(p.stage_bytes);
+  // staging rings (one per column half of the tile).  A group = epi_grp chunks of 16 columns that share one fence /
+  // barrier / TMA-store round; a ring = epi_slots groups.  With a residual: three slots (the prefetch runs two groups
+  // ahead); without: two.  Two-chunk groups are used when that still leaves three pipeline stages (two with a residual:
+  // those layers are bound by the output stage, not by operand latency).
+  {
+    const int nch = p.block_n >> 4;
+    const bool has_res = io.res_hi != nullptr;
+    p.epi_chunk_bytes = static_cast<uint32_t>(kEpiPlaneBytes) * (split ? 2 : 1);
+    p.epi_slots = has_res ? 3 : 2;
+    p.epi_grp = ((kEpiHalves == 2 ? (nch + 1) / 2 : nch) >= 2) ? 2 : 1;
+    auto stages_for = [&](int grp) {
+      const int epi = kEpiHalves * p.epi_slots * grp * static_cast<int>(p.epi_chunk_bytes);
+      return (kSmemBudget - epi) / static_cast<int>(p.stage_bytes);
+    };
+    if (p.epi_grp == 2 && stages_for(2) < (has_res ? 2 : 3) && stages_for(1) > stages_for(2)) p.epi_grp = 1;
+    if (const char* e = getenv("B2_EPI_GRP")) p.epi_grp = atoi(e) == 2 ? 2 : 1;   // experiment hooks
+    if (const char* e = getenv("B2_EPI_SLOTS_RES")) if (has_res) p.epi_slots = atoi(e) == 2 ? 2 : 3;
+    if (const char* e = getenv("B2_EPI_GRP_RES")) if (has_res) p.epi_grp = atoi(e) == 2 ? 2 : 1;
+    if (p.epi_mode != 1) {   // direct mode: no staging ring
+      p.epi_grp = 1;
+      p.epi_slots = 0;
+    }
+  }
+  const int epi_bytes = kEpiHalves * p.epi_slots * p.epi_grp * static_cast<int>(p.epi_chunk_bytes);
+  p.num_stages = (kSmemBudget - epi_bytes) / static_cast<int>(p.stage_bytes);
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   B2_CHECK(p.num_stages >= 2, "conv_tc: tile too large for shared memory");
   p.epi_off = static_cast<uint32_t>(p.num_stages) * p.stage_bytes;
@@ -846,6 +778,7 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   p.acc_kb = d.acc_kb > 0 ? d.acc_kb : kAccChunkKb;
   if (const char* e = getenv("B2_ACC_KB")) p.acc_kb = atoi(e) > 0 ? atoi(e) : kAccChunkKb;   // experiment hook
   pl->acc = split && d.acc_kb >= 0 && p.num_kb > p.acc_kb && getenv("B2_NO_ACC") == nullptr;
+  if (const char* e = getenv("B2_ACC_MIN_KB")) pl->acc = pl->acc && p.num_kb > atoi(e);   // experiment hook
   pl->grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   pl->smem_bytes = static_cast<size_t>(p.num_stages) * p.stage_bytes + epi_bytes + 1024 /*align*/ + 256 /*barriers*/;
   const int in_ld = d.in_ld > 0 ? d.in_ld : d.Cin;
