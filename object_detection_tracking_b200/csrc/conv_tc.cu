@@ -35,13 +35,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                 // fp16 elements = one 128-byte swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr int kUmmaK = 16;
-#ifndef B2_EPI_HALVES
-#define B2_EPI_HALVES 2
-#endif
-#ifndef B2_SETMAXNREG
-#define B2_SETMAXNREG 1
-#endif
-constexpr int kEpiHalves = B2_EPI_HALVES;   // column halves of a tile handled by separate epilogue warp quartets
+constexpr int kEpiHalves = 2;               // column halves of a tile handled by separate epilogue warp quartets
 constexpr int kEpiWarps = 4 * kEpiHalves;   // warps 4..: TMEM lane quarter = warp & 3, column half = (warp - 4) >> 2
 constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kTmemCols = 512;
@@ -334,9 +328,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const uint32_t acc_stage_cols = 256;
 
   // ACC: the epilogue warps hold 64 running sums per thread on top of the output-stage state; take registers from the
-  // (tiny) producer / MMA warpgroup.  384 threads: 128 x 56 + 256 x 224 = 64512 <= 64K.
+  // (tiny) producer / MMA warpgroup.  The CTA is launched with 384 x 168 = 64512 registers; 128 x 56 + 256 x 224 = 64512
+  // (the increase must fit in what the decrease freed, or setmaxnreg.inc never returns).
   if (warp < 4) {
-   if (ACC && B2_SETMAXNREG) setmaxnreg_dec<56>();
+   if (ACC) setmaxnreg_dec<56>();
    if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -443,7 +438,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
    }
   } else if (warp < 4 + kEpiWarps) {
-    if (ACC && B2_SETMAXNREG) setmaxnreg_inc<kEpiHalves == 2 ? 224 : 240>();
+    if (ACC) setmaxnreg_inc<224>();
     // ===================== epilogue =====================
     // Eight warps: warp w reads TMEM lanes 32*(w&3).. (its row quarter of the tile) and owns the column half
     // hf = (w-4)>>2 of the tile: chunks [c_beg, c_end) of 16 columns.  The two halves run independently (own staging
@@ -454,7 +449,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int hf = (warp - 4) >> 2;
     const int row = ew * 32 + lane;
     const int nch = p.block_n >> 4;
-    const int h0 = kEpiHalves == 2 ? (nch + 1) >> 1 : nch;
+    const int h0 = (nch + 1) >> 1;
     const int c_beg = hf ? h0 : 0;
     const int my_n = hf ? nch - h0 : h0;
     const uint32_t lane_off = static_cast<uint32_t>(ew * 32) << 16;
@@ -735,7 +730,7 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
     const bool has_res = io.res_hi != nullptr;
     p.epi_chunk_bytes = static_cast<uint32_t>(kEpiPlaneBytes) * (split ? 2 : 1);
     p.epi_slots = has_res ? 3 : 2;
-    p.epi_grp = ((kEpiHalves == 2 ? (nch + 1) / 2 : nch) >= 2) ? 2 : 1;
+    p.epi_grp = ((nch + 1) / 2 >= 2) ? 2 : 1;
     auto stages_for = [&](int grp) {
       const int epi = kEpiHalves * p.epi_slots * grp * static_cast<int>(p.epi_chunk_bytes);
       return (kSmemBudget - epi) / static_cast<int>(p.stage_bytes);
@@ -780,7 +775,7 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   pl->acc = split && d.acc_kb >= 0 && p.num_kb > p.acc_kb && getenv("B2_NO_ACC") == nullptr;
   if (const char* e = getenv("B2_ACC_MIN_KB")) pl->acc = pl->acc && p.num_kb > atoi(e);   // experiment hook
   pl->grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  pl->smem_bytes = static_cast<size_t>(p.num_stages) * p.stage_bytes + epi_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  pl->smem_bytes = static_cast<size_t>(p.num_stages) * p.stage_bytes + epi_bytes + 1024 /*align*/ + 512 /*barriers*/;
   const int in_ld = d.in_ld > 0 ? d.in_ld : d.Cin;
   const bool plain = (d.R == 1 && d.S == 1 && d.stride == 1 && d.pad_t == 0 && d.pad_b == 0 && d.pad_l == 0 &&
                       d.pad_r == 0 && d.in_H == d.in_pitch_H && d.in_W == d.in_pitch_W);

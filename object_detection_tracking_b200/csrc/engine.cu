@@ -67,7 +67,7 @@ struct Layer {
   ConvWeights w;
   ConvIO io;
   ConvPlan* plan = nullptr;
-  ConvPlan* half_plan[2] = {nullptr, nullptr};   // the same layer over images [0, B/2) and [B/2, B) (dual-stream passes)
+  std::vector<ConvPlan*> part_plan;              // the same layer over each 1/nsplit of the batch (multi-stream passes)
   bool has_bn = false, has_bias = false;
   int kind = 0;            // 0 conv HWIO, 1 fc6 (NCHW-flatten permute), 2 dense, 3 rpn class+box, 4 head outputs
 };
@@ -127,8 +127,9 @@ struct b2_ctx {
   // dual-stream pass: the backbone / FPN / RPN-head phases run as two half-batches on two streams, so that the tail of
   // one layer's persistent kernel (tiles % SMs != 0, no SM busy in the last round) overlaps the other half's kernels
   bool dual = false;
-  cudaStream_t stream2 = nullptr;
-  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  int nsplit = 1;                                  // batch parts (= streams) of the forked phases
+  cudaStream_t side_stream[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork_ev = nullptr, join_ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool weights_loaded = false;
   cudaEvent_t ev[NPHASE + 1];
   float phase_ms[NPHASE];
@@ -487,15 +488,19 @@ int build_plan(b2_ctx* c) {
     }
     // Images are independent through phases 0-2 (stem, ResNet, FPN, RPN head): a second set of plans covers each
     // half of the batch by itself (same tiles per image, so the results are bit-identical to the full-batch plan).
-    c->dual = B >= 2 && B % 2 == 0 && getenv("B2_NO_DUAL") == nullptr;
+    c->nsplit = 2;
+    if (const char* e = getenv("B2_SPLIT")) c->nsplit = atoi(e);   // experiment hook: 1, 2, 4, 8 batch parts
+    if (c->nsplit < 1 || c->nsplit > 8 || B % c->nsplit != 0) c->nsplit = 1;
+    c->dual = c->nsplit > 1 && getenv("B2_NO_DUAL") == nullptr;
     if (c->dual) {
       for (const auto& s : c->steps) {
         if (s.kind != 0 || s.phase > 2) continue;
         Layer* L = s.layer;
-        for (int h = 0; h < 2; ++h) {
+        L->part_plan.assign(c->nsplit, nullptr);
+        for (int h = 0; h < c->nsplit; ++h) {
           ConvDesc d = L->d;
           ConvIO io = L->io;
-          d.B = B / 2;
+          d.B = B / c->nsplit;
           const size_t in_off = static_cast<size_t>(h) * d.B * d.in_pitch_H * d.in_pitch_W * (d.in_ld > 0 ? d.in_ld : d.Cin);
           const size_t out_off = static_cast<size_t>(h) * d.B * d.out_H * d.out_W * d.ldc;
           const size_t res_off = static_cast<size_t>(h) * d.B * d.res_H * d.res_W * d.ldr;
@@ -506,8 +511,8 @@ int build_plan(b2_ctx* c) {
           if (io.out_f32) io.out_f32 += out_off;
           if (io.res_hi) io.res_hi += res_off;
           if (io.res_lo) io.res_lo += res_off;
-          L->half_plan[h] = conv_tc_plan_create(d, L->w, io, c->split, c->num_sms);
-          if (!L->half_plan[h]) {
+          L->part_plan[h] = conv_tc_plan_create(d, L->w, io, c->split, c->num_sms);
+          if (!L->part_plan[h]) {
             set_error(std::string("half-batch plan for ") + L->name + ": " + last_error());
             return -1;
           }
@@ -559,17 +564,17 @@ int run_step(b2_ctx* c, const b2_ctx::Step& s) {
   return -1;
 }
 
-// One step of phases 0-2 over half `h` of the batch, on stream `st`.
+// One step of phases 0-2 over part `h` (of nsplit) of the batch, on stream `st`.
 int run_step_half(b2_ctx* c, const b2_ctx::Step& s, int h, cudaStream_t st) {
   const b2_config& cfg = c->cfg;
-  const int hb = cfg.batch / 2;
+  const int hb = cfg.batch / c->nsplit;
   auto off = [&](const Planes& p) { return static_cast<size_t>(h) * hb * p.H * p.W * p.C; };
   auto lo = [&](const Planes& p) { return p.lo ? p.lo + off(p) : nullptr; };
   switch (s.kind) {
     case 0:
-      return conv_tc_launch(s.layer->half_plan[h], st);
+      return conv_tc_launch(s.layer->part_plan[h], st);
     case 1:
-      return stem_pack_launch(static_cast<const uint8_t*>(c->img) + static_cast<size_t>(h) * (c->img_bytes / 2),
+      return stem_pack_launch(static_cast<const uint8_t*>(c->img) + static_cast<size_t>(h) * (c->img_bytes / c->nsplit),
                               cfg.input_dtype == 1, hb, cfg.height, cfg.width, c->stem_u.hi + off(c->stem_u),
                               lo(c->stem_u), c->stem_u.H, c->stem_u.W, 0, st);
     case 2:
@@ -601,14 +606,16 @@ int step_launches(const b2_ctx::Step& s) {
 // the capture through the fork event and rejoins before the proposals).
 int enqueue_dual(b2_ctx* c) {
   B2_CUDA(cudaEventRecord(c->fork_ev, c->stream));
-  B2_CUDA(cudaStreamWaitEvent(c->stream2, c->fork_ev, 0));
+  for (int h = 1; h < c->nsplit; ++h) B2_CUDA(cudaStreamWaitEvent(c->side_stream[h - 1], c->fork_ev, 0));
   for (const auto& s : c->steps) {
     if (s.phase > 2) continue;
-    if (run_step_half(c, s, 0, c->stream)) return -1;
-    if (run_step_half(c, s, 1, c->stream2)) return -1;
+    for (int h = 0; h < c->nsplit; ++h)
+      if (run_step_half(c, s, h, h == 0 ? c->stream : c->side_stream[h - 1])) return -1;
   }
-  B2_CUDA(cudaEventRecord(c->join_ev, c->stream2));
-  B2_CUDA(cudaStreamWaitEvent(c->stream, c->join_ev, 0));
+  for (int h = 1; h < c->nsplit; ++h) {
+    B2_CUDA(cudaEventRecord(c->join_ev[h - 1], c->side_stream[h - 1]));
+    B2_CUDA(cudaStreamWaitEvent(c->stream, c->join_ev[h - 1], 0));
+  }
   for (const auto& s : c->steps)
     if (s.phase > 2 && run_step(c, s)) return -1;
   return 0;
@@ -777,12 +784,14 @@ int b2_create(b2_ctx** out, int device, const b2_config* cfg) {
     return -1;
   }
   if (c->dual) {
-    B2_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     B2_CUDA(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
-    B2_CUDA(cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming));
+    for (int h = 1; h < c->nsplit; ++h) {
+      B2_CUDA(cudaStreamCreateWithFlags(&c->side_stream[h - 1], cudaStreamNonBlocking));
+      B2_CUDA(cudaEventCreateWithFlags(&c->join_ev[h - 1], cudaEventDisableTiming));
+    }
   }
   c->launches = 0;
-  for (const auto& s : c->steps) c->launches += step_launches(s) * ((c->dual && s.phase <= 2) ? 2 : 1);
+  for (const auto& s : c->steps) c->launches += step_launches(s) * ((c->dual && s.phase <= 2) ? c->nsplit : 1);
   B2_CUDA(cudaDeviceSynchronize());
   *out = c.release();
   return 0;
@@ -795,12 +804,14 @@ void b2_destroy(b2_ctx* c) {
   if (c->graph) cudaGraphExecDestroy(c->graph);
   for (auto& L : c->layers) {
     if (L->plan) conv_tc_plan_destroy(L->plan);
-    for (int h = 0; h < 2; ++h)
-      if (L->half_plan[h]) conv_tc_plan_destroy(L->half_plan[h]);
+    for (ConvPlan* pp : L->part_plan)
+      if (pp) conv_tc_plan_destroy(pp);
   }
   if (c->fork_ev) cudaEventDestroy(c->fork_ev);
-  if (c->join_ev) cudaEventDestroy(c->join_ev);
-  if (c->stream2) cudaStreamDestroy(c->stream2);
+  for (int h = 0; h < 7; ++h) {
+    if (c->join_ev[h]) cudaEventDestroy(c->join_ev[h]);
+    if (c->side_stream[h]) cudaStreamDestroy(c->side_stream[h]);
+  }
   for (void* p : c->allocs) cudaFree(p);
   for (int i = 0; i <= NPHASE; ++i)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
