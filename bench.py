@@ -313,7 +313,10 @@ def main():
                     "avg_launch_ms": conv_ms / len(conv), "share_of_step": conv_ms / total_ms,
                     "mma_flop_multiplier": 3 if args.precision == "split" else 1,
                     "tensor_pipe_work_frac": achieved_tf * (3 if args.precision == "split" else 1) / peak_tf,
-                    "traffic": ncu_traffic(args.precision)}
+                    "traffic": ncu_traffic(args.precision),
+                    # the timed pass forks the backbone / FPN / RPN-head phases over two streams (half-batch launches
+                    # that overlap each other's tails); avg_launch_ms above is the serial full-batch launch
+                    "conv_tflops_over_whole_step": conv_flops / (dt / args.steps) / 1e12}
         if args.profile_json:
             with open(args.profile_json, "w") as f:
                 json.dump({"precision": args.precision, "batch": BATCH, "steps": prof}, f, indent=1)

@@ -65,6 +65,7 @@ struct ConvTcParams {
   int epi_mode;      // 0 = direct global loads/stores per thread, 1 = TMA-staged (residual in, result out)
   int epi_grp;       // staged: 16-column chunks per fence / barrier / store group (1 or 2)
   int epi_slots;     // staged: group slots in each column half's staging ring (2, or 3 when a residual is prefetched)
+  int epi_wide;      // staged, epi_grp == 2: a group is one [128 rows][32 fp16] box per plane (64-byte swizzle, one TMA op)
   uint32_t epi_chunk_bytes;   // staged: bytes of one chunk buffer (4 KB hi plane, + 4 KB lo plane in split precision)
   uint32_t epi_off;  // byte offset of the epilogue staging buffers inside the tile area
 };
@@ -150,12 +151,11 @@ __device__ __forceinline__ void epilogue_chunk16(const ConvTcParams& p, float (&
   }
 }
 
-// Same math on a chunk whose residual sits in (and whose result goes back to) a 32-byte-swizzled
-// shared-memory buffer [128 rows][16 fp16]: row r, 16-byte half jj lives at r*32 + ((jj ^ ((r>>2)&1)) * 16).
-// The lo plane (split precision) follows the hi plane at +kEpiPlaneBytes.
+// Same math on a chunk whose residual sits in (and whose result goes back to) a swizzled shared-memory staging box:
+// hi0 / hi1 (lo0 / lo1 for the lo plane) point at this thread's two 16-byte cells (channels 0-7 and 8-15 of the chunk).
 template <bool SPLIT>
-__device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, float (&v)[16], uint8_t* buf, int row, int n,
-                                                      bool has_res, bool has_res_lo) {
+__device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, float (&v)[16], uint4* hi0, uint4* hi1,
+                                                      uint4* lo0, uint4* lo1, int n, bool has_res, bool has_res_lo) {
   const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -165,11 +165,6 @@ __device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, flo
     v[4 * j + 2] += b.z;
     v[4 * j + 3] += b.w;
   }
-  const int sw = (row >> 2) & 1;
-  uint4* hi0 = reinterpret_cast<uint4*>(buf + row * 32 + ((0 ^ sw) << 4));
-  uint4* hi1 = reinterpret_cast<uint4*>(buf + row * 32 + ((1 ^ sw) << 4));
-  uint4* lo0 = reinterpret_cast<uint4*>(buf + kEpiPlaneBytes + row * 32 + ((0 ^ sw) << 4));
-  uint4* lo1 = reinterpret_cast<uint4*>(buf + kEpiPlaneBytes + row * 32 + ((1 ^ sw) << 4));
   if (has_res) {
     uint4 r[2] = {*hi0, *hi1};
 #pragma unroll
@@ -320,6 +315,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  if (tmem_base != 0) __trap();   // the MMA issuer addresses TMEM from column 0 / lane 0 (whole-TMEM allocation)
 
   const uint32_t a_lo_off = kABytes;
   const uint32_t b_hi_off = SPLIT ? 2 * kABytes : kABytes;
@@ -379,49 +375,71 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop converged and one elected lane issues: every MMA operand (descriptors, TMEM
+    // address, instruction descriptor) is then computed by warp-uniform code and lives in uniform registers.  (Run by
+    // lane 0 alone, each tcgen05.mma was wrapped in an elect / broadcast / compare waterfall -- 276 instructions per
+    // K-block, which bounded the MMA-bound layers: ncu showed this warp never waiting, only issuing.)
+    {
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
       uint32_t qg = 0;     // ACC: running chunk counter -> chunk accumulator qg & 1
+      const uint32_t tiles_u32 = smem_u32(tiles);
+      // shared-memory matrix descriptor (K-major, 128-byte swizzle): low word = start address >> 4 (14 bits) | LBO 1 << 16,
+      // high word = SBO 1024 >> 4 | descriptor version 1 << 14 | SWIZZLE_128B 2 << 29; offsets inside the stage and the
+      // K advance (32 bytes per UMMA_K) add to the address field without carry (all of shared memory is < 2^18 bytes)
+      constexpr uint64_t kDescHi = static_cast<uint64_t>((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+      // this CTA owns the whole TMEM of its SM (512 columns, one CTA per SM): the allocation starts at column 0, lane 0
+      // (checked after the allocation), so the accumulator addresses are plain constants here
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         // plain: acc0 at as*256, acc1 at as*256+128.  ACC: acc0 chunk buffers at 0 / 128, acc1 at 256 + as*128.
-        uint32_t acc0 = tmem_base + as * acc_stage_cols;
-        const uint32_t acc1 = ACC ? tmem_base + 256 + as * 128 : acc0 + 128;
+        uint32_t acc0 = as * acc_stage_cols;
+        const uint32_t acc1 = ACC ? 256 + as * 128 : acc0 + 128;
         int kq = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           if (ACC && kq == 0) {
             const uint32_t cbuf = qg & 1;
             mbar_wait(&c_empty[cbuf], ((qg >> 1) & 1) ^ 1);
             tc_fence_after();
-            acc0 = tmem_base + cbuf * 128;
+            acc0 = cbuf * 128;
           }
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t st = smem_u32(tiles + static_cast<size_t>(stage) * p.stage_bytes);
+          const uint32_t st = tiles_u32 + static_cast<uint32_t>(stage) * p.stage_bytes;
+          const uint32_t d_a_hi = ((st >> 4) & 0x3FFFu) | 0x10000u;
+          const uint32_t d_a_lo = d_a_hi + (a_lo_off >> 4);
+          const uint32_t d_b_hi = d_a_hi + (b_hi_off >> 4);
+          const uint32_t d_b_lo = d_a_hi + (b_lo_off >> 4);
+          const bool chunk_end = ACC && (kq + 1 == p.acc_kb || kb == p.num_kb - 1);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint32_t koff = k * kUmmaK * 2;   // bytes along K inside the 128B swizzle row
-            const uint64_t a_hi = make_smem_desc_sw128(st + koff);
-            const uint64_t b_hi = make_smem_desc_sw128(st + b_hi_off + koff);
-            const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
-            umma_f16(acc0, a_hi, b_hi, p.idesc, ACC ? ((kq > 0 || k > 0) ? 1u : 0u) : first);
-            if (SPLIT) {
-              const uint64_t a_lo = make_smem_desc_sw128(st + a_lo_off + koff);
-              const uint64_t b_lo = make_smem_desc_sw128(st + b_lo_off + koff);
-              umma_f16(acc1, a_hi, b_lo, p.idesc, first);
-              umma_f16(acc1, a_lo, b_hi, p.idesc, 1u);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint32_t ko = k * (kUmmaK * 2 >> 4);   // 32 bytes along K inside the 128B swizzle row, in 16-byte units
+              const uint64_t a_hi = kDescHi | (d_a_hi + ko);
+              const uint64_t b_hi = kDescHi | (d_b_hi + ko);
+              const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
+              umma_f16(acc0, a_hi, b_hi, p.idesc, ACC ? ((kq > 0 || k > 0) ? 1u : 0u) : first);
+              if (SPLIT) {
+                const uint64_t a_lo = kDescHi | (d_a_lo + ko);
+                const uint64_t b_lo = kDescHi | (d_b_lo + ko);
+                umma_f16(acc1, a_hi, b_lo, p.idesc, first);
+                umma_f16(acc1, a_lo, b_hi, p.idesc, 1u);
+              }
             }
+            umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
+            if (chunk_end) umma_commit(&c_full[qg & 1]);   // chunk accumulator complete -> epilogue sums it
+            if (kb == p.num_kb - 1) umma_commit(&tmem_full[as]);        // accumulator complete -> epilogue
           }
-          umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
+          __syncwarp();
           if (ACC) {
-            if (++kq == p.acc_kb || kb == p.num_kb - 1) {
-              umma_commit(&c_full[qg & 1]);   // chunk accumulator complete -> epilogue sums it
+            if (chunk_end) {
               ++qg;
               kq = 0;
+            } else {
+              ++kq;
             }
           }
           if (++stage == p.num_stages) {
@@ -429,7 +447,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[as]);        // accumulator complete -> epilogue
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -483,9 +500,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       uint8_t* b = ring + la_slot * slot_bytes;
       uint64_t* bar = &rfull[la_slot];
       mbar_expect_tx(bar, gn * kEpiPlaneBytes * (res_lo ? 2 : 1));
-      for (int u = 0; u < gn; ++u) {
-        tma_load_2d(b + u * p.epi_chunk_bytes, &tmR_hi, bar, col + u * 16, m_blk * kBlockM);
-        if (res_lo) tma_load_2d(b + u * p.epi_chunk_bytes + kEpiPlaneBytes, &tmR_lo, bar, col + u * 16, m_blk * kBlockM);
+      if (p.epi_wide) {   // one 32-column box per plane (groups are always full in wide mode)
+        tma_load_2d(b, &tmR_hi, bar, col, m_blk * kBlockM);
+        if (res_lo) tma_load_2d(b + 2 * kEpiPlaneBytes, &tmR_lo, bar, col, m_blk * kBlockM);
+      } else {
+        for (int u = 0; u < gn; ++u) {
+          tma_load_2d(b + u * p.epi_chunk_bytes, &tmR_hi, bar, col + u * 16, m_blk * kBlockM);
+          if (res_lo) tma_load_2d(b + u * p.epi_chunk_bytes + kEpiPlaneBytes, &tmR_lo, bar, col + u * 16, m_blk * kBlockM);
+        }
       }
       la_c += gn;
       if (la_c >= my_n) {
@@ -529,7 +551,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           mbar_wait(&rfull[slot], (rph >> slot) & 1u);
           rph ^= 1u << slot;
         }
-        epilogue_chunk16_smem<SPLIT>(p, v, sb + u * p.epi_chunk_bytes, row, n, has_res, res_lo);
+        {
+          // narrow: chunk buffer [128][32 B] per plane, 32-byte swizzle (16-byte cell j of row r at j ^ ((r >> 2) & 1));
+          // wide: group box [128][64 B] per plane, 64-byte swizzle (cell j of row r at j ^ ((r >> 1) & 3)), this chunk = cells 2u, 2u+1
+          uint8_t* hp;
+          uint32_t c0, c1, lo_off;
+          if (p.epi_wide) {
+            const uint32_t sw = (row >> 1) & 3;
+            hp = sb + row * 64;
+            c0 = ((2 * u) ^ sw) << 4;
+            c1 = ((2 * u + 1) ^ sw) << 4;
+            lo_off = 2 * kEpiPlaneBytes;
+          } else {
+            const uint32_t sw = (row >> 2) & 1;
+            hp = sb + u * p.epi_chunk_bytes + row * 32;
+            c0 = sw << 4;
+            c1 = (1 ^ sw) << 4;
+            lo_off = kEpiPlaneBytes;
+          }
+          epilogue_chunk16_smem<SPLIT>(p, v, reinterpret_cast<uint4*>(hp + c0), reinterpret_cast<uint4*>(hp + c1),
+                                       reinterpret_cast<uint4*>(hp + lo_off + c0), reinterpret_cast<uint4*>(hp + lo_off + c1), n,
+                                       has_res, res_lo);
+        }
         if (u == grp - 1 || c == my_n - 1) {
           fence_proxy_async();
           if (elected) {
@@ -539,10 +582,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           named_bar_sync(bar_id, 128);
           if (elected) {
             const int nb = n - u * 16;
-            for (int t = 0; t <= u; ++t) {
-              tma_store_2d(&tmO_hi, sb + t * p.epi_chunk_bytes, nb + t * 16, m_blk * kBlockM);
-              if (SPLIT && p.out_lo != nullptr)
-                tma_store_2d(&tmO_lo, sb + t * p.epi_chunk_bytes + kEpiPlaneBytes, nb + t * 16, m_blk * kBlockM);
+            if (p.epi_wide) {
+              tma_store_2d(&tmO_hi, sb, nb, m_blk * kBlockM);
+              if (SPLIT && p.out_lo != nullptr) tma_store_2d(&tmO_lo, sb + 2 * kEpiPlaneBytes, nb, m_blk * kBlockM);
+            } else {
+              for (int t = 0; t <= u; ++t) {
+                tma_store_2d(&tmO_hi, sb + t * p.epi_chunk_bytes, nb + t * 16, m_blk * kBlockM);
+                if (SPLIT && p.out_lo != nullptr)
+                  tma_store_2d(&tmO_lo, sb + t * p.epi_chunk_bytes + kEpiPlaneBytes, nb + t * 16, m_blk * kBlockM);
+              }
             }
             bulk_commit();
             if (has_res) issue_res_group();
@@ -739,6 +787,8 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
     if (const char* e = getenv("B2_EPI_GRP")) p.epi_grp = atoi(e) == 2 ? 2 : 1;   // experiment hooks
     if (const char* e = getenv("B2_EPI_SLOTS_RES")) if (has_res) p.epi_slots = atoi(e) == 2 ? 2 : 3;
     if (const char* e = getenv("B2_EPI_GRP_RES")) if (has_res) p.epi_grp = atoi(e) == 2 ? 2 : 1;
+    // two-chunk groups move as one 32-column box per plane when every group of both halves is full
+    p.epi_wide = (p.epi_mode == 1 && p.epi_grp == 2 && nch % 4 == 0 && getenv("B2_EPI_NARROW") == nullptr) ? 1 : 0;
     if (p.epi_mode != 1) {   // direct mode: no staging ring
       p.epi_grp = 1;
       p.epi_slots = 0;
@@ -824,23 +874,21 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   pl->tmO_hi = pl->tmO_lo = pl->tmR_hi = pl->tmR_lo = pl->tmB_hi;   // valid placeholders for the direct mode
   if (p.epi_mode == 1) {
     const uint64_t rows = static_cast<uint64_t>(p.M);
-    if (encode_2d(&pl->tmO_hi, io.out_hi, w.Cout_pad, rows, static_cast<uint64_t>(d.ldc) * 2, 16, kBlockM,
-                  CU_TENSOR_MAP_SWIZZLE_32B))
+    const uint32_t ebox = p.epi_wide ? 32 : 16;
+    const CUtensorMapSwizzle eswz = p.epi_wide ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    if (encode_2d(&pl->tmO_hi, io.out_hi, w.Cout_pad, rows, static_cast<uint64_t>(d.ldc) * 2, ebox, kBlockM, eswz))
       return -1;
     pl->tmO_lo = pl->tmO_hi;
     if (split && io.out_lo &&
-        encode_2d(&pl->tmO_lo, io.out_lo, w.Cout_pad, rows, static_cast<uint64_t>(d.ldc) * 2, 16, kBlockM,
-                  CU_TENSOR_MAP_SWIZZLE_32B))
+        encode_2d(&pl->tmO_lo, io.out_lo, w.Cout_pad, rows, static_cast<uint64_t>(d.ldc) * 2, ebox, kBlockM, eswz))
       return -1;
     pl->tmR_hi = pl->tmR_lo = pl->tmO_hi;
     if (io.res_hi) {
-      if (encode_2d(&pl->tmR_hi, io.res_hi, w.Cout_pad, rows, static_cast<uint64_t>(d.ldr) * 2, 16, kBlockM,
-                    CU_TENSOR_MAP_SWIZZLE_32B))
+      if (encode_2d(&pl->tmR_hi, io.res_hi, w.Cout_pad, rows, static_cast<uint64_t>(d.ldr) * 2, ebox, kBlockM, eswz))
         return -1;
       pl->tmR_lo = pl->tmR_hi;
       if (split && io.res_lo &&
-          encode_2d(&pl->tmR_lo, io.res_lo, w.Cout_pad, rows, static_cast<uint64_t>(d.ldr) * 2, 16, kBlockM,
-                    CU_TENSOR_MAP_SWIZZLE_32B))
+          encode_2d(&pl->tmR_lo, io.res_lo, w.Cout_pad, rows, static_cast<uint64_t>(d.ldr) * 2, ebox, kBlockM, eswz))
         return -1;
     }
   }
