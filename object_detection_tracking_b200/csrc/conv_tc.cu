@@ -279,7 +279,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(c_empty + 2);
   uint8_t* epi = tiles + p.epi_off;
 
-  const int warp = threadIdx.x >> 5;
+  // broadcast from lane 0 so that the compiler treats the warp index (and everything derived from it) as warp-uniform
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -330,7 +331,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
    if (ACC) setmaxnreg_dec<56>();
    if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // converged warp, one elected lane issues (uniform-register operands, see the MMA issuer)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -347,25 +349,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           ch = p.lower_h + pp * p.stride;
           cw = p.lower_w + qq * p.stride;
         }
+        int tap = 0, cb = 0;   // K-block = (filter tap, 64-channel block)
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = tiles + static_cast<size_t>(stage) * p.stage_bytes;
-          mbar_expect_tx(&full_bar[stage], p.stage_bytes);
-          const int tap = kb / p.cin_blocks;
-          const int cb = kb - tap * p.cin_blocks;
-          if (p.a_mode == 1) {
-            const int r = tap / p.S;
-            const int s = tap - r * p.S;
-            const uint16_t ow = static_cast<uint16_t>(s * p.dil);
-            const uint16_t oh = static_cast<uint16_t>(r * p.dil);
-            tma_load_im2col_4d(st, &tmA_hi, &full_bar[stage], cb * kBlockK, cw, ch, img, ow, oh);
-            if (SPLIT) tma_load_im2col_4d(st + a_lo_off, &tmA_lo, &full_bar[stage], cb * kBlockK, cw, ch, img, ow, oh);
-          } else {
-            tma_load_2d(st, &tmA_hi, &full_bar[stage], cb * kBlockK, m0);
-            if (SPLIT) tma_load_2d(st + a_lo_off, &tmA_lo, &full_bar[stage], cb * kBlockK, m0);
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[stage], p.stage_bytes);
+            if (p.a_mode == 1) {
+              const int r = tap / p.S;
+              const int s = tap - r * p.S;
+              const uint16_t ow = static_cast<uint16_t>(s * p.dil);
+              const uint16_t oh = static_cast<uint16_t>(r * p.dil);
+              tma_load_im2col_4d(st, &tmA_hi, &full_bar[stage], cb * kBlockK, cw, ch, img, ow, oh);
+              if (SPLIT) tma_load_im2col_4d(st + a_lo_off, &tmA_lo, &full_bar[stage], cb * kBlockK, cw, ch, img, ow, oh);
+            } else {
+              tma_load_2d(st, &tmA_hi, &full_bar[stage], cb * kBlockK, m0);
+              if (SPLIT) tma_load_2d(st + a_lo_off, &tmA_lo, &full_bar[stage], cb * kBlockK, m0);
+            }
+            tma_load_2d(st + b_hi_off, &tmB_hi, &full_bar[stage], kb * kBlockK, n0);
+            if (SPLIT) tma_load_2d(st + b_lo_off, &tmB_lo, &full_bar[stage], kb * kBlockK, n0);
           }
-          tma_load_2d(st + b_hi_off, &tmB_hi, &full_bar[stage], kb * kBlockK, n0);
-          if (SPLIT) tma_load_2d(st + b_lo_off, &tmB_lo, &full_bar[stage], kb * kBlockK, n0);
+          __syncwarp();
+          if (++cb == p.cin_blocks) {
+            cb = 0;
+            ++tap;
+          }
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1;
@@ -479,7 +487,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const bool staged = p.epi_mode == 1;
     const bool has_res = p.res_hi != nullptr;
     const bool res_lo = SPLIT && p.res_lo != nullptr;
-    const bool elected = threadIdx.x == 128 + hf * 128;
+    // TMA traffic of this half is issued by its first warp, converged, through one elected lane: coordinates, staging
+    // addresses and barriers are then warp-uniform values (issued by a lone thread, every bulk-tensor instruction was
+    // wrapped in an elect / broadcast / compare waterfall of ~15 instructions, ~300 per group on the group's critical path)
+    const bool issuer = ew == 0;
     const int grp = p.epi_grp;
     const int nslots = p.epi_slots;
     // before group k+1 may overwrite its slot, the store of group k+1-nslots must be done reading it; with a residual
@@ -491,7 +502,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     int slot = 0, la_slot = 0;
     uint32_t rph = 0;        // phase bits of rfull[]
     int la_tile = blockIdx.x, la_c = 0;   // look-ahead cursor of the residual prefetch (elected thread only)
-    auto issue_res_group = [&]() {
+    auto issue_res_group = [&]() {   // called by every thread of the half (the cursor is warp-uniform state)
       if (la_tile >= p.num_tiles || my_n == 0) return;
       const int m_blk = la_tile / p.num_n_blocks;
       const int n_blk = la_tile - m_blk * p.num_n_blocks;
@@ -499,15 +510,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int col = n_blk * p.block_n + (c_beg + la_c) * 16;
       uint8_t* b = ring + la_slot * slot_bytes;
       uint64_t* bar = &rfull[la_slot];
-      mbar_expect_tx(bar, gn * kEpiPlaneBytes * (res_lo ? 2 : 1));
-      if (p.epi_wide) {   // one 32-column box per plane (groups are always full in wide mode)
-        tma_load_2d(b, &tmR_hi, bar, col, m_blk * kBlockM);
-        if (res_lo) tma_load_2d(b + 2 * kEpiPlaneBytes, &tmR_lo, bar, col, m_blk * kBlockM);
-      } else {
-        for (int u = 0; u < gn; ++u) {
-          tma_load_2d(b + u * p.epi_chunk_bytes, &tmR_hi, bar, col + u * 16, m_blk * kBlockM);
-          if (res_lo) tma_load_2d(b + u * p.epi_chunk_bytes + kEpiPlaneBytes, &tmR_lo, bar, col + u * 16, m_blk * kBlockM);
+      if (issuer) {
+        if (elect_one()) {
+          mbar_expect_tx(bar, gn * kEpiPlaneBytes * (res_lo ? 2 : 1));
+          if (p.epi_wide) {   // one 32-column box per plane (groups are always full in wide mode)
+            tma_load_2d(b, &tmR_hi, bar, col, m_blk * kBlockM);
+            if (res_lo) tma_load_2d(b + 2 * kEpiPlaneBytes, &tmR_lo, bar, col, m_blk * kBlockM);
+          } else {
+            for (int u = 0; u < gn; ++u) {
+              tma_load_2d(b + u * p.epi_chunk_bytes, &tmR_hi, bar, col + u * 16, m_blk * kBlockM);
+              if (res_lo) tma_load_2d(b + u * p.epi_chunk_bytes + kEpiPlaneBytes, &tmR_lo, bar, col + u * 16, m_blk * kBlockM);
+            }
+          }
         }
+        __syncwarp();
       }
       la_c += gn;
       if (la_c >= my_n) {
@@ -516,7 +532,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
       if (++la_slot == nslots) la_slot = 0;
     };
-    if (staged && elected && has_res)
+    if (staged && has_res)
       for (int i = 0; i < nslots - 1; ++i) issue_res_group();
 
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -575,26 +591,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         if (u == grp - 1 || c == my_n - 1) {
           fence_proxy_async();
-          if (elected) {
-            if (wait_all_reads) bulk_wait_read<0>();
-            else bulk_wait_read<1>();
+          if (issuer) {
+            if (elect_one()) {
+              if (wait_all_reads) bulk_wait_read<0>();
+              else bulk_wait_read<1>();
+            }
+            __syncwarp();
           }
           named_bar_sync(bar_id, 128);
-          if (elected) {
-            const int nb = n - u * 16;
-            if (p.epi_wide) {
-              tma_store_2d(&tmO_hi, sb, nb, m_blk * kBlockM);
-              if (SPLIT && p.out_lo != nullptr) tma_store_2d(&tmO_lo, sb + 2 * kEpiPlaneBytes, nb, m_blk * kBlockM);
-            } else {
-              for (int t = 0; t <= u; ++t) {
-                tma_store_2d(&tmO_hi, sb + t * p.epi_chunk_bytes, nb + t * 16, m_blk * kBlockM);
-                if (SPLIT && p.out_lo != nullptr)
-                  tma_store_2d(&tmO_lo, sb + t * p.epi_chunk_bytes + kEpiPlaneBytes, nb + t * 16, m_blk * kBlockM);
+          if (issuer) {
+            if (elect_one()) {
+              const int nb = n - u * 16;
+              if (p.epi_wide) {
+                tma_store_2d(&tmO_hi, sb, nb, m_blk * kBlockM);
+                if (SPLIT && p.out_lo != nullptr) tma_store_2d(&tmO_lo, sb + 2 * kEpiPlaneBytes, nb, m_blk * kBlockM);
+              } else {
+                for (int t = 0; t <= u; ++t) {
+                  tma_store_2d(&tmO_hi, sb + t * p.epi_chunk_bytes, nb + t * 16, m_blk * kBlockM);
+                  if (SPLIT && p.out_lo != nullptr)
+                    tma_store_2d(&tmO_lo, sb + t * p.epi_chunk_bytes + kEpiPlaneBytes, nb + t * 16, m_blk * kBlockM);
+                }
               }
+              bulk_commit();
             }
-            bulk_commit();
-            if (has_res) issue_res_group();
+            __syncwarp();
           }
+          if (has_res) issue_res_group();
           if (++slot == nslots) slot = 0;
         }
       };
@@ -651,7 +673,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         aphase ^= 1;
       }
     }
-    if (staged && elected) bulk_wait_all();   // the output must be globally written before the CTA retires
+    if (staged && issuer) {   // the output must be globally written before the CTA retires
+      if (elect_one()) bulk_wait_all();
+      __syncwarp();
+    }
   }
   tc_fence_before();
   __syncthreads();
