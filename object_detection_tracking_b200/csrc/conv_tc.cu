@@ -61,6 +61,8 @@ struct ConvTcParams {
   int ldr, res_H, res_W, res_shift;
   int relu;
   int acc_kb;        // ACC: K-blocks per tensor-core accumulation chunk
+  int acc_ring;      // ACC: chunk accumulators in the TMEM ring (2 for 128-column tiles, 6 for 64-column tiles)
+  int acc_stride;    // ACC: TMEM columns per accumulator (ring at 0.., the two correction accumulators after it)
   int dbg_nodrain;   // perf experiment only (wrong results): skip the TMEM reads of the ACC drain
   int epi_mode;      // 0 = direct global loads/stores per thread, 1 = TMA-staged (residual in, result out)
   int epi_grp;       // staged: 16-column chunks per fence / barrier / store group (1 or 2)
@@ -221,6 +223,7 @@ __device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, flo
 // buffers and the epilogue warps sum the chunk results in registers with round-to-nearest fp32 adds
 // (overlapped with the MMAs of the next chunk), which brings the result to CUDA-core fp32 accuracy.
 constexpr int kAccChunkKb = 1;   // default: restart every K-block (64 K-elements = 4 truncating accumulations)
+constexpr int kAccRingMax = 6;
 constexpr int kAccMaxChunks = 8 / kEpiHalves; // ACC tiles are at most 128 columns wide -> chunks of 16 per column half
 
 // ACC drain: fold this thread's share (my_n chunks of 16 columns of its row) of one chunk accumulator into the
@@ -274,9 +277,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* tmem_full = bars + 2 * kMaxStages;
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;
   uint64_t* res_full = bars + 2 * kMaxStages + 4;                       // [2 halves][kEpiSlotsMax]
-  uint64_t* c_full = bars + 2 * kMaxStages + 4 + 2 * kEpiSlotsMax;      // [2] ACC chunk accumulator ready
-  uint64_t* c_empty = c_full + 2;                                       // [2] ACC chunk accumulator drained
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(c_empty + 2);
+  uint64_t* c_full = bars + 2 * kMaxStages + 4 + 2 * kEpiSlotsMax;      // [kAccRingMax] ACC chunk accumulator ready
+  uint64_t* c_empty = c_full + kAccRingMax;                             // [kAccRingMax] ACC chunk accumulator drained
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(c_empty + kAccRingMax);
   uint8_t* epi = tiles + p.epi_off;
 
   // broadcast from lane 0 so that the compiler treats the warp index (and everything derived from it) as warp-uniform
@@ -301,7 +304,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_init(&tmem_empty[i], kEpiWarps);   // one arrive per epilogue warp
     }
     for (int i = 0; i < 2 * kEpiSlotsMax; ++i) mbar_init(&res_full[i], 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kAccRingMax; ++i) {
       mbar_init(&c_full[i], 1);
       mbar_init(&c_empty[i], kEpiWarps);
     }
@@ -392,7 +395,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      uint32_t qg = 0;     // ACC: running chunk counter -> chunk accumulator qg & 1
+      int cbuf = 0;          // ACC: chunk accumulator ring cursor + phase bit (flips when the ring wraps)
+      uint32_t cphase = 0;
       const uint32_t tiles_u32 = smem_u32(tiles);
       // shared-memory matrix descriptor (K-major, 128-byte swizzle): low word = start address >> 4 (14 bits) | LBO 1 << 16,
       // high word = SBO 1024 >> 4 | descriptor version 1 << 14 | SWIZZLE_128B 2 << 29; offsets inside the stage and the
@@ -405,14 +409,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         tc_fence_after();
         // plain: acc0 at as*256, acc1 at as*256+128.  ACC: acc0 chunk buffers at 0 / 128, acc1 at 256 + as*128.
         uint32_t acc0 = as * acc_stage_cols;
-        const uint32_t acc1 = ACC ? 256 + as * 128 : acc0 + 128;
+        const uint32_t acc1 = ACC ? (p.acc_ring + as) * p.acc_stride : acc0 + 128;
         int kq = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           if (ACC && kq == 0) {
-            const uint32_t cbuf = qg & 1;
-            mbar_wait(&c_empty[cbuf], ((qg >> 1) & 1) ^ 1);
+            mbar_wait(&c_empty[cbuf], cphase ^ 1);
             tc_fence_after();
-            acc0 = cbuf * 128;
+            acc0 = cbuf * p.acc_stride;
           }
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -438,13 +441,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               }
             }
             umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
-            if (chunk_end) umma_commit(&c_full[qg & 1]);   // chunk accumulator complete -> epilogue sums it
+            if (chunk_end) umma_commit(&c_full[cbuf]);   // chunk accumulator complete -> epilogue sums it
             if (kb == p.num_kb - 1) umma_commit(&tmem_full[as]);        // accumulator complete -> epilogue
           }
           __syncwarp();
           if (ACC) {
             if (chunk_end) {
-              ++qg;
+              if (++cbuf == p.acc_ring) {
+                cbuf = 0;
+                cphase ^= 1;
+              }
               kq = 0;
             } else {
               ++kq;
@@ -480,7 +486,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const uint32_t lane_off = static_cast<uint32_t>(ew * 32) << 16;
     int as = 0;
     uint32_t aphase = 0;
-    uint32_t qe = 0;     // ACC: running chunk counter (mirrors the MMA issuer's)
+    int ecbuf = 0;       // ACC: chunk accumulator ring cursor + phase bit (mirror the MMA issuer's)
+    uint32_t ecphase = 0;
 
     // ---- staged output state (epi_mode 1): residual chunks arrive in swizzled smem buffers (TMA loads issued
     // epi_slots-1 groups ahead, also across tile boundaries), results overwrite them in place and leave by TMA store.
@@ -626,17 +633,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
         for (int i = 0; i < kAccMaxChunks * 16; ++i) sums[i] = 0.0f;
         const int nq = (p.num_kb + p.acc_kb - 1) / p.acc_kb;
-        for (int q = 0; q < nq; ++q, ++qe) {
-          const uint32_t cbuf = qe & 1;
-          mbar_wait(&c_full[cbuf], (qe >> 1) & 1);
+        for (int q = 0; q < nq; ++q) {
+          const int cbuf = ecbuf;
+          mbar_wait(&c_full[cbuf], ecphase);
+          if (++ecbuf == p.acc_ring) {
+            ecbuf = 0;
+            ecphase ^= 1;
+          }
           tc_fence_after();
-          acc_fold<false>(sums, tmem_base + lane_off + cbuf * 128 + c_beg * 16, p.dbg_nodrain ? 0 : my_n, &c_empty[cbuf], lane);
+          acc_fold<false>(sums, tmem_base + lane_off + cbuf * p.acc_stride + c_beg * 16, p.dbg_nodrain ? 0 : my_n, &c_empty[cbuf], lane);
         }
         // the correction accumulator (hi*lo + lo*hi) is folded into the sums right away, which hands the tile's TMEM
         // stage back before the output stage starts
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
-        acc_fold<true>(sums, tmem_base + lane_off + 256 + as * 128 + c_beg * 16, my_n, &tmem_empty[as], lane);
+        acc_fold<true>(sums, tmem_base + lane_off + (p.acc_ring + as) * p.acc_stride + c_beg * 16, my_n, &tmem_empty[as], lane);
 #pragma unroll
         for (int c = 0; c < kAccMaxChunks; ++c) {
           if (c < my_n) {
@@ -780,6 +791,10 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   p.cin_blocks = d.Cin / kBlockK;
   p.num_kb = d.R * d.S * p.cin_blocks;
   p.block_n = pick_block_n(w.Cout_pad, split);
+  // short-K layers in split precision (K <= 256: at most four accumulation chunks per tile) are bound by the output
+  // stage; 64-column tiles leave TMEM room for a ring of six chunk accumulators, so the MMA issuer can run a whole tile
+  // ahead of the epilogue instead of stalling after two chunks (experiment hook until measured)
+  if (split && getenv("B2_SHORTK_BN64") != nullptr && p.num_kb <= 4 && p.block_n == 128 && w.Cout_pad % 64 == 0) p.block_n = 64;
   p.num_n_blocks = w.Cout_pad / p.block_n;
   B2_CHECK(p.num_n_blocks * p.block_n == w.Cout_pad, "conv_tc: Cout_pad not divisible by block_n");
   const int num_m_blocks = (p.M + kBlockM - 1) / kBlockM;
@@ -848,6 +863,8 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   p.acc_kb = d.acc_kb > 0 ? d.acc_kb : kAccChunkKb;
   if (const char* e = getenv("B2_ACC_KB")) p.acc_kb = atoi(e) > 0 ? atoi(e) : kAccChunkKb;   // experiment hook
   pl->acc = split && d.acc_kb >= 0 && p.num_kb > p.acc_kb && getenv("B2_NO_ACC") == nullptr;
+  p.acc_stride = p.block_n == 64 ? 64 : 128;
+  p.acc_ring = p.block_n == 64 ? kAccRingMax : 2;   // (ring + 2 correction accumulators) * stride <= 512 columns
   if (const char* e = getenv("B2_ACC_MIN_KB")) pl->acc = pl->acc && p.num_kb > atoi(e);   // experiment hook
   pl->grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   pl->smem_bytes = static_cast<size_t>(p.num_stages) * p.stage_bytes + epi_bytes + 1024 /*align*/ + 512 /*barriers*/;
