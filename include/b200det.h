@@ -109,6 +109,37 @@ int b2_step_info(b2_ctx* ctx, int idx, char* name, int name_cap, double* flops, 
 int b2_cosine_cost(int device, const float* gallery, const int32_t* seg_offsets, int T, const float* dets, int N,
                    int D, int precision, float* cost);
 
+/* ---- DeepSORT association loop in native host code.  Replaces deep_sort/tracker.py:10-138
+ * (Tracker.predict / Tracker.update / _match), track.py:19-166, kalman_filter.py:23-232 (float64 state),
+ * linear_assignment.py:12-194 (min_cost_matching, matching_cascade, gate_cost_matrix), iou_matching.py:8-81 and the
+ * per-track gallery bookkeeping of nn_matching.py:137-154; scipy.optimize.linear_sum_assignment
+ * (linear_assignment.py:5,60) is restated natively with SciPy's tie behaviour.  The appearance cost matrix
+ * of every cascade level comes from b2_cosine_cost on `device` (one tensor-core GEMM) unless a cost function is
+ * installed (tests install the CPU oracle there; there is no built-in CPU path).
+ * b2_tracker_create mirrors Tracker(metric, max_iou_distance, max_age, n_init) + NearestNeighborDistanceMetric("cosine",
+ * matching_threshold, budget) (tracker.py:40-48, nn_matching.py:120-131; budget <= 0 = None).
+ * b2_tracker_update takes the frame's detections: tlwh [n,4] float64, confidence [n] float64 (may be NULL), features
+ * [n,feat_dim] float32 (detection.py:27-42).  b2_tracker_get_tracks copies the live tracks in list order (ids, TrackState
+ * 1 tentative / 2 confirmed, hits, age, time_since_update, mean [*,8], covariance [*,64]) and returns their number. */
+typedef struct b2_tracker b2_tracker;
+typedef int (*b2_appearance_cost_fn)(void* user, const float* gallery, const int32_t* seg_offsets, int T,
+                                     const float* dets, int N, int D, float* cost);
+int b2_tracker_create(b2_tracker** out, int device, double max_iou_distance, int max_age, int n_init,
+                      double matching_threshold, int budget, int feat_dim, int precision);
+void b2_tracker_destroy(b2_tracker* trk);
+int b2_tracker_set_cost_fn(b2_tracker* trk, b2_appearance_cost_fn fn, void* user);
+int b2_tracker_predict(b2_tracker* trk);
+int b2_tracker_update(b2_tracker* trk, const double* tlwh, const double* confidence, const float* features, int n);
+int b2_tracker_num_tracks(b2_tracker* trk);
+int b2_tracker_get_tracks(b2_tracker* trk, int cap, int32_t* ids, int32_t* state, int32_t* hits, int32_t* age,
+                          int32_t* time_since_update, double* mean, double* cov);
+/* scipy.optimize.linear_sum_assignment on a row-major [nr,nc] float64 matrix: writes min(nr,nc) (row, col) pairs sorted by
+ * row, returns their number. */
+int b2_linear_sum_assignment(const double* cost, int nr, int nc, int32_t* rows, int32_t* cols);
+/* application_util/preprocessing.py:6-74 non_max_suppression(boxes tlwh, max_bbox_overlap, scores): writes the kept
+ * indices in pick order, returns their number (scores NULL = order by bottom edge, as the reference). */
+int b2_track_nms(const double* tlwh, const double* scores, int n, double max_bbox_overlap, int32_t* keep);
+
 /* ---- ReID embedding: torchreid FeatureExtractor (torchreid/feature_extractor.py:121-252) with osnet_x1_0
  * (torchreid/models/osnet.py:522-534).  b2_reid_create fixes the crop batch; b2_reid_load_weights takes the
  * model's state_dict (torch names, fp32); b2_reid_embed takes host RGB uint8 crops already resized to

@@ -58,6 +58,15 @@ SYMBOLS = [
     ("b2_profile_steps", c_int, [c_void_p, c_int, POINTER(c_float), c_int, POINTER(c_int)]),
     ("b2_step_info", c_int, [c_void_p, c_int, ctypes.c_char_p, c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int)]),
     ("b2_cosine_cost", c_int, [c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    ("b2_tracker_create", c_int, [POINTER(c_void_p), c_int, ctypes.c_double, c_int, c_int, ctypes.c_double, c_int, c_int, c_int]),
+    ("b2_tracker_destroy", None, [c_void_p]),
+    ("b2_tracker_set_cost_fn", c_int, [c_void_p, c_void_p, c_void_p]),
+    ("b2_tracker_predict", c_int, [c_void_p]),
+    ("b2_tracker_update", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    ("b2_tracker_num_tracks", c_int, [c_void_p]),
+    ("b2_tracker_get_tracks", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("b2_linear_sum_assignment", c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    ("b2_track_nms", c_int, [c_void_p, c_void_p, c_int, ctypes.c_double, c_void_p]),
     ("b2_reid_create", c_int, [POINTER(c_void_p), c_int, c_int, c_int]),
     ("b2_reid_destroy", None, [c_void_p]),
     ("b2_reid_load_weights", c_int, [c_void_p, POINTER(c_char_p), POINTER(c_void_p), POINTER(c_int64), c_int]),

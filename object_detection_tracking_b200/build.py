@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200det.so")
 SOURCES = ["engine.cu", "conv_tc.cu", "conv_simt.cu", "stem.cu", "rpn.cu", "roialign.cu", "head.cu", "cosine.cu", "reid.cu",
-           "reid_engine.cu", "effdet.cu", "effnet.cu", "effdet_engine.cu"]
+           "reid_engine.cu", "effdet.cu", "effnet.cu", "effdet_engine.cu", "tracker.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
               "-Xcompiler", "-Wno-attributes"]
@@ -27,7 +27,7 @@ def _digest() -> str:
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(HERE, "..", "include")):
         for name in sorted(os.listdir(root)):
-            if name.endswith((".cu", ".cuh", ".h")):
+            if name.endswith((".cu", ".cuh", ".h", ".cpp")):
                 with open(os.path.join(root, name), "rb") as f:
                     h.update(name.encode())
                     h.update(f.read())
@@ -45,7 +45,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     objs = []
     for src in SOURCES:
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
         objs.append(obj)
         cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:

@@ -48,3 +48,169 @@ class GpuNearestNeighborDistanceMetric(object):
         gallery = np.concatenate(rows, axis=0)
         cost[:, :] = cosine_cost(gallery, seg, feats, device=self.device, precision=self.precision)
         return cost
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Native association loop: same surface as deep_sort.tracker.Tracker / deep_sort.track.Track.
+# ----------------------------------------------------------------------------------------------------------------
+import ctypes  # noqa: E402
+
+from . import _lib  # noqa: E402
+
+
+class TrackState(object):            # deep_sort/track.py:5-16
+    Tentative = 1
+    Confirmed = 2
+    Deleted = 3
+
+
+class Track(object):
+    """Read-only view of one live track of the native tracker (deep_sort/track.py:19-166 attribute names)."""
+
+    __slots__ = ("mean", "covariance", "track_id", "hits", "age", "time_since_update", "state")
+
+    def __init__(self, mean, covariance, track_id, hits, age, time_since_update, state):
+        self.mean, self.covariance, self.track_id = mean, covariance, track_id
+        self.hits, self.age, self.time_since_update, self.state = hits, age, time_since_update, state
+
+    def to_tlwh(self):
+        ret = self.mean[:4].copy()
+        ret[2] *= ret[3]
+        ret[:2] -= ret[2:] / 2
+        return ret
+
+    def to_tlbr(self):
+        ret = self.to_tlwh()
+        ret[2:] = ret[:2] + ret[2:]
+        return ret
+
+    def is_tentative(self):
+        return self.state == TrackState.Tentative
+
+    def is_confirmed(self):
+        return self.state == TrackState.Confirmed
+
+    def is_deleted(self):
+        return self.state == TrackState.Deleted
+
+
+_COST_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32),
+                            ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.c_int, ctypes.c_int,
+                            ctypes.POINTER(ctypes.c_float))
+
+
+class Tracker(object):
+    """Drop-in for deep_sort.tracker.Tracker (tracker.py:10-138): `Tracker(metric, max_iou_distance, max_age, n_init)`,
+    `predict()`, `update(detections)`, `.tracks`.  The whole association step (Kalman filter in float64, matching cascade,
+    IoU matching, linear assignment, track management, gallery bookkeeping) runs in libb200det (csrc/tracker.cpp); the
+    appearance cost matrices come from b2_cosine_cost on the GPU.
+
+    `metric` supplies the parameters exactly as in the reference: an object with `matching_threshold` and `budget`
+    (nn_matching.NearestNeighborDistanceMetric or GpuNearestNeighborDistanceMetric); its own sample store is not used --
+    the native tracker keeps the per-track galleries.  `cost_fn(gallery, seg_offsets, dets) -> [T,N]` replaces the GPU
+    appearance cost (tests pass the CPU oracle there); without it a B200 is required.
+    Detections need `.tlwh`, `.confidence`, `.feature` (deep_sort/detection.py:27-42)."""
+
+    def __init__(self, metric, max_iou_distance=0.5, max_age=60, n_init=1, device=0, precision="split", cost_fn=None):
+        self.metric = metric
+        self.max_iou_distance, self.max_age, self.n_init = max_iou_distance, max_age, n_init
+        self.device = getattr(metric, "device", device)
+        self._precision = {"fp16": 0, "split": 1}[getattr(metric, "precision", precision)]
+        self._lib = _lib.load()
+        self._h = None
+        self._dim = None
+        self._user_cost = cost_fn
+        self._cb = None
+        self.tracks = []
+
+    def _create(self, dim):
+        h = ctypes.c_void_p()
+        budget = self.metric.budget if getattr(self.metric, "budget", None) is not None else 0
+        _lib.check(self._lib.b2_tracker_create(ctypes.byref(h), int(self.device), float(self.max_iou_distance),
+                                               int(self.max_age), int(self.n_init),
+                                               float(self.metric.matching_threshold), int(budget), int(dim),
+                                               self._precision), "b2_tracker_create")
+        self._h, self._dim = h, dim
+        if self._user_cost is not None:
+            fn = self._user_cost
+
+            def _cb(user, gal, seg, T, dets, N, D, cost):
+                try:
+                    seg_a = np.ctypeslib.as_array(seg, shape=(T + 1,)).copy()
+                    gal_a = np.ctypeslib.as_array(gal, shape=(int(seg_a[-1]), D)).copy()
+                    det_a = np.ctypeslib.as_array(dets, shape=(N, D)).copy()
+                    out = np.asarray(fn(gal_a, seg_a, det_a), dtype=np.float32).reshape(T, N)
+                    np.ctypeslib.as_array(cost, shape=(T, N))[:, :] = out
+                    return 0
+                except Exception:      # an exception must not cross the C ABI
+                    return -1
+            self._cb = _COST_FN(_cb)
+            _lib.check(self._lib.b2_tracker_set_cost_fn(self._h, ctypes.cast(self._cb, ctypes.c_void_p), None),
+                       "b2_tracker_set_cost_fn")
+
+    def close(self):
+        if self._h is not None:
+            self._lib.b2_tracker_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def predict(self):
+        if self._h is not None:
+            _lib.check(self._lib.b2_tracker_predict(self._h), "b2_tracker_predict")
+            self._refresh()
+
+    def update(self, detections):
+        n = len(detections)
+        if self._h is None:
+            if n == 0:
+                return
+            self._create(int(np.asarray(detections[0].feature).shape[-1]))
+        tlwh = np.ascontiguousarray([d.tlwh for d in detections], dtype=np.float64).reshape(n, 4)
+        conf = np.ascontiguousarray([d.confidence for d in detections], dtype=np.float64).reshape(n)
+        feat = np.ascontiguousarray([d.feature for d in detections], dtype=np.float32).reshape(n, self._dim)
+        _lib.check(self._lib.b2_tracker_update(self._h, _lib.ptr(tlwh), _lib.ptr(conf), _lib.ptr(feat), n),
+                   "b2_tracker_update")
+        self._refresh()
+
+    def _refresh(self):
+        n = self._lib.b2_tracker_num_tracks(self._h)
+        ids, st, hits, age, tsu = (np.zeros(n, np.int32) for _ in range(5))
+        mean = np.zeros((n, 8), np.float64)
+        cov = np.zeros((n, 8, 8), np.float64)
+        got = self._lib.b2_tracker_get_tracks(self._h, n, _lib.ptr(ids), _lib.ptr(st), _lib.ptr(hits), _lib.ptr(age),
+                                              _lib.ptr(tsu), _lib.ptr(mean), _lib.ptr(cov))
+        if got != n:
+            _lib.check(-1, "b2_tracker_get_tracks")
+        self.tracks = [Track(mean[k], cov[k], int(ids[k]), int(hits[k]), int(age[k]), int(tsu[k]), int(st[k]))
+                       for k in range(n)]
+
+
+def linear_sum_assignment(cost_matrix):
+    """scipy.optimize.linear_sum_assignment restated natively (the solver the tracker uses; exported for the parity tests)."""
+    c = np.ascontiguousarray(cost_matrix, dtype=np.float64)
+    nr, nc = c.shape
+    k = min(nr, nc)
+    rows, cols = np.zeros(k, np.int32), np.zeros(k, np.int32)
+    got = _lib.load().b2_linear_sum_assignment(_lib.ptr(c), nr, nc, _lib.ptr(rows), _lib.ptr(cols))
+    if got < 0:
+        _lib.check(got, "b2_linear_sum_assignment")
+    return rows[:got].astype(np.int64), cols[:got].astype(np.int64)
+
+
+def non_max_suppression(boxes, max_bbox_overlap, scores=None):
+    """application_util/preprocessing.py:6-74 (pre-tracker NMS over tlwh boxes): kept indices in pick order."""
+    boxes = np.ascontiguousarray(boxes, dtype=np.float64).reshape(-1, 4)
+    n = len(boxes)
+    if n == 0:
+        return []
+    sc = None if scores is None else np.ascontiguousarray(scores, dtype=np.float64).reshape(n)
+    keep = np.zeros(n, np.int32)
+    got = _lib.load().b2_track_nms(_lib.ptr(boxes), _lib.ptr(sc), n, float(max_bbox_overlap), _lib.ptr(keep))
+    if got < 0:
+        _lib.check(got, "b2_track_nms")
+    return [int(i) for i in keep[:got]]

@@ -79,6 +79,66 @@ def tracker_run():
              **{"frame%d" % i: fr for i, fr in enumerate(frames)})
 
 
+def tracker_crowd():
+    """90 frames, up to 22 objects with crossing paths, look-alike appearance vectors, misses, false positives, objects that
+    leave (so that tracks age out after max_age = 60 misses) and late arrivals, through the reference Tracker + pre-tracker
+    NMS inputs -> rows (frame, track_id, tlwh) of the confirmed tracks, plus every live track's (id, state, hits, age,
+    time_since_update) after each frame (life-cycle bookkeeping)."""
+    rng = np.random.default_rng(23)
+    D, n_obj, n_frames = 32, 22, 90
+    base = np.abs(rng.standard_normal((6, D))).astype(np.float32) + 0.05
+    proto = np.stack([base[o % 6] + 0.35 * np.abs(rng.standard_normal(D)).astype(np.float32) for o in range(n_obj)])
+    pos = rng.uniform(80, 1100, (n_obj, 2))
+    vel = rng.uniform(-9, 9, (n_obj, 2))
+    size = rng.uniform(30, 110, (n_obj, 2))
+    t_in = np.where(rng.uniform(size=n_obj) < 0.3, rng.integers(5, 40, n_obj), 0)
+    t_out = np.where(rng.uniform(size=n_obj) < 0.35, rng.integers(8, 25, n_obj), n_frames)
+    metric = nn_matching.NearestNeighborDistanceMetric("cosine", 0.5, 5)
+    tracker = Tracker(metric, max_iou_distance=0.5)
+    frames, results, life = [], [], []
+    for f in range(n_frames):
+        rows = []
+        for o in range(n_obj):
+            if f < t_in[o] or f >= t_out[o] or rng.uniform() < 0.2:
+                continue
+            p = pos[o] + vel[o] * f + rng.normal(0, 1.5, 2)
+            feat = proto[o] + np.abs(rng.standard_normal(D)).astype(np.float32) * 0.08
+            rows.append(np.concatenate([p, size[o] * rng.uniform(0.95, 1.05, 2), [rng.uniform(0.5, 1.0)], feat]))
+        for _ in range(rng.integers(0, 3)):       # false positives
+            rows.append(np.concatenate([rng.uniform(50, 1100, 2), rng.uniform(30, 90, 2), [rng.uniform(0.3, 0.7)],
+                                        np.abs(rng.standard_normal(D)) + 0.05]))
+        dets_f = np.asarray(rows, dtype=np.float32).reshape(-1, 5 + D)
+        frames.append(dets_f)
+        tracker.predict()
+        tracker.update([Detection(r[:4], r[4], r[5:]) for r in dets_f])
+        for t in tracker.tracks:
+            life.append([f, t.track_id, t.state, t.hits, t.age, t.time_since_update])
+            if t.is_confirmed() and t.time_since_update <= 1:
+                results.append([f, t.track_id] + t.to_tlwh().tolist())
+    np.savez_compressed(os.path.join(HERE, "deepsort_tracker_crowd.npz"), results=np.asarray(results, dtype=np.float64),
+                        life=np.asarray(life, dtype=np.int64), **{"frame%d" % i: fr for i, fr in enumerate(frames)})
+    print("tracker_crowd: %d result rows, %d ids, max live tracks %d" % (
+        len(results), len(set(int(r[1]) for r in results)), max(np.bincount(np.asarray(life)[:, 0]))))
+
+
+def track_nms():
+    """application_util/preprocessing.non_max_suppression on seeded boxes (with and without scores)."""
+    import types
+    sys.modules.setdefault("cv2", types.ModuleType("cv2"))     # preprocessing.py imports cv2 at module top, unused here
+    from application_util import preprocessing
+    rng = np.random.default_rng(5)
+    out = {}
+    for case in range(6):
+        n = int(rng.integers(1, 40))
+        boxes = np.concatenate([rng.uniform(0, 300, (n, 2)), rng.uniform(20, 120, (n, 2))], axis=1)
+        scores = rng.uniform(0.1, 1.0, n)
+        thr = float(rng.choice([0.3, 0.5, 0.85, 1.0]))
+        out["boxes%d" % case] = boxes
+        out["scores%d" % case] = scores
+        out["thr%d" % case] = np.float64(thr)
+        out["keep_scored%d" % case] = np.asarray(preprocessing.non_max_suppression(boxes, thr, scores), dtype=np.int64)
+        out["keep_plain%d" % case] = np.asarray(preprocessing.non_max_suppression(boxes, thr), dtype=np.int64)
+    np.savez(os.path.join(HERE, "track_nms.npz"), **out)
 
 
 def osnet():
@@ -155,6 +215,8 @@ if __name__ == "__main__":
     anchors()
     cosine()
     tracker_run()
+    tracker_crowd()
+    track_nms()
     osnet()
     effdet_numpy()
     print("golden fixtures written to", HERE)

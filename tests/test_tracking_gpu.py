@@ -65,3 +65,27 @@ def test_track_ids_with_gpu_metric_equal_reference_run(golden_dir):
     assert got.shape == g["results"].shape
     np.testing.assert_array_equal(got[:, :2], g["results"][:, :2])
     assert np.abs(got[:, 2:] - g["results"][:, 2:]).max() < 1e-6
+
+
+def test_native_tracker_with_gpu_appearance_cost_equals_reference_run(golden_dir):
+    """csrc/tracker.cpp end to end (Kalman, cascade, assignment in native code; appearance cost = b2_cosine_cost on the GPU,
+    the default): ids and life cycle of the reference's own Tracker on both golden sequences."""
+    from object_detection_tracking_b200.tracking import GpuNearestNeighborDistanceMetric, Tracker
+    from oracle import deepsort
+    for name in ("deepsort_tracker.npz", "deepsort_tracker_crowd.npz"):
+        g = np.load(os.path.join(golden_dir, name))
+        n = len([k for k in g.files if k.startswith("frame")])
+        trk = Tracker(GpuNearestNeighborDistanceMetric("cosine", 0.5, 5))
+        rows_out = []
+        for f in range(n):
+            dets = [deepsort.Detection(r[:4], r[4], r[5:]) for r in g["frame%d" % f]]
+            trk.predict()
+            trk.update(dets)
+            for t in trk.tracks:
+                if t.is_confirmed() and t.time_since_update <= 1:
+                    rows_out.append([f, t.track_id] + t.to_tlwh().tolist())
+        got = np.asarray(rows_out, dtype=np.float64).reshape(-1, 6)
+        assert got.shape == g["results"].shape
+        np.testing.assert_array_equal(got[:, :2], g["results"][:, :2])
+        assert np.abs(got[:, 2:] - g["results"][:, 2:]).max() < 1e-6
+        trk.close()
