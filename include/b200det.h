@@ -140,6 +140,43 @@ int b2_linear_sum_assignment(const double* cost, int nr, int nc, int32_t* rows, 
  * indices in pick order, returns their number (scores NULL = order by bottom edge, as the reference). */
 int b2_track_nms(const double* tlwh, const double* scores, int n, double max_bbox_overlap, int32_t* keep);
 
+/* ---- TMOT / JDE association in native host code.  Replaces tmot/matching.py:28-109 and the JDETracker loop
+ * of tmot/multitracker.py:13-398 (state float64, embeddings float32).  lap.lapjv (lap 0.4.0) and cython_bbox.bbox_overlaps
+ * are third-party and absent from the reference tree: restated from their published algorithms (csrc/tmot.cpp header).
+ * b2_lapjv              = lap.lapjv(cost, extend_cost=True, cost_limit) as matching.linear_assignment uses it (:28-38) and
+ *                         multi_video_reid.py:512: x[nr] / y[nc] = matched column / row or -1, *opt = matched cost sum.
+ * b2_tmot_iou_distance  = matching.iou_distance (:57-77): 1 - IoU(+1 pixel convention) of tlbr boxes, out [na,nb].
+ * b2_tmot_fuse_motion   = matching.fuse_motion (:97-109): Kalman gate (chi2inv95 of 4 or 2 dof -> inf) and
+ *                         cost = lambda * cost + (1 - lambda) * squared Mahalanobis distance, in place on cost [T,N].
+ * b2_tmot_embedding_distance = matching.embedding_distance (:80-94): euclidean distance of track / detection embeddings,
+ *                         one tensor-core GEMM on `device` (|a|^2 + |b|^2 - 2ab, then sqrt(max(0, .))), out float64 [T,N]. */
+int b2_lapjv(const double* cost, int nr, int nc, double cost_limit, int32_t* x, int32_t* y, double* opt);
+int b2_tmot_iou_distance(const double* atlbr, int na, const double* btlbr, int nb, double* out);
+int b2_tmot_fuse_motion(const double* means, const double* covs, int T, const double* xyah, int N, double* cost,
+                        int only_position, double lambda);
+int b2_tmot_embedding_distance(int device, const float* track_feats, int T, const float* det_feats, int N, int D,
+                               int precision, double* out);
+/* JDETracker(conf_thres, track_max_second_lost, emb_max_dist, iou_max_dist1, iou_max_dist2, emb_smooth_alpha, frame_gap,
+ * frame_rate) (multitracker.py:176-204).  Track ids come from a counter shared by every tracker created with the same
+ * `share_ids_with` chain (BaseTrack._count is a class attribute, basetrack.py:13,34-37; NULL = own counter).
+ * b2_jde_update takes the frame's detections after the pre-tracker NMS: tlwh [n,4] float64, conf [n] float64, features
+ * [n,feat_dim] float32 and returns the number of output tracks (tracked and activated, :355).  The embedding distance of
+ * the first association comes from b2_distance_matrix on `device` unless a cost function is installed (it then receives
+ * one gallery row per track, seg_offsets 0..T, and must write euclidean distances).
+ * b2_jde_get_tracks copies list `which` (0 output, 1 tracked_stracks, 2 lost_stracks) in list order; with cap == 0 and
+ * ids == NULL it only returns the length. */
+typedef struct b2_jde b2_jde;
+int b2_jde_create(b2_jde** out, int device, double conf_thres, double track_max_second_lost, double emb_max_dist,
+                  double iou_max_dist1, double iou_max_dist2, double emb_smooth_alpha, double frame_gap, double frame_rate,
+                  int feat_dim, int precision, b2_jde* share_ids_with);
+void b2_jde_destroy(b2_jde* trk);
+int b2_jde_set_cost_fn(b2_jde* trk, b2_appearance_cost_fn fn, void* user);
+int b2_jde_reset(b2_jde* trk);
+int b2_jde_update(b2_jde* trk, const double* tlwh, const double* conf, const float* features, int n);
+int b2_jde_get_tracks(b2_jde* trk, int which, int cap, int32_t* ids, int32_t* state, int32_t* is_activated,
+                      int32_t* frame_id, int32_t* start_frame, int32_t* tracklet_len, double* tlwh, double* det_tlwh,
+                      double* det_conf, double* score, double* mean, double* cov);
+
 /* ---- ReID embedding: torchreid FeatureExtractor (torchreid/feature_extractor.py:121-252) with osnet_x1_0
  * (torchreid/models/osnet.py:522-534).  b2_reid_create fixes the crop batch; b2_reid_load_weights takes the
  * model's state_dict (torch names, fp32); b2_reid_embed takes host RGB uint8 crops already resized to

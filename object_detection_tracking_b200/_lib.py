@@ -67,6 +67,16 @@ SYMBOLS = [
     ("b2_tracker_get_tracks", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("b2_linear_sum_assignment", c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     ("b2_track_nms", c_int, [c_void_p, c_void_p, c_int, ctypes.c_double, c_void_p]),
+    ("b2_lapjv", c_int, [c_void_p, c_int, c_int, ctypes.c_double, c_void_p, c_void_p, POINTER(ctypes.c_double)]),
+    ("b2_tmot_iou_distance", c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    ("b2_tmot_fuse_motion", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, ctypes.c_double]),
+    ("b2_tmot_embedding_distance", c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    ("b2_jde_create", c_int, [POINTER(c_void_p), c_int] + [ctypes.c_double] * 8 + [c_int, c_int, c_void_p]),
+    ("b2_jde_destroy", None, [c_void_p]),
+    ("b2_jde_set_cost_fn", c_int, [c_void_p, c_void_p, c_void_p]),
+    ("b2_jde_reset", c_int, [c_void_p]),
+    ("b2_jde_update", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    ("b2_jde_get_tracks", c_int, [c_void_p, c_int, c_int] + [c_void_p] * 12),
     ("b2_reid_create", c_int, [POINTER(c_void_p), c_int, c_int, c_int]),
     ("b2_reid_destroy", None, [c_void_p]),
     ("b2_reid_load_weights", c_int, [c_void_p, POINTER(c_char_p), POINTER(c_void_p), POINTER(c_int64), c_int]),
