@@ -236,6 +236,19 @@ int b2_effdet_step_info(b2_effdet* ctx, int idx, char* name, int name_cap, doubl
 int b2_distance_matrix(int device, const float* a, int na, const float* b, int nb, int D, int metric, int precision,
                        float* out);
 
+/* ---- Multi-camera ReID track-pair costs (BASELINE config 5; multi_video_reid.py:260-324, 486-512).
+ * b2_track_pair_cost = compute_feature_dist (:308-324): crop embeddings of camera 1's tracks a [seg_a[N], D] grouped by
+ * seg_a[N+1], camera 2's b / seg_b[M+1] (host, float32); out[i][j] = min over the two tracks' crops of the squared
+ * euclidean distance (clamped at 0, as sklearn.euclidean_distances) where gate[i][j] != 0 (gate NULL = all pairs), else
+ * `fill` (999 in the reference).  One tensor-core GEMM over the concatenated galleries + one segmented-min kernel.
+ * b2_track_spatial_dist = compute_spatial_dist (:260-305) without the ignore-pairs reset: trajectories as (frame, x, y)
+ * rows grouped per track, out[i][j] = mean point distance over common frames (camera-2 frames + frame_offset) if <= tol,
+ * else 9999.  Host code, float64. */
+int b2_track_pair_cost(int device, const float* a, const int32_t* seg_a, int N, const float* b, const int32_t* seg_b,
+                       int M, int D, const uint8_t* gate, float fill, int precision, float* out);
+int b2_track_spatial_dist(const int32_t* frames1, const double* pts1, const int32_t* seg1, int N, const int32_t* frames2,
+                          const double* pts2, const int32_t* seg2, int M, int frame_offset, double tol, double* out);
+
 /* Single-op entry used by the kernel parity tests (host pointers, NHWC activations, HWIO kernel). */
 int b2_op_conv2d(int device, const float* x, const float* w, const float* bias, const float* res, int B, int H, int W,
                  int Cin, int R, int S, int Cout, int stride, int dil, int pad_t, int pad_b, int pad_l, int pad_r,

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200det.so")
 SOURCES = ["engine.cu", "conv_tc.cu", "conv_simt.cu", "stem.cu", "rpn.cu", "roialign.cu", "head.cu", "cosine.cu", "reid.cu",
-           "reid_engine.cu", "effdet.cu", "effnet.cu", "effdet_engine.cu", "tracker.cpp", "tmot.cpp"]
+           "reid_engine.cu", "effdet.cu", "effnet.cu", "effdet_engine.cu", "tracker.cpp", "tmot.cpp", "pairmatch.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
               "-Xcompiler", "-Wno-attributes"]

@@ -72,6 +72,36 @@ __global__ void distance_finish_kernel(const float* __restrict__ dots, int ld, i
   out[idx] = metric == 0 ? __fsub_rn(1.f, d) : __fsub_rn(__fadd_rn(na2[i], nb2[j]), __fmul_rn(2.f, d));
 }
 
+// Multi-camera ReID pair cost (multi_video_reid.py:308-324 compute_feature_dist): one warp per (track i of camera 1,
+// track j of camera 2); out[i][j] = min over the tracks' crops of max(0, |a|^2 + |b|^2 - 2 a.b) where gate[i][j] != 0,
+// else `fill`.  Lanes stride over the columns of track j (coalesced reads of the dot-product rows).
+__global__ void pair_segmin_kernel(const float* __restrict__ dots, int ld, const float* __restrict__ na2,
+                                   const float* __restrict__ nb2, const int* __restrict__ seg_a, int N,
+                                   const int* __restrict__ seg_b, int M, const unsigned char* __restrict__ gate, float fill,
+                                   float* __restrict__ out) {
+  const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (pair >= N * M) return;
+  const int i = pair / M, j = pair - i * M;
+  if (gate && !gate[pair]) {
+    if (lane == 0) out[pair] = fill;
+    return;
+  }
+  const int r0 = seg_a[i], r1 = seg_a[i + 1], c0 = seg_b[j], c1 = seg_b[j + 1];
+  float best = 3.4e38f;
+  for (int r = r0; r < r1; ++r) {
+    const float a2 = na2[r];
+    const float* row = dots + static_cast<size_t>(r) * ld;
+    for (int c = c0 + lane; c < c1; c += 32) {
+      const float d = __fsub_rn(__fadd_rn(a2, nb2[c]), __fmul_rn(2.f, row[c]));
+      best = fminf(best, fmaxf(d, 0.f));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if (lane == 0) out[pair] = (r1 > r0 && c1 > c0) ? best : fill;
+}
+
 }  // namespace
 
 int rows_to_planes(const float* src, int rows, int D, __half* hi, __half* lo, int ld, float* sqnorm, cudaStream_t s) {
@@ -85,6 +115,16 @@ int distance_finish(const float* dots, int ld, int na, int nb, int metric, const
                     cudaStream_t s) {
   if (na * nb <= 0) return 0;
   distance_finish_kernel<<<(na * nb + 255) / 256, 256, 0, s>>>(dots, ld, na, nb, metric, na2, nb2, out);
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pair_segmin(const float* dots, int ld, const float* na2, const float* nb2, const int* seg_a, int N, const int* seg_b,
+                int M, const unsigned char* gate, float fill, float* out, cudaStream_t s) {
+  if (N * M <= 0) return 0;
+  const long long threads = static_cast<long long>(N) * M * 32;
+  pair_segmin_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(dots, ld, na2, nb2, seg_a, N, seg_b, M,
+                                                                                  gate, fill, out);
   B2_CUDA(cudaGetLastError());
   return 0;
 }

@@ -178,6 +178,8 @@ int cosine_normalize_rows(const float* src, int rows, int D, __half* hi, __half*
 int rows_to_planes(const float* src, int rows, int D, __half* hi, __half* lo, int ld, float* sqnorm, cudaStream_t s);
 int distance_finish(const float* dots, int ld, int na, int nb, int metric, const float* na2, const float* nb2, float* out,
                     cudaStream_t s);
+int pair_segmin(const float* dots, int ld, const float* na2, const float* nb2, const int* seg_a, int N, const int* seg_b,
+                int M, const unsigned char* gate, float fill, float* out, cudaStream_t s);
 int cosine_segmin(const float* dots, int ld, const int* seg_offsets, int T, int N, float* cost, cudaStream_t s);
 
 }  // namespace b2

@@ -151,3 +151,76 @@ def allgather_gallery(local_feats, group=None):
     bufs = [torch.zeros_like(padded) for _ in range(world)]
     dist.all_gather(bufs, padded, group=group)
     return torch.cat([b[:c] for b, c in zip(bufs, counts)], 0), counts
+
+
+# ---- multi-camera track matching (multi_video_reid.py:260-324, 486-534) -----------------------------------------------
+
+def _pack_tracks(tracks):
+    """tracks: {track_id: (boxes [K,>=3] with frame id first and the top-down point last, features [K',D])} -> sorted ids,
+    trajectory arrays and the concatenated gallery with segment offsets."""
+    ids = sorted(tracks.keys())
+    frames, pts, seg_t, feats, seg_f = [], [], [0], [], [0]
+    for tid in ids:
+        data = np.asarray(tracks[tid][0], dtype=np.float64).reshape(len(tracks[tid][0]), -1)
+        frames.append(data[:, 0].astype(np.int32))          # int(p[0])
+        pts.append(data[:, -2:])
+        seg_t.append(seg_t[-1] + len(data))
+        f = np.asarray(tracks[tid][1], dtype=np.float32)
+        f = f.reshape(-1, f.shape[-1])
+        feats.append(f)
+        seg_f.append(seg_f[-1] + len(f))
+    return (ids, np.ascontiguousarray(np.concatenate(frames)), np.ascontiguousarray(np.concatenate(pts)),
+            np.asarray(seg_t, np.int32), np.ascontiguousarray(np.concatenate(feats)), np.asarray(seg_f, np.int32))
+
+
+def compute_spatial_dist(tracks1, tracks2, frame_offset=0, tol=50, ignore_pairs=([], [])):
+    """multi_video_reid.py:260-305 ([N,M] float64, 9999 = not comparable)."""
+    ids1, fr1, pt1, seg1, _, _ = _pack_tracks(tracks1)
+    ids2, fr2, pt2, seg2, _, _ = _pack_tracks(tracks2)
+    out = np.zeros((len(ids1), len(ids2)), dtype=np.float64)
+    _lib.check(_lib.load().b2_track_spatial_dist(_lib.ptr(fr1), _lib.ptr(pt1), _lib.ptr(seg1), len(ids1), _lib.ptr(fr2),
+                                                 _lib.ptr(pt2), _lib.ptr(seg2), len(ids2), int(frame_offset), float(tol),
+                                                 _lib.ptr(out)), "b2_track_spatial_dist")
+    for i, t1 in enumerate(ids1):                          # :299-303
+        for j, t2 in enumerate(ids2):
+            if t1 in ignore_pairs[0] and t2 in ignore_pairs[1]:
+                out[i, j] = 9999.
+    return out
+
+
+def compute_feature_dist(tracks1, tracks2, spatial_dist, device=0, precision="split"):
+    """multi_video_reid.py:308-324: [N,M] minimum squared crop-embedding distance where spatial_dist < 9999, else 999.
+    One GEMM over both cameras' galleries on the GPU instead of one sklearn call per track pair."""
+    ids1, _, _, _, f1, s1 = _pack_tracks(tracks1)
+    ids2, _, _, _, f2, s2 = _pack_tracks(tracks2)
+    gate = np.ascontiguousarray(np.asarray(spatial_dist) < 9999., dtype=np.uint8)
+    out = np.zeros((len(ids1), len(ids2)), dtype=np.float32)
+    _lib.check(_lib.load().b2_track_pair_cost(int(device), _lib.ptr(f1), _lib.ptr(s1), len(ids1), _lib.ptr(f2), _lib.ptr(s2),
+                                              len(ids2), f1.shape[1], _lib.ptr(gate), 999.0,
+                                              {"fp16": 0, "split": 1}[precision], _lib.ptr(out)), "b2_track_pair_cost")
+    return out.astype(np.float64)
+
+
+def match_tracks(tracks1, tracks2, frame_offset=0, tol=50, ignore_pairs=([], []), cost_limit=998., device=0,
+                 precision="split", feature_dist_fn=None):
+    """One camera pair of the bubble compare (multi_video_reid.py:486-534): spatial gate -> feature distance ->
+    lap.lapjv(extend_cost=True, cost_limit=998) -> [(track id in camera 1, track id in camera 2), ...].
+    `feature_dist_fn(tracks1, tracks2, spatial_dist)` replaces the GPU cost (the CPU tests pass the oracle)."""
+    from .tmot import lapjv
+    if not tracks1 or not tracks2:
+        return []
+    spatial = compute_spatial_dist(tracks1, tracks2, frame_offset, tol, ignore_pairs)
+    if feature_dist_fn is not None:
+        feat = np.asarray(feature_dist_fn(tracks1, tracks2, spatial), dtype=np.float64)
+    else:
+        feat = compute_feature_dist(tracks1, tracks2, spatial, device, precision)
+    _, x, _ = lapjv(feat, extend_cost=True, cost_limit=cost_limit)
+    ids1, ids2 = sorted(tracks1.keys()), sorted(tracks2.keys())
+    return [(ids1[i], ids2[int(j)]) for i, j in enumerate(x) if j >= 0]
+
+
+def camera_pairs(n_cameras, rank=0, world_size=1):
+    """The bubble-compare pairs (i < j) of multi_video_reid.py:474-476, dealt round-robin to the ranks: after the gallery
+    all-gather every GPU scores its share of the pairs (28 pairs on 8 cameras) independently."""
+    pairs = [(i, j) for i in range(n_cameras - 1) for j in range(i + 1, n_cameras)]
+    return pairs[rank::world_size]

@@ -1,0 +1,61 @@
+"""Multi-camera track-pair matching (BASELINE config 5, multi_video_reid.py:260-324, 486-534): the native trajectory
+distance and the assignment step against fixtures produced by the REFERENCE's own compute_spatial_dist /
+compute_feature_dist (tests/golden/make_golden_tmot.py: reid_pairs).  The feature distance itself is GPU work
+(b2_track_pair_cost; tests/test_zz_widen_gpu.py) -- here a float64 numpy checker stands in for it."""
+import os
+
+import numpy as np
+
+
+def load_cameras(g):
+    cams = []
+    for name in ("c1", "c2"):
+        cams.append({int(t): (g["%s_t%d_rows" % (name, t)], g["%s_t%d_feat" % (name, t)]) for t in g[name + "_ids"]})
+    return cams
+
+
+def feature_dist_checker(tracks1, tracks2, spatial):          # compute_feature_dist restated in float64 numpy
+    out = np.full(spatial.shape, 999.0)
+    for i, t1 in enumerate(sorted(tracks1)):
+        for j, t2 in enumerate(sorted(tracks2)):
+            if spatial[i, j] < 9999.:
+                a, b = tracks1[t1][1].astype(np.float64), tracks2[t2][1].astype(np.float64)
+                d = (a * a).sum(1)[:, None] + (b * b).sum(1)[None, :] - 2 * a @ b.T
+                out[i, j] = np.maximum(d, 0).min()
+    return out
+
+
+def test_spatial_distance_matches_reference(golden_dir):
+    from object_detection_tracking_b200 import reid
+    g = np.load(os.path.join(golden_dir, "reid_pairs.npz"))
+    c1, c2 = load_cameras(g)
+    sp = reid.compute_spatial_dist(c1, c2, frame_offset=4, tol=50, ignore_pairs=[list(g["ignore0"]), list(g["ignore1"])])
+    np.testing.assert_array_equal(sp < 9999, g["spatial"] < 9999)
+    assert (g["spatial"] < 9999).sum() >= 10
+    np.testing.assert_allclose(sp, g["spatial"], rtol=0, atol=1e-10)
+    # without the frame offset the common frames change
+    sp0 = reid.compute_spatial_dist(c1, c2, frame_offset=0, tol=50)
+    assert not np.array_equal(sp0 < 9999, sp < 9999)
+
+
+def test_checker_and_matching_match_reference(golden_dir):
+    from object_detection_tracking_b200 import reid
+    g = np.load(os.path.join(golden_dir, "reid_pairs.npz"))
+    c1, c2 = load_cameras(g)
+    fd = feature_dist_checker(c1, c2, g["spatial"])
+    np.testing.assert_allclose(fd, g["feature"], rtol=1e-6, atol=5e-5)     # sklearn keeps float32 inputs in float32 (~1e-7 of the squared norms)
+    got = reid.match_tracks(c1, c2, frame_offset=4, tol=50, ignore_pairs=[list(g["ignore0"]), list(g["ignore1"])],
+                            feature_dist_fn=feature_dist_checker)
+    ids1, ids2 = sorted(c1), sorted(c2)
+    ref = [(ids1[i], ids2[int(j)]) for i, j in enumerate(g["x"]) if j >= 0]
+    assert got == ref and len(ref) >= 5
+    assert reid.match_tracks({}, c2) == []
+
+
+def test_camera_pairs_cover_the_bubble_compare():
+    from object_detection_tracking_b200.reid import camera_pairs
+    allp = camera_pairs(8)
+    assert len(allp) == 28 and allp[0] == (0, 1) and allp[-1] == (6, 7)
+    dealt = [camera_pairs(8, r, 8) for r in range(8)]
+    assert sorted(p for d in dealt for p in d) == sorted(allp)
+    assert max(len(d) for d in dealt) - min(len(d) for d in dealt) <= 1

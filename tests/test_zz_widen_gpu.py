@@ -1,0 +1,94 @@
+"""GPU parity of the section-8f widening that composes already-verified kernels (the tensor-core GEMM behind
+b2_distance_matrix) with small new ones: TMOT embedding distance, the JDE tracker with its embedding cost on the GPU, and
+the multi-camera track-pair cost (b2_track_pair_cost).  NOTE: written in a session whose GPU budget was exhausted -- these
+tests had not yet run on a B200 when they were committed (the file sorts last so that an issue here cannot mask the
+verified suites)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def cdist64(a, b):
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    return np.sqrt(np.maximum(0.0, ((a[:, None, :] - b[None, :, :]) ** 2).sum(-1)))
+
+
+def test_tmot_embedding_distance_matches_cdist(golden_dir):
+    from object_detection_tracking_b200 import tmot
+    g = np.load(os.path.join(golden_dir, "tmot_matching.npz"))
+    got = tmot.embedding_distance(g["track_feats"], g["det_feats"])
+    # unit vectors: d^2 = 2 - 2ab carries ~1e-7 absolute error, so d is good to ~1e-7 / d (3e-4 at d -> 0)
+    assert np.abs(got - g["emb"]).max() < 1e-3
+    far = g["emb"] > 0.1
+    assert np.abs(got[far] - g["emb"][far]).max() < 5e-6
+    rng = np.random.default_rng(2)
+    a = rng.standard_normal((150, 512)).astype(np.float32)
+    b = rng.standard_normal((90, 512)).astype(np.float32)
+    assert np.abs(tmot.embedding_distance(a, b) - cdist64(a, b)).max() < 1e-3
+    assert tmot.embedding_distance(np.zeros((0, 8), np.float32), b[:, :8]).shape == (0, 90)
+
+
+def test_jde_tracker_on_gpu_reproduces_reference_ids(golden_dir):
+    """Same 80-frame, two-tracker sequence as tests/test_tmot_cpu.py, embedding cost from the tensor cores."""
+    from object_detection_tracking_b200.tmot import JDETracker, _IdGroup
+    g = np.load(os.path.join(golden_dir, "tmot_jde.npz"))
+    grp = _IdGroup()
+    trackers = [JDETracker(0.5, track_max_second_lost=4.0, frame_gap=8., frame_rate=30., id_group=grp) for _ in range(2)]
+    rows = []
+    for f in range(80):
+        for k, trk in enumerate(trackers):
+            fr = g["s%d_f%d" % (k, f)]
+            for t in trk.update([(r[:4].astype(np.float64), float(r[4]), r[5:].copy()) for r in fr]):
+                rows.append([f, k, t.track_id] + t.tlwh.tolist())
+    got = np.asarray(rows, dtype=np.float64)
+    assert got.shape[0] == g["out"].shape[0]
+    np.testing.assert_array_equal(got[:, :3], g["out"][:, :3])          # frame, tracker, track id: bit-exact
+    assert np.abs(got[:, 3:7] - g["out"][:, 3:7]).max() < 1e-6
+    for t in trackers:
+        t.close()
+
+
+def test_track_pair_cost_matches_reference(golden_dir):
+    from object_detection_tracking_b200 import reid
+    g = np.load(os.path.join(golden_dir, "reid_pairs.npz"))
+    cams = []
+    for name in ("c1", "c2"):
+        cams.append({int(t): (g["%s_t%d_rows" % (name, t)], g["%s_t%d_feat" % (name, t)]) for t in g[name + "_ids"]})
+    fd = reid.compute_feature_dist(cams[0], cams[1], g["spatial"])
+    np.testing.assert_array_equal(fd == 999.0, g["feature"] == 999.0)
+    scale = max(float((c[t][1].astype(np.float64) ** 2).sum(1).max()) for c in cams for t in c)
+    assert np.abs(fd - g["feature"]).max() <= 2e-6 * scale
+    got = reid.match_tracks(cams[0], cams[1], frame_offset=4, tol=50,
+                            ignore_pairs=[list(g["ignore0"]), list(g["ignore1"])])
+    ids1, ids2 = sorted(cams[0]), sorted(cams[1])
+    assert got == [(ids1[i], ids2[int(j)]) for i, j in enumerate(g["x"]) if j >= 0]
+
+
+def test_track_pair_cost_large_ungated():
+    """50 x 40 tracks with 1..12 crops each, D = 512, no gate, plus empty tracks -> `fill`."""
+    from object_detection_tracking_b200 import _lib
+    rng = np.random.default_rng(9)
+    N, M, D = 50, 40, 512
+    ka, kb = rng.integers(1, 13, N), rng.integers(1, 9, M)
+    ka[7] = 0
+    kb[3] = 0
+    sa = np.concatenate([[0], np.cumsum(ka)]).astype(np.int32)
+    sb = np.concatenate([[0], np.cumsum(kb)]).astype(np.int32)
+    a = rng.standard_normal((sa[-1], D)).astype(np.float32)
+    b = rng.standard_normal((sb[-1], D)).astype(np.float32)
+    out = np.zeros((N, M), np.float32)
+    _lib.check(_lib.load().b2_track_pair_cost(0, _lib.ptr(a), _lib.ptr(sa), N, _lib.ptr(b), _lib.ptr(sb), M, D, None, 999.0, 1,
+                                              _lib.ptr(out)), "b2_track_pair_cost")
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    full = (a64 ** 2).sum(1)[:, None] + (b64 ** 2).sum(1)[None, :] - 2 * a64 @ b64.T
+    ref = np.full((N, M), 999.0)
+    for i in range(N):
+        for j in range(M):
+            blk = full[sa[i]:sa[i + 1], sb[j]:sb[j + 1]]
+            if blk.size:
+                ref[i, j] = max(blk.min(), 0.0)
+    assert (ref[7] == 999.0).all() and (ref[:, 3] == 999.0).all()
+    assert np.abs(out - ref).max() <= 5e-6 * np.abs(full).max()
