@@ -24,6 +24,32 @@ from .config import normalize_config
 from .engine import Detector
 
 
+_SLOT_NAMES = ("Adam", "Adam_1", "Adadelta", "Adadelta_1", "Momentum", "beta1_power", "beta2_power")
+
+
+def check_weights(config, weights: dict) -> dict:
+    """The importer's host half (reference: initialize(), obj_detect_tracking.py:392-448).  Accepts a name -> array dict in
+    the checkpoint naming with or without the ':0' tensor suffix (utils.get_op_tensor_name, utils.py:708-723); like the
+    reference it ignores entries the inference graph has no variable for (optimizer slots, global_step, learning rate, the
+    mask / training heads) -- but where the reference silently leaves a MISSING variable at its random initial value, this
+    raises, listing every missing or mis-shaped name.  Returns float32 C-contiguous arrays keyed by op name."""
+    from .synth import frcnn_weight_shapes
+    need = frcnn_weight_shapes(config)
+    got = {}
+    for k, v in weights.items():
+        name = k[:-2] if (len(k) >= 3 and k[-2] == ":") else k
+        if name.split("/")[-1] in _SLOT_NAMES or name not in need:
+            continue
+        got[name] = np.ascontiguousarray(v, dtype=np.float32)
+    missing = sorted(set(need) - set(got))
+    bad = sorted("%s: %s, expected %s" % (n, got[n].shape, need[n]) for n in got if tuple(got[n].shape) != tuple(need[n]))
+    if missing or bad:
+        raise ValueError("checkpoint does not fit the configured graph (num_class=%d, blocks=%s): %d missing %s%s; %d "
+                         "mis-shaped %s" % (config.num_class, tuple(config.resnet_num_block), len(missing), missing[:8],
+                                            " ..." if len(missing) > 8 else "", len(bad), bad[:8]))
+    return got
+
+
 class TensorHandle:
     """Stands in for a tf.Tensor / placeholder: only identity and a name matter to the drivers."""
 
@@ -57,14 +83,14 @@ class Mask_RCNN_FPN:
 
     # -- weights (reference: initialize(), obj_detect_tracking.py:392-448) ----------------------------
     def set_weights(self, weights: dict):
-        self._weights = {k: np.asarray(v, dtype=np.float32) for k, v in weights.items()}
+        self._weights = check_weights(self.config, weights)
         for d in self._detectors.values():
             d.load_weights(self._weights)
 
     def load_npz(self, path: str):
         """Tensorpack-style .npz: names with or without the ':0' suffix (obj_detect_tracking.py:417-443)."""
         with np.load(path) as z:
-            self.set_weights({(k[:-2] if k.endswith(":0") else k): z[k] for k in z.files})
+            self.set_weights({k: z[k] for k in z.files})
 
     # -- feed dicts -----------------------------------------------------------------------------------
     def get_feed_dict_forward(self, imgdata):
@@ -193,7 +219,7 @@ class EfficientDet:
 
     def load_npz(self, path: str):
         with np.load(path) as z:
-            self.set_weights({(k[:-2] if k.endswith(":0") else k): z[k] for k in z.files})
+            self.set_weights({k: z[k] for k in z.files})
 
     def get_feed_dict_forward(self, imgdata):
         """wrapper :105-111: {image placeholder (uint8 [h,w,3] BGR): frame}."""

@@ -82,6 +82,52 @@ def synth_weights(cfg, seed: int = 1234) -> dict:
     return w
 
 
+def frcnn_weight_shapes(cfg) -> dict:
+    """Name -> shape of every variable the inference graph reads, in the reference's checkpoint naming (Tensorpack-style:
+    conv2d `W`/`b` nn.py:367,376, BatchNorm `gamma`/`beta`/`mean/EMA`/`variance/EMA` nn.py:1739-1826, dense nn.py:762;
+    scopes: nn.py:843-944 resnet, :947-1014 fpn, models.py:979-1009 rpn, :1030-1108 fastrcnn).  Used by the importer
+    (backend.check_weights) to refuse incomplete or mis-shaped checkpoints before anything reaches the device."""
+    sh = {}
+
+    def conv(name, k, cin, cout, bias=False):
+        sh[name + "/W"] = (k, k, cin, cout)
+        if bias:
+            sh[name + "/b"] = (cout,)
+
+    def bn(name, c):
+        for k in ("gamma", "beta", "mean/EMA", "variance/EMA"):
+            sh["%s/bn/%s" % (name, k)] = (c,)
+
+    conv("conv0", 7, 3, 64)
+    bn("conv0", 64)
+    cin = 64
+    for g, (feat, count) in enumerate(zip((64, 128, 256, 512), cfg.resnet_num_block)):
+        for i in range(count):
+            p = "group%d/block%d" % (g, i)
+            for name, k, ci, co in (("conv1", 1, cin, feat), ("conv2", 3, feat, feat), ("conv3", 1, feat, feat * 4)):
+                conv("%s/%s" % (p, name), k, ci, co)
+                bn("%s/%s" % (p, name), co)
+            if cin != feat * 4:
+                conv(p + "/convshortcut", 1, cin, feat * 4)
+                bn(p + "/convshortcut", feat * 4)
+            cin = feat * 4
+    nc = cfg.fpn_num_channel
+    for i, c in enumerate((256, 512, 1024, 2048)):
+        conv("fpn/lateral_1x1_c%d" % (i + 2), 1, c, nc, bias=True)
+        conv("fpn/posthoc_3x3_p%d" % (i + 2), 3, nc, nc, bias=True)
+    na = len(cfg.anchor_ratios)
+    conv("rpn/conv0", 3, nc, nc, bias=True)
+    conv("rpn/class", 1, nc, na, bias=True)
+    conv("rpn/box", 1, nc, 4 * na, bias=True)
+    dim = cfg.fpn_frcnn_fc_head_dim
+    nbox = 1 if cfg.use_frcnn_class_agnostic else cfg.num_class
+    for name, fin, fout in (("fastrcnn/fc6", nc * 49, dim), ("fastrcnn/fc7", dim, dim),
+                            ("fastrcnn/outputs/class", dim, cfg.num_class), ("fastrcnn/outputs/box", dim, nbox * 4)):
+        sh[name + "/W"] = (fin, fout)
+        sh[name + "/b"] = (fout,)
+    return sh
+
+
 def synth_frame(h: int, w: int, seed: int = 0, n_rects: int = 4) -> np.ndarray:
     """uint8 [h, w, 3] BGR frame: low-pass noise + a few flat rectangles + white noise
     (SURVEY.md section 8d), so RPN logits have spatial structure."""
