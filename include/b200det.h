@@ -77,6 +77,17 @@ int b2_detect(b2_ctx* ctx, const void* frames_dev, float* boxes, float* probs, i
 int b2_detect_host(b2_ctx* ctx, const void* frames_host, float* boxes, float* probs, int32_t* labels,
                    int32_t* valid, float* box_feat, int feat_mode);
 
+/* Frame ingest with the resize on the device.  The reference resizes on the host
+ * (frame.astype("float32") -> resizeImage = cv2.resize INTER_LINEAR, nn.py:1540-1560; obj_detect_tracking.py:597-608,
+ * enqueuer_thread.py:259-266) and feeds the resized float32 frame.  Here the uint8 source frames [batch, src_h, src_w, 3]
+ * (BGR) are uploaded and resized to the context's height x width by a kernel (same bilinear arithmetic, csrc/resize_math.h),
+ * then the pass runs as in b2_detect_host.  The context must have input_dtype = 0; the caller picks height / width with
+ * get_new_hw (nn.py:1548-1560).  b2_resize_frames runs the resize alone (parity tests), host in / host out. */
+int b2_detect_host_resize(b2_ctx* ctx, const uint8_t* frames_u8, int src_h, int src_w, float* boxes, float* probs,
+                          int32_t* labels, int32_t* valid, float* box_feat, int feat_mode);
+int b2_resize_frames(int device, const uint8_t* frames_u8, int n, int src_h, int src_w, int dst_h, int dst_w,
+                     float* out_host);
+
 /* Pipelined ingest for streaming drivers (the queue-fed loop of obj_detect_tracking_multi_queuer.py:386-480):
  * b2_submit_host returns as soon as the upload, the pass and the download of the results are enqueued; b2_wait(slot)
  * blocks until that slot's results are in the caller's buffers.  Two slots: the upload of batch i+1 overlaps the pass

@@ -46,6 +46,8 @@ SYMBOLS = [
     ("b2_load_weights", c_int, [c_void_p, POINTER(c_char_p), POINTER(c_void_p), POINTER(c_int64), c_int]),
     ("b2_detect", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
     ("b2_detect_host", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    ("b2_detect_host_resize", c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    ("b2_resize_frames", c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     ("b2_submit_host", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
     ("b2_wait", c_int, [c_void_p, c_int]),
     ("b2_stage_shape", c_int, [c_void_p, c_char_p, POINTER(c_int64), POINTER(c_int32)]),

@@ -100,6 +100,8 @@ struct b2_ctx {
   // buffers
   void* img = nullptr;
   size_t img_bytes = 0;
+  uint8_t* raw_frames = nullptr;   // b2_detect_host_resize: source-resolution uint8 frames
+  size_t raw_bytes = 0;
   // pipelined ingest (b2_submit_host / b2_wait): two staging buffers fed by a copy stream
   cudaStream_t copy_stream = nullptr, down_stream = nullptr;
   void* stage_in[2] = {nullptr, nullptr};
@@ -812,6 +814,7 @@ void b2_destroy(b2_ctx* c) {
     if (c->join_ev[h]) cudaEventDestroy(c->join_ev[h]);
     if (c->side_stream[h]) cudaStreamDestroy(c->side_stream[h]);
   }
+  if (c->raw_frames) cudaFree(c->raw_frames);
   for (void* p : c->allocs) cudaFree(p);
   for (int i = 0; i <= NPHASE; ++i)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -993,6 +996,57 @@ int b2_detect_host(b2_ctx* c, const void* frames_host, float* boxes, float* prob
   if (run_all(c)) return -1;
   if (copy_outputs(c, boxes, probs, labels, valid, box_feat, feat_mode, cudaMemcpyDeviceToHost)) return -1;
   B2_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// Frame ingest with the resize on the device (reference host path: frame.astype("float32") ->
+// resizeImage (cv2.resize INTER_LINEAR, nn.py:1540-1545) -> feed, obj_detect_tracking.py:597-608): the uint8 source frames
+// cross PCIe (4x fewer bytes than the resized float32 frames the reference feeds, no host resize), resize_u8_to_f32_kernel
+// writes the float32 network input.  The caller computes the target size with get_new_hw (nn.py:1548-1560) and creates the
+// context for it with input_dtype = 0.
+int b2_detect_host_resize(b2_ctx* c, const uint8_t* frames_u8, int src_h, int src_w, float* boxes, float* probs,
+                          int32_t* labels, int32_t* valid, float* box_feat, int feat_mode) {
+  B2_CHECK(c && frames_u8, "b2_detect_host_resize: null argument");
+  B2_CHECK(src_h > 0 && src_w > 0, "b2_detect_host_resize: bad source size");
+  B2_CHECK(c->cfg.input_dtype == 0, "b2_detect_host_resize: the context must be created with input_dtype = 0 (float32 frames)");
+  B2_CUDA(cudaSetDevice(c->device));
+  B2_CHECK(c->weights_loaded, "b2_detect_host_resize: weights not loaded");
+  const size_t need = static_cast<size_t>(c->cfg.batch) * src_h * src_w * 3;
+  if (need > c->raw_bytes) {
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->raw_frames) B2_CUDA(cudaFree(c->raw_frames));
+    c->raw_frames = nullptr;
+    c->raw_bytes = 0;
+    B2_CUDA(cudaMalloc(&c->raw_frames, need));
+    c->raw_bytes = need;
+  }
+  B2_CUDA(cudaMemcpyAsync(c->raw_frames, frames_u8, need, cudaMemcpyHostToDevice, c->stream));
+  if (resize_u8_launch(c->raw_frames, c->cfg.batch, src_h, src_w, static_cast<float*>(c->img), c->cfg.height, c->cfg.width,
+                       c->stream)) return -1;
+  if (run_all(c)) return -1;
+  if (copy_outputs(c, boxes, probs, labels, valid, box_feat, feat_mode, cudaMemcpyDeviceToHost)) return -1;
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// The resize alone (parity tests): host uint8 [n, src_h, src_w, 3] -> host float32 [n, dst_h, dst_w, 3].
+int b2_resize_frames(int device, const uint8_t* frames_u8, int n, int src_h, int src_w, int dst_h, int dst_w,
+                     float* out_host) {
+  B2_CHECK(frames_u8 && out_host && n > 0 && src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0, "b2_resize_frames: bad argument");
+  B2_CUDA(cudaSetDevice(device));
+  uint8_t* d_src = nullptr;
+  float* d_dst = nullptr;
+  const size_t nb_src = static_cast<size_t>(n) * src_h * src_w * 3, nb_dst = static_cast<size_t>(n) * dst_h * dst_w * 3 * sizeof(float);
+  B2_CUDA(cudaMalloc(&d_src, nb_src));
+  cudaError_t e = cudaMalloc(&d_dst, nb_dst);
+  if (e == cudaSuccess) e = cudaMemcpy(d_src, frames_u8, nb_src, cudaMemcpyHostToDevice);
+  int rc = 0;
+  if (e == cudaSuccess) rc = resize_u8_launch(d_src, n, src_h, src_w, d_dst, dst_h, dst_w, nullptr);
+  if (e == cudaSuccess && !rc) e = cudaMemcpy(out_host, d_dst, nb_dst, cudaMemcpyDeviceToHost);
+  cudaFree(d_src);
+  cudaFree(d_dst);
+  if (rc) return -1;
+  B2_CUDA(e);
   return 0;
 }
 

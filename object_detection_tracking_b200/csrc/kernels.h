@@ -10,6 +10,7 @@ int f32_to_planes(const float* src, __half* hi, __half* lo, size_t n, cudaStream
 int planes_to_f32(const __half* hi, const __half* lo, float* dst, size_t n, cudaStream_t s);
 // norm_mode 0: detector (x * (1/255) - mean) / std with BGR constants (models.py:345-355);
 // norm_mode 1: torchvision ToTensor + Normalize (x / 255 - mean) / std with RGB constants (feature_extractor.py:190-196)
+int resize_u8_launch(const uint8_t* src, int B, int sh, int sw, float* dst, int dh, int dw, cudaStream_t s);
 int stem_pack_launch(const void* img, int is_u8, int B, int H, int W, __half* out_hi, __half* out_lo, int Hu, int Wu,
                      int norm_mode, cudaStream_t s);
 int maxpool_launch(const __half* in_hi, const __half* in_lo, int B, int H, int W, int C, __half* out_hi,

@@ -4,6 +4,7 @@
 // Reference ops replaced: build_preprocess (models.py:337-357), resnet_fpn_backbone stem
 // (nn.py:871-900: pad [3, 2+pad32], conv0 7x7 s2 VALID + BN + ReLU, pad [1,0], MaxPooling 3x3 s2 VALID).
 #include "common.h"
+#include "resize_math.h"
 
 namespace b2 {
 namespace {
@@ -127,6 +128,29 @@ __global__ void maxpool_kernel(const __half* __restrict__ in_hi, const __half* _
   }
 }
 
+// Frame-resize ingest (nn.py:1540-1545 resizeImage = cv2.resize INTER_LINEAR on the float32 frame): uint8 HWC source
+// frames -> float32 HWC frames of the network input size, one thread per destination pixel (3 channels), coalesced
+// 12-byte stores; the 4 source taps of neighbouring threads share cache lines.  Arithmetic: resize_math.h.
+__global__ void resize_u8_to_f32_kernel(const uint8_t* __restrict__ src, int B, int sh, int sw, float* __restrict__ dst,
+                                        int dh, int dw) {
+  const size_t total = static_cast<size_t>(B) * dh * dw;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(idx % dw);
+    const int y = static_cast<int>((idx / dw) % dh);
+    const int b = static_cast<int>(idx / (static_cast<size_t>(dw) * dh));
+    const ResizeTap tx = resize_tap_x(x, sw, dw), ty = resize_tap_y(y, sh, dh);
+    const uint8_t* base = src + static_cast<size_t>(b) * sh * sw * 3;
+    const uint8_t* r0 = base + static_cast<size_t>(ty.i0) * sw * 3;
+    const uint8_t* r1 = base + static_cast<size_t>(ty.i1) * sw * 3;
+    float* o = dst + idx * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      o[c] = resize_sample(static_cast<float>(r0[tx.i0 * 3 + c]), static_cast<float>(r0[tx.i1 * 3 + c]),
+                           static_cast<float>(r1[tx.i0 * 3 + c]), static_cast<float>(r1[tx.i1 * 3 + c]), tx, ty);
+  }
+}
+
 inline unsigned grid_for(size_t total, int threads, unsigned cap = 148 * 32) {
   size_t b = (total + threads - 1) / threads;
   if (b > cap) b = cap;
@@ -155,6 +179,13 @@ int stem_pack_launch(const void* img, int is_u8, int B, int H, int W, __half* ou
     stem_pack_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(img), B, H, W, out_hi, out_lo, Hu, Wu, norm_mode);
   else
     stem_pack_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(img), B, H, W, out_hi, out_lo, Hu, Wu, norm_mode);
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int resize_u8_launch(const uint8_t* src, int B, int sh, int sw, float* dst, int dh, int dw, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(B) * dh * dw;
+  resize_u8_to_f32_kernel<<<grid_for(total, 256), 256, 0, s>>>(src, B, sh, sw, dst, dh, dw);
   B2_CUDA(cudaGetLastError());
   return 0;
 }

@@ -81,6 +81,20 @@ class Detector:
                    "b2_detect_host")
         return out
 
+    def detect_host_resize(self, frames_u8, out: dict | None = None, feat_mode: int = 0, want_feat: bool = True):
+        """Source-resolution uint8 frames [B,h,w,3] (BGR): upload, resize on the device to the configured height x width
+        (cv2.resize INTER_LINEAR arithmetic, nn.py:1540-1545), then the pass.  Needs input_dtype="float32"."""
+        frames_u8 = np.ascontiguousarray(frames_u8, dtype=np.uint8)
+        assert frames_u8.ndim == 4 and frames_u8.shape[0] == self.batch and frames_u8.shape[3] == 3, frames_u8.shape
+        if out is None:
+            out = self.alloc_outputs(feat_mode)
+        _lib.check(self.lib.b2_detect_host_resize(self._ctx, _lib.ptr(frames_u8), int(frames_u8.shape[1]),
+                                                  int(frames_u8.shape[2]), _lib.ptr(out["boxes"]), _lib.ptr(out["probs"]),
+                                                  _lib.ptr(out["labels"]), _lib.ptr(out["valid"]),
+                                                  _lib.ptr(out["feat"]) if want_feat else c_void_p(0), feat_mode),
+                   "b2_detect_host_resize")
+        return out
+
     def submit_host(self, frames, out: dict, slot: int, feat_mode: int = 0, want_feat: bool = True):
         """Asynchronous detect_host: enqueue upload + pass + download for `slot` (0/1) and return; `frames` and the
         arrays of `out` must stay alive (pinned for real overlap) until wait(slot).  Streaming drivers alternate slots
@@ -191,4 +205,28 @@ def op_conv2d(x, w, bias=None, res=None, stride=1, dil=1, pad=(0, 0, 0, 0), relu
                                 stride, dil, pt, pb, pl, pr, int(relu), int(res_shift),
                                 {"tcgen05": 0, "simt": 1}[impl], int(split), int(a_mode), _lib.ptr(out)),
                "b2_op_conv2d")
+    return out
+
+
+def get_new_hw(h, w, size, max_size):
+    """nn.py:1548-1560: (neww, newh) of resizeImage for an h x w frame."""
+    scale = size * 1.0 / min(h, w)
+    if h < w:
+        newh, neww = size, scale * w
+    else:
+        newh, neww = scale * h, size
+    if max(newh, neww) > max_size:
+        scale = max_size * 1.0 / max(newh, neww)
+        newh = newh * scale
+        neww = neww * scale
+    return int(neww + 0.5), int(newh + 0.5)
+
+
+def resize_frames(frames_u8, new_w, new_h, device=0):
+    """The ingest resize alone: uint8 [n,h,w,3] -> float32 [n,new_h,new_w,3] on the GPU (b2_resize_frames)."""
+    frames_u8 = np.ascontiguousarray(frames_u8, dtype=np.uint8)
+    n, h, w, _ = frames_u8.shape
+    out = np.empty((n, int(new_h), int(new_w), 3), dtype=np.float32)
+    _lib.check(_lib.load().b2_resize_frames(int(device), _lib.ptr(frames_u8), n, h, w, int(new_h), int(new_w), _lib.ptr(out)),
+               "b2_resize_frames")
     return out

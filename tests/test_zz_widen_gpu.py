@@ -92,3 +92,39 @@ def test_track_pair_cost_large_ungated():
                 ref[i, j] = max(blk.min(), 0.0)
     assert (ref[7] == 999.0).all() and (ref[:, 3] == 999.0).all()
     assert np.abs(out - ref).max() <= 5e-6 * np.abs(full).max()
+
+
+def test_resize_kernel_matches_oracle_and_cv2_fixture(golden_dir):
+    """b2_resize_frames (the ingest resize alone) is bit-exact with the cv2-pinned oracle."""
+    from object_detection_tracking_b200.engine import resize_frames
+    from oracle import resize
+    g = np.load(os.path.join(golden_dir, "resize_cv2.npz"))
+    for k in range(6):
+        nw, nh = (int(v) for v in g["size%d" % k])
+        got = resize_frames(g["src%d" % k][None], nw, nh)[0]
+        np.testing.assert_array_equal(got, g["dst%d" % k])
+    rng = np.random.default_rng(4)
+    src = rng.integers(0, 256, (2, 1080, 1920, 3)).astype(np.uint8)        # BASELINE frame source size, batch of 2
+    got = resize_frames(src, 1280, 720)
+    for b in range(2):
+        np.testing.assert_array_equal(got[b], resize.resize_linear(src[b], 1280, 720))
+
+
+def test_detect_with_device_resize_equals_host_resize_path():
+    """b2_detect_host_resize(uint8 source frames) == b2_detect_host(oracle-resized float32 frames), bit for bit."""
+    from object_detection_tracking_b200.config import make_config
+    from object_detection_tracking_b200.engine import Detector, get_new_hw
+    from object_detection_tracking_b200.synth import synth_frame, synth_weights
+    from oracle import resize
+    cfg = make_config(resnet_num_block=(1, 1, 2, 1), max_size=256, short_edge_size=144)
+    src = np.stack([synth_frame(216, 384, s) for s in (3, 4)])                      # 1.5x larger than the network input
+    nw, nh = get_new_hw(216, 384, 144, 256)
+    assert (nw, nh) == (256, 144)
+    det = Detector(cfg, 2, nh, nw, device=0, precision="split", use_cuda_graph=True)
+    det.load_weights(synth_weights(cfg, 1234))
+    a = det.detect_host_resize(src)
+    a = {k: v.copy() for k, v in a.items()}
+    b = det.detect_host(np.stack([resize.resize_linear(f, nw, nh) for f in src]))
+    assert int(a["valid"].sum()) > 0
+    for k in ("valid", "labels", "boxes", "probs"):
+        np.testing.assert_array_equal(a[k], b[k])
