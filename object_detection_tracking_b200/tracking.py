@@ -214,3 +214,74 @@ def non_max_suppression(boxes, max_bbox_overlap, scores=None):
     if got < 0:
         _lib.check(got, "b2_track_nms")
     return [int(i) for i in keep[:got]]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Detector output -> tracker input: host glue of the reference drivers, vectorised.
+# ----------------------------------------------------------------------------------------------------------------
+class Detection(object):
+    """deep_sort/detection.py:5-49: tlwh float64, confidence float, feature float32."""
+
+    def __init__(self, tlwh, confidence, feature):
+        self.tlwh = np.asarray(tlwh, dtype=np.float64)
+        self.confidence = float(confidence)
+        self.feature = np.asarray(feature, dtype=np.float32)
+
+    def to_tlbr(self):
+        ret = self.tlwh.copy()
+        ret[2:] += ret[:2]
+        return ret
+
+    def to_xyah(self):
+        ret = self.tlwh.copy()
+        ret[:2] += ret[2:] / 2
+        ret[2] /= ret[3]
+        return ret
+
+
+def _select_detections(final_boxes, final_probs, final_labels, box_feats, targetid2class, tracking_objs, min_confidence,
+                       scale, is_coco_model, coco_to_actev_mapping):
+    """Common body of deep_sort/utils.py:5-35 and obj_detect_tracking_multi_queuer_tmot.py:456-488: boxes / scale, class
+    filter (with the COCO -> ActEV name mapping), round(prob, 7) >= min_confidence, x1y1x2y2 -> xywh in the boxes' own
+    dtype, feature = mean over the 7x7 grid unless the detector already returned pooled features (feat_mode 1)."""
+    boxes = np.asarray(final_boxes) / scale
+    probs = np.asarray(final_probs)
+    feats = np.asarray(box_feats)
+    keep, confs = [], []
+    for j, label in enumerate(final_labels):
+        cat_name = targetid2class[label]
+        if is_coco_model:
+            if cat_name not in coco_to_actev_mapping:
+                continue
+            cat_name = coco_to_actev_mapping[cat_name]
+        conf = float(round(probs[j], 7))
+        if cat_name not in tracking_objs or conf < min_confidence:
+            continue
+        keep.append(j)
+        confs.append(conf)
+    keep = np.asarray(keep, dtype=np.int64)
+    xywh = boxes[keep].copy() if len(keep) else np.zeros((0, 4), boxes.dtype)
+    xywh[:, 2] -= xywh[:, 0]
+    xywh[:, 3] -= xywh[:, 1]
+    f = feats[keep] if len(keep) else np.zeros((0,) + feats.shape[1:], feats.dtype)
+    if f.ndim > 2:                                   # [R, C, 7, 7] -> [R, C]
+        f = np.mean(f, axis=(2, 3))
+    return xywh, confs, f
+
+
+def create_obj_infos(cur_frame, final_boxes, final_probs, final_labels, box_feats, targetid2class, tracking_objs,
+                     min_confidence, min_detection_height, scale, is_coco_model=False, coco_to_actev_mapping=None):
+    """Drop-in for deep_sort.utils.create_obj_infos (deep_sort/utils.py:5-44) -> list of Detection."""
+    xywh, confs, f = _select_detections(final_boxes, final_probs, final_labels, box_feats, targetid2class, tracking_objs,
+                                        min_confidence, scale, is_coco_model, coco_to_actev_mapping)
+    return [Detection(xywh[k].tolist(), confs[k], f[k].tolist()) for k in range(len(confs))
+            if not xywh[k, 3] < min_detection_height]
+
+
+def preprocess_detections(final_boxes, final_probs, final_labels, box_feats, targetid2class, tracking_objs, min_confidence,
+                          scale, is_coco_model=False, coco_to_actev_mapping=None):
+    """Drop-in for the TMOT driver's preprocess_detections (obj_detect_tracking_multi_queuer_tmot.py:456-488) ->
+    [(xywh, confidence, feature), ...] as JDETracker.update takes them."""
+    xywh, confs, f = _select_detections(final_boxes, final_probs, final_labels, box_feats, targetid2class, tracking_objs,
+                                        min_confidence, scale, is_coco_model, coco_to_actev_mapping)
+    return [(xywh[k], confs[k], f[k]) for k in range(len(confs))]

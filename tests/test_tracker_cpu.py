@@ -120,3 +120,29 @@ def test_pre_tracker_nms_matches_reference_golden(golden_dir):
         assert non_max_suppression(boxes, thr, scores) == g["keep_scored%d" % case].tolist()
         assert non_max_suppression(boxes, thr) == g["keep_plain%d" % case].tolist()
     assert non_max_suppression(np.zeros((0, 4)), 0.5) == []
+
+
+def test_create_obj_infos_matches_reference(golden_dir):
+    """Detector output -> tracker input against deep_sort.utils.create_obj_infos run on the same
+    arrays (tests/golden/make_golden_tmot.py: obj_infos)."""
+    from object_detection_tracking_b200.tracking import create_obj_infos, preprocess_detections
+    g = np.load(os.path.join(golden_dir, "obj_infos.npz"))
+    id2class = {1: "Person", 2: "Vehicle", 3: "Bike", 4: "car", 5: "person"}
+    coco_map = {"car": "Vehicle", "person": "Person"}
+    pooled = g["feats"].mean(axis=(2, 3))
+    cases = [("actev", ["Person"], 0.6, 0.0, 0.75, False, g["feats"]), ("coco", ["Vehicle"], 0.3, 40.0, 1.5, True, g["feats"]),
+             ("pooled", ["Person"], 0.2, 0.0, 1.0, False, pooled)]
+    for name, objs, conf, minh, scale, coco, ft in cases:
+        boxes = g["boxes"].copy()
+        dets = create_obj_infos(7, boxes, g["probs"], g["labels"], ft, id2class, objs, conf, minh, scale,
+                                is_coco_model=coco, coco_to_actev_mapping=coco_map)
+        assert len(dets) == len(g[name + "_conf"]) > 0
+        np.testing.assert_array_equal(np.asarray([d.tlwh for d in dets]).reshape(-1, 4), g[name + "_tlwh"])
+        np.testing.assert_array_equal([d.confidence for d in dets], g[name + "_conf"])
+        np.testing.assert_allclose(np.asarray([d.feature for d in dets]), g[name + "_feat"], rtol=0, atol=1e-6)
+        assert dets[0].tlwh.dtype == np.float64 and dets[0].feature.dtype == np.float32
+        np.testing.assert_array_equal(boxes, g["boxes"])              # the caller's boxes are not modified
+    tm = preprocess_detections(g["boxes"], g["probs"], g["labels"], g["feats"], id2class, ["Person"], 0.6, 0.75)
+    assert len(tm) == len(g["actev_conf"])
+    np.testing.assert_array_equal(np.asarray([t[0] for t in tm], dtype=np.float64), g["actev_tlwh"])
+    np.testing.assert_array_equal([t[1] for t in tm], g["actev_conf"])
