@@ -194,6 +194,11 @@ int b2_jde_get_tracks(b2_jde* trk, int which, int cap, int32_t* ids, int32_t* st
  * 256x128 ([n,256,128,3], n <= batch) and returns [n,512] fp32 (ToTensor + Normalize + OSNet eval forward). */
 typedef struct b2_reid b2_reid;
 int b2_reid_create(b2_reid** out, int device, int batch, int precision);
+/* model 0 = osnet_x1_0 as above; model 1 = torchreid's resnet101 (torchreid/models/resnet.py:441-455, the vehicle extractor
+ * of single_video_reid.py:410-415): b2_reid_embed then takes crops resized to 128x256 ([n,128,256,3] RGB uint8) and
+ * returns [n,2048] (global average pool of layer4, eval mode); state_dict names "conv1.weight", "bn1.*",
+ * "layer3.22.conv2.weight", "layer2.0.downsample.0.weight", ... */
+int b2_reid_create_model(b2_reid** out, int device, int batch, int precision, int model);
 void b2_reid_destroy(b2_reid* ctx);
 int b2_reid_load_weights(b2_reid* ctx, const char* const* names, const float* const* data, const int64_t* numel, int n);
 int b2_reid_embed(b2_reid* ctx, const uint8_t* crops_host, int n, float* feats_host);

@@ -80,6 +80,7 @@ SYMBOLS = [
     ("b2_jde_update", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     ("b2_jde_get_tracks", c_int, [c_void_p, c_int, c_int] + [c_void_p] * 12),
     ("b2_reid_create", c_int, [POINTER(c_void_p), c_int, c_int, c_int]),
+    ("b2_reid_create_model", c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int]),
     ("b2_reid_destroy", None, [c_void_p]),
     ("b2_reid_load_weights", c_int, [c_void_p, POINTER(c_char_p), POINTER(c_void_p), POINTER(c_int64), c_int]),
     ("b2_reid_embed", c_int, [c_void_p, c_void_p, c_int, c_void_p]),

@@ -7,6 +7,13 @@
 //   -> global avg-pool -> fc(512) + BatchNorm1d + ReLU  (eval mode returns this 512-d vector)
 // Input contract (torchreid/feature_extractor.py:190-196,209-252): RGB uint8 crops already resized to
 // 256x128 (the PIL resize stays on the host), ToTensor + Normalize happen in the stem pack kernel.
+//
+// Second model (b2_reid_create_model(..., model = 1)): torchreid's resnet101 (torchreid/models/resnet.py:441-455 ->
+// ResNet(Bottleneck, [3, 4, 23, 3], last_stride=2, fc_dims=None), forward :342-366), the vehicle extractor of
+// single_video_reid.py:410-415 with image_size (128, 256):  conv1 7x7/2 + BN + ReLU -> maxpool 3/2 pad 1 ->
+// layer1..4 of Bottleneck blocks (1x1 -> 3x3 carrying the stride -> 1x1, BN folded, ReLU / residual in the epilogue,
+// 1x1 strided downsample on the first block of a layer) -> global avg-pool = the 2048-d feature (eval mode).
+// Every conv runs on conv_tc_kernel (tcgen05); max-pool / global-average kernels are shared with OSNet.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -39,7 +46,7 @@ struct RConv {
   ConvWeights w;
   ConvIO io;
   ConvPlan* plan = nullptr;
-  int cin_real = 0, cout_real = 0, kind = 0;   // kind 0 = 1x1/dense, 1 = stem (packed 7x7)
+  int cin_real = 0, cout_real = 0, kind = 0;   // kind 0 = 1x1/dense, 1 = stem (packed 7x7), 2 = RxS conv (torch OIHW)
 };
 
 struct RDw {
@@ -67,6 +74,9 @@ struct RStep {
 
 struct b2_reid {
   int device = 0, num_sms = 148, B = 0;
+  int model = 0;                     // 0 osnet_x1_0, 1 resnet101
+  int in_h = 256, in_w = 128;        // crop size (h, w) the extractor resizes to
+  int feat_dim = 512;
   bool split = true;
   cudaStream_t stream = nullptr;
   std::vector<void*> allocs;
@@ -244,11 +254,91 @@ int build(b2_reid* c) {
   return 0;
 }
 
+// General RxS conv (torch Conv2d, symmetric padding) + BN (+ReLU) (+residual) on conv_tc_kernel.
+RConv* add_conv(b2_reid* c, const std::string& wname, const std::string& bn, const RPlanes& in, const RPlanes& out, int k,
+                int stride, int pad, bool relu, const RPlanes* res) {
+  RConv* L = add_pw(c, wname, bn, "", in, in.C, out, out.C, relu, res);
+  if (k != 1 || stride != 1) {
+    L->kind = 2;
+    L->d.R = k; L->d.S = k; L->d.stride = stride;
+    L->d.pad_t = L->d.pad_l = pad;
+    // stride 2 on even extents: the last window ends one row / column before torch's bottom / right padding, so
+    // (pad, pad - 1) is the same convolution -- and exactly the geometry the detector's strided layers use
+    // (nn.py:487-492 3x3 with pads (1,0); :555-560 1x1 with the last row / column dropped).
+    L->d.pad_b = L->d.pad_r = stride == 2 ? pad - 1 : pad;
+    L->w.K = k * k * in.C;
+    L->w.w_hi = c->alloc<__half>(static_cast<size_t>(L->w.Cout_pad) * L->w.K);
+    L->w.w_lo = c->split ? c->alloc<__half>(static_cast<size_t>(L->w.Cout_pad) * L->w.K) : nullptr;
+  }
+  return L;
+}
+
+// torchreid resnet101 (resnet.py:157-366): see the header comment.
+int build_resnet101(b2_reid* c) {
+  const int B = c->B, H = c->in_h, W = c->in_w;
+  c->crops = c->alloc<uint8_t>(static_cast<size_t>(B) * H * W * 3);
+  const int h1 = (H + 6 - 7) / 2 + 1, w1 = (W + 6 - 7) / 2 + 1;       // conv1 7x7/2 pad 3 (:211-213)
+  c->stem_u = c->planes(B, h1 + 3, w1, 64);
+  c->steps.push_back({1, 0, RPlanes(), RPlanes()});
+  RPlanes c1 = c->planes(B, h1, w1, 64);
+  {
+    RConv* L = add_pw(c, "conv1.weight", "bn1", "", c->stem_u, 64, c1, 64, true, nullptr);
+    L->kind = 1;
+    L->d.R = 4; L->d.S = 1; L->w.K = 4 * 64;
+    L->d.in_H = h1 + 3; L->d.out_H = h1;
+    L->w.w_hi = c->alloc<__half>(static_cast<size_t>(L->w.Cout_pad) * L->w.K);
+    L->w.w_lo = c->split ? c->alloc<__half>(static_cast<size_t>(L->w.Cout_pad) * L->w.K) : nullptr;
+  }
+  RPlanes x = c->planes(B, h1 / 2, w1 / 2, 64);                       // maxpool 3/2 pad 1 (:216)
+  c->steps.push_back({2, 0, c1, x});
+  c->named["conv1"] = c1;
+  c->named["maxpool"] = x;
+  const int blocks[4] = {3, 4, 23, 3}, planes[4] = {64, 128, 256, 512};
+  for (int li = 0; li < 4; ++li) {
+    const std::string ln = "layer" + std::to_string(li + 1);
+    for (int bi = 0; bi < blocks[li]; ++bi) {
+      const std::string pre = ln + "." + std::to_string(bi);
+      const int stride = (bi == 0 && li > 0) ? 2 : 1;                 // _make_layer :246-290 (last_stride = 2)
+      const int width = planes[li], cout = width * 4;
+      if (stride == 2 && ((x.H | x.W) & 1)) {
+        set_error("resnet101 reid: odd feature-map extent before a stride-2 layer");
+        return -1;
+      }
+      const int ho = x.H / stride, wo = x.W / stride;
+      RPlanes t1 = c->planes(B, x.H, x.W, width);
+      add_conv(c, pre + ".conv1.weight", pre + ".bn1", x, t1, 1, 1, 0, true, nullptr);
+      RPlanes t2 = c->planes(B, ho, wo, width);
+      add_conv(c, pre + ".conv2.weight", pre + ".bn2", t1, t2, 3, stride, 1, true, nullptr);   // stride on the 3x3 (:126)
+      RPlanes identity = x;
+      if (bi == 0) {                                                   // downsample: conv1x1(stride) + BN (:262-268)
+        identity = c->planes(B, ho, wo, cout);
+        add_conv(c, pre + ".downsample.0.weight", pre + ".downsample.1", x, identity, 1, stride, 0, false, nullptr);
+      }
+      RPlanes out = c->planes(B, ho, wo, cout);
+      add_conv(c, pre + ".conv3.weight", pre + ".bn3", t2, out, 1, 1, 0, true, &identity);       // relu(bn3 + identity)
+      x = out;
+      c->named[pre] = x;
+    }
+    c->named[ln] = x;
+  }
+  const int Bp = (B + 127) / 128 * 128;
+  c->feats = c->alloc<float>(static_cast<size_t>(Bp) * c->feat_dim);
+  c->steps.push_back({7, 0, x, RPlanes()});                            // global_avgpool -> v (:355-359)
+  for (auto& L : c->convs) {
+    L->plan = conv_tc_plan_create(L->d, L->w, L->io, c->split, c->num_sms);
+    if (!L->plan) {
+      set_error("reid plan for " + L->wname + ": " + last_error());
+      return -1;
+    }
+  }
+  return 0;
+}
+
 int run_step(b2_reid* c, const RStep& s) {
   cudaStream_t st = c->stream;
   switch (s.kind) {
     case 0: return conv_tc_launch(c->convs[s.idx]->plan, st);
-    case 1: return stem_pack_launch(c->crops, 1, c->B, 256, 128, c->stem_u.hi, c->stem_u.lo, c->stem_u.H, c->stem_u.W, 1, st);
+    case 1: return stem_pack_launch(c->crops, 1, c->B, c->in_h, c->in_w, c->stem_u.hi, c->stem_u.lo, c->stem_u.H, c->stem_u.W, 1, st);
     case 2: return maxpool_launch(s.a.hi, s.a.lo, s.a.B, s.a.H, s.a.W, s.a.C, s.b.hi, s.b.lo, s.b.H, s.b.W, st);
     case 3: {
       RDw* d = c->dws[s.idx].get();
@@ -268,6 +358,7 @@ int run_step(b2_reid* c, const RStep& s) {
     case 6:
       if (gap_launch(s.a.hi, s.a.lo, s.a.B, s.a.H * s.a.W, s.a.C, c->gap_f32, s.a.C, st)) return -1;
       return f32_to_planes(c->gap_f32, c->gap_planes.hi, c->gap_planes.lo, static_cast<size_t>(s.a.B) * s.a.C, st);
+    case 7: return gap_launch(s.a.hi, s.a.lo, s.a.B, s.a.H * s.a.W, s.a.C, c->feats, s.a.C, st);
   }
   return -1;
 }
@@ -319,17 +410,24 @@ int upload(b2_reid* c, RConv* L, const std::vector<float>& packed, const std::ve
 extern "C" {
 
 int b2_reid_create(b2_reid** out, int device, int batch, int precision) {
+  return b2_reid_create_model(out, device, batch, precision, 0);
+}
+
+int b2_reid_create_model(b2_reid** out, int device, int batch, int precision, int model) {
   B2_CHECK(out && batch >= 1, "b2_reid_create: bad argument");
   *out = nullptr;
+  B2_CHECK(model == 0 || model == 1, "b2_reid_create_model: model must be 0 (osnet_x1_0) or 1 (resnet101)");
   B2_CUDA(cudaSetDevice(device));
   std::unique_ptr<b2_reid> c(new b2_reid());
   c->device = device; c->B = batch; c->split = precision == 1;
+  c->model = model;
+  if (model == 1) { c->in_h = 128; c->in_w = 256; c->feat_dim = 2048; }   // single_video_reid.py:410-415
   cudaDeviceProp prop;
   B2_CUDA(cudaGetDeviceProperties(&prop, device));
   B2_CHECK(prop.major == 10, "b2_reid_create: this library is built for sm_100a (B200) only");
   c->num_sms = prop.multiProcessorCount;
   B2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  if (build(c.get())) { b2_reid_destroy(c.release()); return -1; }
+  if ((model == 1 ? build_resnet101(c.get()) : build(c.get()))) { b2_reid_destroy(c.release()); return -1; }
   B2_CUDA(cudaDeviceSynchronize());
   *out = c.release();
   return 0;
@@ -369,6 +467,17 @@ int b2_reid_load_weights(b2_reid* c, const char* const* names, const float* cons
             if (rr >= 7 || ss >= 7) continue;
             packed[static_cast<size_t>(o) * K + r * 64 + ch] = static_cast<float>(w[((o * 3 + cc) * 7 + rr) * 7 + ss] * scale[o]);
           }
+    } else if (L->kind == 2) {
+      // torch OIHW [co][ci][R][S] -> K-major [o][r][s][ci]
+      const int R = L->d.R, S = L->d.S;
+      const float* w = ws.get(L->wname, static_cast<int64_t>(co) * ci * R * S);
+      if (!w) return -1;
+      for (int o = 0; o < co; ++o)
+        for (int i = 0; i < ci; ++i)
+          for (int r = 0; r < R; ++r)
+            for (int q = 0; q < S; ++q)
+              packed[static_cast<size_t>(o) * K + (static_cast<size_t>(r) * S + q) * ci + i] =
+                  static_cast<float>(w[((static_cast<size_t>(o) * ci + i) * R + r) * S + q] * scale[o]);
     } else {
       const float* w = ws.get(L->wname, static_cast<int64_t>(co) * ci);   // [O][I] (1x1 OIHW or Linear)
       if (!w) return -1;
@@ -426,12 +535,12 @@ int b2_reid_embed(b2_reid* c, const uint8_t* crops_host, int n, float* feats_hos
   B2_CHECK(n >= 1 && n <= c->B, "b2_reid_embed: batch larger than the context was created for");
   B2_CUDA(cudaSetDevice(c->device));
   B2_CHECK(c->loaded, "b2_reid_embed: weights not loaded");
-  const size_t per = 256 * 128 * 3;
+  const size_t per = static_cast<size_t>(c->in_h) * c->in_w * 3;
   if (n < c->B) B2_CUDA(cudaMemsetAsync(c->crops + n * per, 0, (c->B - n) * per, c->stream));
   B2_CUDA(cudaMemcpyAsync(c->crops, crops_host, n * per, cudaMemcpyHostToDevice, c->stream));
   if (getenv("B2_REID_NO_GRAPH") != nullptr) {
     if (reid_enqueue(c)) return -1;
-    B2_CUDA(cudaMemcpyAsync(feats_host, c->feats, sizeof(float) * n * 512, cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaMemcpyAsync(feats_host, c->feats, sizeof(float) * n * c->feat_dim, cudaMemcpyDeviceToHost, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
   }
@@ -448,7 +557,7 @@ int b2_reid_embed(b2_reid* c, const uint8_t* crops_host, int n, float* feats_hos
     B2_CUDA(cudaGraphDestroy(g));
   }
   B2_CUDA(cudaGraphLaunch(c->graph, c->stream));
-  B2_CUDA(cudaMemcpyAsync(feats_host, c->feats, sizeof(float) * n * 512, cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaMemcpyAsync(feats_host, c->feats, sizeof(float) * n * c->feat_dim, cudaMemcpyDeviceToHost, c->stream));
   B2_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -477,7 +586,7 @@ int b2_reid_get_activation(b2_reid* c, const char* name, float* dst, int64_t cap
 int b2_reid_num_launches(b2_reid* c) {
   if (!c) return -1;
   int n = 0;
-  for (const auto& s : c->steps) n += s.kind == 4 ? 6 : (s.kind == 6 ? 2 : 1);
+  for (const auto& s : c->steps) n += s.kind == 4 ? 6 : (s.kind == 6 ? 2 : 1);   // gate = 4 GAP + MLP + sum
   return n;
 }
 

@@ -20,12 +20,16 @@ from . import _lib
 class ReidEngine:
     """Owner of a b2_reid context for one crop batch size."""
 
-    def __init__(self, batch: int, device: int = 0, precision: str = "split"):
+    MODELS = {"osnet_x1_0": (0, (256, 128), 512), "resnet101": (1, (128, 256), 2048)}   # id, crop (h, w), feature width
+
+    def __init__(self, batch: int, device: int = 0, precision: str = "split", model: str = "osnet_x1_0"):
         self.lib = _lib.load()
         self.batch = int(batch)
+        self.model = model
+        self.model_id, self.image_size, self.feat_dim = self.MODELS[model]
         self._ctx = c_void_p(0)
-        _lib.check(self.lib.b2_reid_create(ctypes.byref(self._ctx), int(device), self.batch,
-                                           {"fp16": 0, "split": 1}[precision]), "b2_reid_create")
+        _lib.check(self.lib.b2_reid_create_model(ctypes.byref(self._ctx), int(device), self.batch,
+                                                 {"fp16": 0, "split": 1}[precision], self.model_id), "b2_reid_create_model")
 
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
@@ -47,18 +51,19 @@ class ReidEngine:
                                                  (c_int64 * n)(*[a.size for a in arrs]), n), "b2_reid_load_weights")
 
     def embed(self, crops_u8: np.ndarray) -> np.ndarray:
-        """crops_u8: [n, 256, 128, 3] RGB uint8, n <= batch -> [n, 512] float32."""
+        """crops_u8: [n, h, w, 3] RGB uint8 already resized to the model's crop size (256x128 osnet_x1_0, 128x256
+        resnet101), n <= batch -> [n, 512 | 2048] float32."""
         crops_u8 = np.ascontiguousarray(crops_u8, dtype=np.uint8)
         n = crops_u8.shape[0]
-        assert crops_u8.shape[1:] == (256, 128, 3), crops_u8.shape
-        out = np.empty((n, 512), dtype=np.float32)
+        assert crops_u8.shape[1:] == self.image_size + (3,), crops_u8.shape
+        out = np.empty((n, self.feat_dim), dtype=np.float32)
         _lib.check(self.lib.b2_reid_embed(self._ctx, _lib.ptr(crops_u8), n, _lib.ptr(out)), "b2_reid_embed")
         return out
 
     def get_activation(self, name: str) -> np.ndarray:
         """fp32 NHWC copy of a named intermediate of the last pass (parity tests)."""
         shape = (c_int64 * 4)()
-        cap = self.batch * 131 * 64 * 64 * 4 + 1024
+        cap = self.batch * 131 * 64 * 64 * 4 * (4 if self.model_id == 1 else 1) + 1024
         buf = np.empty(cap // 4, dtype=np.float32)
         _lib.check(self.lib.b2_reid_get_activation(self._ctx, name.encode(), _lib.ptr(buf), buf.nbytes, shape),
                    "b2_reid_get_activation")
@@ -70,21 +75,24 @@ class ReidEngine:
 
 
 class FeatureExtractor(object):
-    """torchreid/feature_extractor.py:121-252 with model_name='osnet_x1_0'."""
+    """torchreid/feature_extractor.py:121-252 with model_name='osnet_x1_0' (person, image_size (256, 128)) or 'resnet101'
+    (vehicle, image_size (128, 256): single_video_reid.py:404-415)."""
 
     def __init__(self, model_name="osnet_x1_0", model_path="", image_size=(256, 128),
                  pixel_mean=(0.485, 0.456, 0.406), pixel_std=(0.229, 0.224, 0.225), pixel_norm=True,
                  device="cuda", verbose=False, batch=32, precision="split", state_dict=None):
-        if model_name != "osnet_x1_0":
-            raise NotImplementedError("the B200 path implements osnet_x1_0 (person ReID, multi_video_reid.py:422-427)")
-        if tuple(image_size) != (256, 128) or not pixel_norm or tuple(pixel_mean) != (0.485, 0.456, 0.406) \
-                or tuple(pixel_std) != (0.229, 0.224, 0.225):
-            raise NotImplementedError("only the reference defaults (256x128, ImageNet mean/std) are built")
+        if model_name not in ReidEngine.MODELS:
+            raise NotImplementedError("the B200 path implements osnet_x1_0 (person) and resnet101 (vehicle), the two "
+                                      "extractors the drivers build (single_video_reid.py:404-415)")
+        if tuple(image_size) != ReidEngine.MODELS[model_name][1] or not pixel_norm \
+                or tuple(pixel_mean) != (0.485, 0.456, 0.406) or tuple(pixel_std) != (0.229, 0.224, 0.225):
+            raise NotImplementedError("only the drivers' settings are built: 256x128 for osnet_x1_0, 128x256 for "
+                                      "resnet101, ImageNet mean/std")
         dev = 0
         if isinstance(device, str) and ":" in device:
             dev = int(device.split(":")[1])
         self.image_size = tuple(image_size)
-        self.engine = ReidEngine(batch, dev, precision)
+        self.engine = ReidEngine(batch, dev, precision, model_name)
         self.batch = batch
         if state_dict is None and model_path and os.path.isfile(model_path):
             import torch
@@ -112,7 +120,7 @@ class FeatureExtractor(object):
         feats = []
         for i in range(0, len(crops), self.batch):
             feats.append(self.engine.embed(np.stack(crops[i:i + self.batch])))
-        return torch.from_numpy(np.concatenate(feats, 0) if feats else np.zeros((0, 512), np.float32))
+        return torch.from_numpy(np.concatenate(feats, 0) if feats else np.zeros((0, self.engine.feat_dim), np.float32))
 
 
 def compute_distance_matrix(input1, input2, metric="euclidean", device=0, precision="split"):

@@ -228,6 +228,57 @@ def synth_osnet_state(seed: int = 4321) -> dict:
     return out
 
 
+def resnet101_reid_param_shapes() -> dict:
+    """Parameter / buffer names and shapes of torchreid's resnet101 state_dict (torchreid/models/resnet.py:157-290,
+    441-455: Bottleneck [3, 4, 23, 3], last_stride 2), minus the unused classifier."""
+    shapes = {"conv1.weight": (64, 3, 7, 7)}
+
+    def bn(prefix, c):
+        for k in ("weight", "bias", "running_mean", "running_var"):
+            shapes[prefix + "." + k] = (c,)
+
+    bn("bn1", 64)
+    cin = 64
+    for li, (n, planes) in enumerate(zip((3, 4, 23, 3), (64, 128, 256, 512))):
+        for bi in range(n):
+            p = "layer%d.%d" % (li + 1, bi)
+            shapes[p + ".conv1.weight"] = (planes, cin, 1, 1)
+            bn(p + ".bn1", planes)
+            shapes[p + ".conv2.weight"] = (planes, planes, 3, 3)
+            bn(p + ".bn2", planes)
+            shapes[p + ".conv3.weight"] = (planes * 4, planes, 1, 1)
+            bn(p + ".bn3", planes * 4)
+            if bi == 0:
+                shapes[p + ".downsample.0.weight"] = (planes * 4, cin, 1, 1)
+                bn(p + ".downsample.1", planes * 4)
+            cin = planes * 4
+    return shapes
+
+
+def synth_resnet101_reid_state(seed: int = 2468) -> dict:
+    """Seeded float32 state_dict for torchreid's resnet101 with non-trivial BatchNorm statistics; the last BN of every
+    residual branch gets a small gamma so that 33 stacked blocks keep activations O(1) (fp16-plane range)."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, shp in resnet101_reid_param_shapes().items():
+        if name.endswith("running_var"):
+            v = rng.uniform(0.6, 1.4, shp)
+        elif name.endswith("running_mean"):
+            v = rng.standard_normal(shp) * 0.1
+        elif name.endswith("bn3.weight"):
+            v = rng.uniform(0.1, 0.3, shp)
+        elif name.endswith(".weight") and len(shp) == 1:
+            v = rng.uniform(0.7, 1.3, shp)
+        elif name.endswith("bias"):
+            v = rng.standard_normal(shp) * 0.05
+        else:
+            fan_in = int(np.prod(shp[1:]))
+            gain = 1.0 if (name.endswith("conv3.weight") or "downsample" in name) else 2.0
+            v = rng.standard_normal(shp) * np.sqrt(gain / fan_in)
+        out[name] = v.astype(np.float32)
+    return out
+
+
 def synth_effdet_weights(cfg, seed: int = 99) -> dict:
     """Seeded weights of the EfficientDet feature network + class/box nets in the TF variable naming of
     efficientdet_arch.py (kernels HWIO, depthwise [3,3,C,1]); BN statistics non-trivial; predict biases spread

@@ -65,3 +65,25 @@ def test_gallery_allgather_world2_gloo():
         assert p.exitcode == 0
     for r in res:
         assert r[1] == [3, 5] and r[2] == 8 and r[3] == 1.0 and r[4] == 2.0    # ragged galleries, rank order
+
+
+def test_resnet101_reid_state_layout_and_param_count():
+    from object_detection_tracking_b200.synth import resnet101_reid_param_shapes, synth_resnet101_reid_state
+    shapes = resnet101_reid_param_shapes()
+    n_params = sum(int(np.prod(s)) for k, s in shapes.items() if "running_" not in k)
+    assert n_params == 44549160 - 2048 * 1000 - 1000          # torchvision resnet101 minus its 1000-way fc
+    assert shapes["layer3.22.conv2.weight"] == (256, 256, 3, 3) and shapes["layer2.0.downsample.0.weight"] == (512, 256, 1, 1)
+    assert "layer1.1.downsample.0.weight" not in shapes
+    a = synth_resnet101_reid_state(7)["layer4.2.conv3.weight"]
+    assert a.dtype == np.float32 and a.shape == (2048, 512, 1, 1)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/torchreid"), reason="reference checkout not present")
+def test_resnet101_state_layout_matches_reference_model():
+    import sys
+    sys.path.insert(0, "/root/reference")
+    from torchreid.models import build_model
+    from object_detection_tracking_b200.synth import resnet101_reid_param_shapes
+    sd = build_model("resnet101", num_classes=1, pretrained=False, use_gpu=False).state_dict()
+    ref = {k: tuple(v.shape) for k, v in sd.items() if not k.startswith("classifier") and not k.endswith("num_batches_tracked")}
+    assert ref == {k: tuple(v) for k, v in resnet101_reid_param_shapes().items()}
