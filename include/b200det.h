@@ -54,6 +54,9 @@ typedef struct b2_config {
                                  partial sum is folded in with round-to-nearest; 0 = default (1), <0 = never */
   int32_t multi_semantics;    /* 1 = post-processing of Mask_RCNN_FPN_multi (combined_non_max_suppression:
                                  no RPN min-size filter, zero-padded level merge + zero-area drop, no score threshold) */
+  int32_t add_mask;           /* --add_mask: mask head on the final boxes (models.py:934-961, 1173-1199; mrcnn_head_dim 256):
+                                 ROIAlign 14x14 -> 4 x conv3x3 -> 2x2/2 transposed conv -> conv1x1 -> sigmoid of the box's own
+                                 class; results through b2_get_masks */
 } b2_config;
 
 const char* b2_last_error(void);
@@ -95,6 +98,10 @@ int b2_resize_frames(int device, const uint8_t* frames_u8, int n, int src_h, int
 int b2_submit_host(b2_ctx* ctx, const void* frames_host, float* boxes, float* probs, int32_t* labels, int32_t* valid,
                    float* box_feat, int feat_mode, int slot);
 int b2_wait(b2_ctx* ctx, int slot);
+
+/* final_masks of the last pass (needs cfg.add_mask): [batch][result_per_im][28][28] float32 (models.py:958-961; the
+ * drivers paste them into the frame with fill_full_mask, obj_detect_tracking.py:719); rows >= valid[b] are zero. */
+int b2_get_masks(b2_ctx* ctx, float* masks_host, int64_t capacity_bytes);
 
 /* Stage-addressable access for parity tests.  Activations are returned as fp32. */
 int b2_stage_shape(b2_ctx* ctx, const char* name, int64_t shape[4], int32_t* dtype /*0 f32, 1 i32*/);

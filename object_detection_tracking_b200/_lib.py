@@ -23,6 +23,7 @@ class B2Config(ctypes.Structure):
         ("fastrcnn_nms_iou_thres", c_float), ("result_score_thres", c_float),
         ("anchor_strides", c_float * 5), ("anchor_sizes", c_float * 5), ("anchor_ratios", c_float * 3),
         ("bbox_reg_weights", c_float * 4), ("accum_chunk", c_int32), ("multi_semantics", c_int32),
+        ("add_mask", c_int32),
     ]
 
 
@@ -50,6 +51,7 @@ SYMBOLS = [
     ("b2_resize_frames", c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     ("b2_submit_host", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
     ("b2_wait", c_int, [c_void_p, c_int]),
+    ("b2_get_masks", c_int, [c_void_p, c_void_p, c_int64]),
     ("b2_stage_shape", c_int, [c_void_p, c_char_p, POINTER(c_int64), POINTER(c_int32)]),
     ("b2_get_stage", c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
     ("b2_set_stage", c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
@@ -174,4 +176,5 @@ def make_config(cfg, batch: int, height: int, width: int, input_dtype: str = "fl
         c.bbox_reg_weights[i] = float(cfg.fastrcnn_bbox_reg_weights[i])
     c.multi_semantics = int(bool(multi_semantics))
     c.accum_chunk = int(accum_chunk)
+    c.add_mask = int(bool(getattr(cfg, "add_mask", False)))
     return c

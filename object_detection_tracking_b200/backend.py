@@ -78,6 +78,7 @@ class Mask_RCNN_FPN:
         self.final_probs = TensorHandle(self, "final_probs:0")
         self.fpn_box_feat = TensorHandle(self, "fpn_box_feat:0")
         self.final_valid_indices = TensorHandle(self, "final_valid_indices:0")
+        self.final_masks = TensorHandle(self, "final_masks:0")          # with config.add_mask (models.py:143-146,958-961)
         self._weights = None
         self._detectors = {}
 
@@ -138,6 +139,10 @@ class Mask_RCNN_FPN:
                     res.append(out["feat"][:r].copy())
                 elif f is self.final_valid_indices:
                     res.append(valid.copy())
+                elif f is self.final_masks:
+                    if not getattr(self.config, "add_mask", False):
+                        raise KeyError("final_masks needs config.add_mask (models.py:934)")
+                    res.append(det.get_masks()[0, :r].copy())                  # [R,28,28] float32
                 else:
                     raise KeyError("unknown fetch %r" % (f,))
             else:

@@ -37,6 +37,7 @@ _DEFAULTS = dict(
     im_batch_size=1,
     is_train=False,
     add_mask=False,
+    mrcnn_head_dim=256,                # obj_detect_tracking.py:324
     use_partial_classes=False,
     is_efficientdet=False,
 )

@@ -54,6 +54,27 @@ __global__ void pool_feat_kernel(const float* __restrict__ feat, int rows, int C
   out[idx] = s / 49.f;
 }
 
+// Mask head output (models.py:950-958): per final detection the logits of its own class, sigmoid, and the un-shuffle of
+// the 2x2 transposed-conv taps.  logits rows are ((roi * 196 + y * 14 + x) * 4 + dy * 2 + dx); out [B*R][28][28].
+__global__ void mask_select_kernel(const float* __restrict__ logits, int ld, const int* __restrict__ labels,
+                                   const int* __restrict__ count, int B, int R, float* __restrict__ out) {
+  const size_t total = static_cast<size_t>(B) * R * 784;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int px = static_cast<int>(idx % 784);
+    const size_t roi = idx / 784;
+    const int b = static_cast<int>(roi / R), j = static_cast<int>(roi % R);
+    float v = 0.f;
+    if (j < count[b]) {
+      const int Y = px / 28, X = px % 28;
+      const size_t row = (roi * 196 + static_cast<size_t>(Y >> 1) * 14 + (X >> 1)) * 4 + (Y & 1) * 2 + (X & 1);
+      const float z = logits[row * ld + (labels[roi] - 1)];
+      v = 1.f / (1.f + expf(-z));
+    }
+    out[idx] = v;
+  }
+}
+
 struct Planes {
   __half* hi = nullptr;
   __half* lo = nullptr;
@@ -69,7 +90,8 @@ struct Layer {
   ConvPlan* plan = nullptr;
   std::vector<ConvPlan*> part_plan;              // the same layer over each 1/nsplit of the batch (multi-stream passes)
   bool has_bn = false, has_bias = false;
-  int kind = 0;            // 0 conv HWIO, 1 fc6 (NCHW-flatten permute), 2 dense, 3 rpn class+box, 4 head outputs
+  int kind = 0;            // 0 conv HWIO, 1 fc6 (NCHW-flatten permute), 2 dense, 3 rpn class+box, 4 head outputs,
+                           // 5 stem, 6 mask-head transposed conv 2x2/2 (as a 1x1 conv onto 4 taps x C outputs)
 };
 
 struct StageRef {
@@ -112,16 +134,22 @@ struct b2_ctx {
   Planes stem_u, c1, pool, cfeat[4], lat[4], pfeat[5], rpn_h[5];
   float* rpn_out[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   RpnParams rpn;
-  RoiAlignParams roi1, roi2;
+  RoiAlignParams roi1, roi2, roi3;
   HeadPostParams post;
   Planes roi_feat, fc6, fc7;
   float* head_logits = nullptr;
   float* box_feat = nullptr;
   float* box_feat_pooled = nullptr;
+  // mask head (cfg.add_mask): ROIAlign 14 of the final boxes -> 4 x conv3x3 -> deconv -> conv1x1 -> sigmoid of own class
+  Planes mask_a, mask_b, mask_up;
+  float* mask_logits = nullptr;
+  int mask_ld = 0;
+  float* final_masks = nullptr;    // [B][R][28][28]
   // launch bookkeeping
   struct Step {
     int phase;
-    int kind;   // 0 conv layer, 1 stem, 2 maxpool, 3 subsample p6, 4 proposals, 5 roialign1, 6 post, 7 roialign2
+    int kind;   // 0 conv layer, 1 stem, 2 maxpool, 3 subsample p6, 4 proposals, 5 roialign1, 6 post, 7 roialign2,
+                // 8 roialign 14x14 of the final boxes (mask head), 9 mask select + sigmoid
     Layer* layer;
   };
   std::vector<Step> steps;
@@ -479,6 +507,41 @@ int build_plan(b2_ctx* c) {
   c->steps.push_back({7, 7, nullptr});
   reg_raw(c, "fpn_box_feat", c->box_feat, 1, static_cast<int64_t>(B) * R, nc, 7, 7);
 
+  // ---- mask head (models.py:934-961, 1173-1199), phase 7, only with cfg.add_mask ----
+  if (cfg.add_mask) {
+    B2_CHECK(cfg.num_class >= 2, "b2_create: add_mask needs at least one foreground class");
+    const int MR = B * R, md = 256;                  // mrcnn_head_dim (obj_detect_tracking.py:324)
+    B2_CHECK(c->alloc_planes(c->mask_a, MR, 14, 14, md), "alloc mask head a");
+    B2_CHECK(c->alloc_planes(c->mask_b, MR, 14, 14, md), "alloc mask head b");
+    B2_CHECK(c->alloc_planes(c->mask_up, MR, 14, 14, 4 * md), "alloc mask head deconv");
+    RoiAlignParams& r3 = c->roi3;
+    r3 = r1;
+    r3.rois_per_image = R;
+    r3.boxes = hp.final_boxes; r3.count = hp.final_count;
+    r3.out_hi = c->mask_a.hi; r3.out_lo = c->mask_a.lo; r3.out_nchw = nullptr; r3.out_res = 14;
+    c->steps.push_back({7, 8, nullptr});
+    const Planes* pp[2] = {&c->mask_a, &c->mask_b};
+    for (int k = 0; k < 4; ++k)                      // conv2d 3x3 SAME + bias + ReLU
+      add_conv(c, 7, "maskrcnn/fcn" + std::to_string(k), *pp[k & 1], 14, 14, 3, 1, 1, 1, 1, 1, 1, md, false, true, true,
+               *pp[(k + 1) & 1], 0, 0, nullptr, 0);
+    // Conv2DTranspose 2x2 stride 2: no overlap between taps, so it is a 1x1 conv onto (tap, channel) outputs
+    add_conv(c, 7, "maskrcnn/deconv", c->mask_a, 14, 14, 1, 1, 1, 0, 0, 0, 0, 4 * md, false, true, true, c->mask_up, 0, 0,
+             nullptr, 0, nullptr, 0, 6);
+    // the 1x1 class conv commutes with the pixel shuffle: apply it to the (pixel, tap) rows directly
+    const int rows = MR * 196 * 4, rows_pad = (rows + 127) / 128 * 128;
+    c->mask_ld = (cfg.num_class - 1 + 15) / 16 * 16;
+    c->mask_logits = c->alloc<float>(static_cast<size_t>(rows_pad) * c->mask_ld);
+    Planes up_rows = c->mask_up;
+    up_rows.B = 1; up_rows.H = 1; up_rows.W = rows; up_rows.C = md;
+    add_conv(c, 7, "maskrcnn/conv", up_rows, 1, rows, 1, 1, 1, 0, 0, 0, 0, cfg.num_class - 1, false, true, false, Planes(),
+             0, 0, nullptr, 0, c->mask_logits, c->mask_ld);
+    c->final_masks = c->alloc<float>(static_cast<size_t>(MR) * 784);
+    c->steps.push_back({7, 9, nullptr});
+    reg_planes(c, "mask_roi_feat", c->mask_a);       // valid right after step 8 only (ping-pong buffer)
+    reg_raw(c, "mask_logits", c->mask_logits, 1, MR, 196 * 4, c->mask_ld, 1);
+    reg_raw(c, "final_masks", c->final_masks, 1, B, R, 28, 28);
+  }
+
   // ---- tensor-core plans ----
   if (cfg.conv_impl == 0) {
     for (auto& L : c->layers) {
@@ -559,6 +622,16 @@ int run_step(b2_ctx* c, const b2_ctx::Step& s) {
       pool_feat_kernel<<<(rows * cfg.fpn_num_channel + 255) / 256, 256, 0, st>>>(c->box_feat, rows,
                                                                                  cfg.fpn_num_channel,
                                                                                  c->box_feat_pooled);
+      B2_CUDA(cudaGetLastError());
+      return 0;
+    }
+    case 8:
+      return roialign_launch(c->roi3, st);
+    case 9: {
+      const size_t total = static_cast<size_t>(cfg.batch) * cfg.result_per_im * 784;
+      mask_select_kernel<<<static_cast<unsigned>(std::min<size_t>((total + 255) / 256, 148 * 32)), 256, 0, st>>>(
+          c->mask_logits, c->mask_ld, c->post.final_labels, c->post.final_count, cfg.batch, cfg.result_per_im,
+          c->final_masks);
       B2_CUDA(cudaGetLastError());
       return 0;
     }
@@ -701,6 +774,18 @@ int load_layer(b2_ctx* c, Layer* L, const WeightSet& ws) {
         const float* src = w + (static_cast<size_t>(t) * Cin + ci) * Cout;
         for (int o = 0; o < Cout; ++o)
           packed[static_cast<size_t>(o) * K + static_cast<size_t>(t) * Cin + ci] = static_cast<float>(src[o] * scale[o]);
+      }
+  } else if (L->kind == 6) {
+    // tf.layers.Conv2DTranspose kernel [kh=2, kw=2, out, in] (nn.py:402-412): output row (dy*2+dx)*out + o of the 1x1 conv
+    const int co = Cout / 4;
+    const float* w = ws.get(L->name + "/W", static_cast<int64_t>(4) * co * Cin);
+    const float* b = ws.get(L->name + "/b", co);
+    if (!w || !b) return -1;
+    for (int t = 0; t < 4; ++t)
+      for (int o = 0; o < co; ++o) {
+        const float* src = w + (static_cast<size_t>(t) * co + o) * Cin;
+        for (int ci = 0; ci < Cin; ++ci) packed[static_cast<size_t>(t * co + o) * K + ci] = src[ci];
+        shift[t * co + o] = b[o];
       }
   } else if (L->kind == 5) {
     // stem: reference HWIO [7,7,3,64] re-indexed for the packed operand (stem.cu):
@@ -905,7 +990,7 @@ int b2_step_info(b2_ctx* c, int idx, char* name, int name_cap, double* flops, do
   B2_CHECK(idx >= 0 && idx < static_cast<int>(c->steps.size()), "b2_step_info: index out of range");
   const b2_ctx::Step& s = c->steps[idx];
   static const char* kKindNames[] = {"conv", "stem_pack", "maxpool", "p6_subsample", "rpn_proposals", "roialign_proposals",
-                                     "head_post", "roialign_final"};
+                                     "head_post", "roialign_final", "roialign_mask", "mask_select"};
   std::string nm = s.kind == 0 ? s.layer->name : kKindNames[s.kind];
   *kind = s.kind;
   *flops = 0;
@@ -1119,6 +1204,18 @@ int b2_wait(b2_ctx* c, int slot) {
   B2_CHECK(c->slot_busy[slot], "b2_wait: nothing was submitted on this slot");
   B2_CUDA(cudaEventSynchronize(c->out_done[slot]));
   c->slot_busy[slot] = false;
+  return 0;
+}
+
+// final_masks of the last pass (models.py:958-961): [batch][result_per_im][28][28] float32, rows beyond valid[b] are 0.
+int b2_get_masks(b2_ctx* c, float* masks_host, int64_t capacity_bytes) {
+  B2_CHECK(c && masks_host, "b2_get_masks: null argument");
+  B2_CHECK(c->cfg.add_mask && c->final_masks, "b2_get_masks: the context was created without add_mask");
+  B2_CUDA(cudaSetDevice(c->device));
+  const int64_t bytes = static_cast<int64_t>(c->cfg.batch) * c->cfg.result_per_im * 784 * 4;
+  B2_CHECK(capacity_bytes >= bytes, "b2_get_masks: buffer too small");
+  B2_CUDA(cudaMemcpyAsync(masks_host, c->final_masks, bytes, cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

@@ -48,6 +48,8 @@ struct RoiAlignParams {
   __half* out_hi;             // [B*rois][7][7][C]   (fc6 operand order), or
   __half* out_lo;
   float* out_nchw;            // [B*rois][C][7][7]   fp32 (fpn_box_feat contract)
+  int out_res;                // 0 / 7: 7x7 bins from a 14x14 crop; 14: 14x14 bins from a 28x28 crop (mask head,
+                              // models.py:936-937), planes output [B*rois][14][14][C]
 };
 int roialign_launch(const RoiAlignParams& p, cudaStream_t s);
 

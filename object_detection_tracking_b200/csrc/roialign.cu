@@ -12,8 +12,7 @@
 namespace b2 {
 namespace {
 
-constexpr int kOut = 7;
-constexpr int kCrop = 14;
+constexpr int kOut = 7;      // box head / fpn_box_feat resolution (level_roi_feat_kernel, default of roialign_kernel)
 
 struct Axis {
   int lo[2], hi[2];
@@ -21,7 +20,8 @@ struct Axis {
   bool ok[2];
 };
 
-// sample coordinates of the two crop rows/cols (2*bin, 2*bin+1) along one axis of size `dim`
+// sample coordinates of the two crop rows/cols (2*bin, 2*bin+1) along one axis of size `dim`; kCrop = 2 * output bins
+template <int kCrop = 2 * kOut>
 __device__ __forceinline__ Axis make_axis(float c0, float c1, int dim, int bin) {
   const float dm1 = static_cast<float>(dim - 1);
   const float spacing = __fdiv_rn(__fsub_rn(c1, c0), static_cast<float>(kCrop));
@@ -66,6 +66,7 @@ __device__ __forceinline__ void load8(const __half* hi, const __half* lo, size_t
   }
 }
 
+template <int kOut>
 __global__ void __launch_bounds__(256) roialign_kernel(const __grid_constant__ RoiAlignParams p) {
   const int lane = threadIdx.x & 31;
   const size_t wid = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
@@ -91,8 +92,8 @@ __global__ void __launch_bounds__(256) roialign_kernel(const __grid_constant__ R
     lvl = min(max(lvl, 2), 5) - 2;
     const float is = p.inv_stride[lvl];
     const int H = p.H[lvl], W = p.W[lvl];
-    const Axis ay = make_axis(__fmul_rn(bx.y, is), __fmul_rn(bx.w, is), H, oy);
-    const Axis ax = make_axis(__fmul_rn(bx.x, is), __fmul_rn(bx.z, is), W, ox);
+    const Axis ay = make_axis<2 * kOut>(__fmul_rn(bx.y, is), __fmul_rn(bx.w, is), H, oy);
+    const Axis ax = make_axis<2 * kOut>(__fmul_rn(bx.x, is), __fmul_rn(bx.z, is), W, ox);
     const __half* fh = p.feat_hi[lvl];
     const __half* fl = p.feat_lo[lvl];
     const size_t img_off = static_cast<size_t>(b) * p.pitch_H[lvl] * p.pitch_W[lvl];
@@ -211,9 +212,13 @@ int level_roi_feat_launch(const LevelRoiFeatParams& p, cudaStream_t s) {
 
 int roialign_launch(const RoiAlignParams& p, cudaStream_t s) {
   B2_CHECK(p.C == 256, "roialign: C must be 256 (one 16-byte vector per lane)");
-  const size_t warps = static_cast<size_t>(p.B) * p.rois_per_image * kOut * kOut;
+  B2_CHECK(p.out_res == 0 || p.out_res == 7 || p.out_res == 14, "roialign: out_res must be 7 or 14");
+  const int res = p.out_res == 14 ? 14 : 7;
+  B2_CHECK(res == 7 || p.out_nchw == nullptr, "roialign: the 14x14 variant writes planes only");
+  const size_t warps = static_cast<size_t>(p.B) * p.rois_per_image * res * res;
   const unsigned blocks = static_cast<unsigned>((warps * 32 + 255) / 256);
-  roialign_kernel<<<blocks, 256, 0, s>>>(p);
+  if (res == 14) roialign_kernel<14><<<blocks, 256, 0, s>>>(p);
+  else roialign_kernel<7><<<blocks, 256, 0, s>>>(p);
   B2_CUDA(cudaGetLastError());
   return 0;
 }

@@ -95,6 +95,12 @@ class Detector:
                    "b2_detect_host_resize")
         return out
 
+    def get_masks(self) -> np.ndarray:
+        """final_masks of the last pass (config.add_mask): [B, result_per_im, 28, 28] float32 (models.py:958-961)."""
+        out = np.empty((self.batch, int(self.cfg.result_per_im), 28, 28), dtype=np.float32)
+        _lib.check(self.lib.b2_get_masks(self._ctx, _lib.ptr(out), out.nbytes), "b2_get_masks")
+        return out
+
     def submit_host(self, frames, out: dict, slot: int, feat_mode: int = 0, want_feat: bool = True):
         """Asynchronous detect_host: enqueue upload + pass + download for `slot` (0/1) and return; `frames` and the
         arrays of `out` must stay alive (pinned for real overlap) until wait(slot).  Streaming drivers alternate slots

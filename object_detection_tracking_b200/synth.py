@@ -79,6 +79,15 @@ def synth_weights(cfg, seed: int = 1234) -> dict:
     nbox = ncls if not cfg.use_frcnn_class_agnostic else 1
     w["fastrcnn/outputs/box/W"] = (rng.standard_normal((dim, nbox * 4)) * 0.03).astype(np.float32)
     w["fastrcnn/outputs/box/b"] = (rng.standard_normal(nbox * 4) * 0.02).astype(np.float32)
+    if getattr(cfg, "add_mask", False):              # maskrcnn_up4conv_head (models.py:1173-1199); drawn last so that the
+        md = getattr(cfg, "mrcnn_head_dim", 256)     # detector weights of a seed do not depend on add_mask
+        for k in range(4):
+            w["maskrcnn/fcn%d/W" % k] = _conv_w(rng, 3, nc if k == 0 else md, md)
+            w["maskrcnn/fcn%d/b" % k] = (rng.standard_normal(md) * 0.02).astype(np.float32)
+        w["maskrcnn/deconv/W"] = (rng.standard_normal((2, 2, md, md)) * np.sqrt(2.0 / md)).astype(np.float32)   # [kh,kw,out,in]
+        w["maskrcnn/deconv/b"] = (rng.standard_normal(md) * 0.02).astype(np.float32)
+        w["maskrcnn/conv/W"] = (rng.standard_normal((1, 1, md, ncls - 1)) * np.sqrt(4.0 / md)).astype(np.float32)
+        w["maskrcnn/conv/b"] = (rng.standard_normal(ncls - 1) * 0.5).astype(np.float32)
     return w
 
 
@@ -125,6 +134,13 @@ def frcnn_weight_shapes(cfg) -> dict:
                             ("fastrcnn/outputs/class", dim, cfg.num_class), ("fastrcnn/outputs/box", dim, nbox * 4)):
         sh[name + "/W"] = (fin, fout)
         sh[name + "/b"] = (fout,)
+    if getattr(cfg, "add_mask", False):              # models.py:1173-1199; Conv2DTranspose kernel is [kh, kw, out, in]
+        md = getattr(cfg, "mrcnn_head_dim", 256)
+        for k in range(4):
+            conv("maskrcnn/fcn%d" % k, 3, nc if k == 0 else md, md, bias=True)
+        sh["maskrcnn/deconv/W"] = (2, 2, md, md)
+        sh["maskrcnn/deconv/b"] = (md,)
+        conv("maskrcnn/conv", 1, md, cfg.num_class - 1, bias=True)
     return sh
 
 

@@ -249,6 +249,32 @@ def fastrcnn_predictions(boxes, probs, cfg):
     return sel[ti][:, ::-1].copy(), tp
 
 
+def maskrcnn_head(feat, W, num_class):
+    """maskrcnn_up4conv_head (models.py:1173-1199): 4 x [conv3x3 SAME + bias + ReLU] on the [R,256,14,14] ROI features,
+    Conv2DTranspose 2x2 stride 2 + bias + ReLU (nn.deconv2d, nn.py:383-413; TF kernel layout [kh, kw, out, in]),
+    conv1x1 + bias -> [R, num_class - 1, 28, 28] logits."""
+    x = _t(feat)
+    with torch.no_grad():
+        for k in range(4):
+            x = torch.relu(_conv(x, W["maskrcnn/fcn%d/W" % k], pad=(1, 1, 1, 1), bias=W["maskrcnn/fcn%d/b" % k]))
+        wd = _t(W["maskrcnn/deconv/W"]).permute(3, 2, 0, 1).contiguous()      # -> torch's [in, out, kh, kw]
+        x = torch.relu(F.conv_transpose2d(x, wd, _t(W["maskrcnn/deconv/b"]), stride=2))
+        x = _conv(x, W["maskrcnn/conv/W"], bias=W["maskrcnn/conv/b"])
+    assert x.shape[1] == num_class - 1
+    return x.numpy()
+
+
+def final_masks(cfg, W, feats, fboxes, flabels):
+    """models.py:934-961: ROIAlign 14 of the final boxes -> mask head -> the logits of each box's own class ->
+    sigmoid -> [R,28,28]."""
+    if not len(fboxes):
+        return np.zeros((0, 28, 28), np.float32), np.zeros((0, cfg.num_class - 1, 28, 28), np.float32)
+    roi14, _ = multilevel_roi_align(feats, fboxes, 14, cfg.anchor_strides)
+    logits = maskrcnn_head(roi14, W, cfg.num_class)
+    sel = logits[np.arange(len(fboxes)), np.asarray(flabels, dtype=np.int64) - 1]
+    return (1.0 / (1.0 + np.exp(-sel.astype(np.float32)))).astype(np.float32), logits
+
+
 def forward(cfg, W, img_hwc_f32: np.ndarray, stages: bool = True) -> dict:
     """Mask_RCNN_FPN.build_forward inference branch (models.py:488-973) for one image
     (already resized by the caller, float32 HWC BGR as obj_detect_tracking.py:597-610)."""
@@ -299,6 +325,8 @@ def forward(cfg, W, img_hwc_f32: np.ndarray, stages: bool = True) -> dict:
         box_feat = np.zeros((0, feats[0].shape[0], 7, 7), np.float32)
     out.update(final_boxes=fboxes.astype(np.float32), final_labels=flabels,
                final_probs=fprobs.astype(np.float32), fpn_box_feat=box_feat)
+    if getattr(cfg, "add_mask", False):
+        out["final_masks"], out["mask_logits"] = final_masks(cfg, W, feats, fboxes.astype(np.float32), flabels)
     if stages:
         out.update(c2345=[c[0].numpy() for c in c2345], p23456=[p[0].numpy() for p in p23456],
                    rpn=rpn_out, level_proposals=lvl_props, proposal_boxes=pb, proposal_scores=ps,

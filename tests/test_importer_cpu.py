@@ -68,3 +68,17 @@ def test_model_load_npz_roundtrip(tmp_path):
     model.load_npz(path)                                                   # host side only: no device needed yet
     assert set(model._weights) == set(W)
     np.testing.assert_array_equal(model._weights["rpn/box/b"], W["rpn/box/b"])
+
+
+def test_mask_head_variables_join_the_manifest_with_add_mask():
+    cfg = make_config(resnet_num_block=(1, 1, 1, 1), add_mask=True)
+    sh = frcnn_weight_shapes(cfg)
+    assert sh["maskrcnn/fcn3/W"] == (3, 3, 256, 256) and sh["maskrcnn/deconv/W"] == (2, 2, 256, 256)
+    assert sh["maskrcnn/conv/W"] == (1, 1, 256, 14) and sh["maskrcnn/conv/b"] == (14,)
+    W = synth_weights(cfg, 9)
+    assert set(W) == set(sh) and all(tuple(W[k].shape) == tuple(sh[k]) for k in sh)
+    base = synth_weights(make_config(resnet_num_block=(1, 1, 1, 1)), 9)
+    assert "maskrcnn/conv/W" not in base
+    np.testing.assert_array_equal(base["fastrcnn/fc7/W"], W["fastrcnn/fc7/W"])      # detector weights independent of add_mask
+    with pytest.raises(ValueError):
+        check_weights(cfg, base)                                                      # mask graph, checkpoint without the head

@@ -114,3 +114,43 @@ def test_deepsort_restatement_reproduces_reference_tracker_run(golden_dir):
     np.testing.assert_array_equal(got[:, :2], expect[:, :2])           # frame, track id: bit-exact
     np.testing.assert_allclose(got[:, 2:], expect[:, 2:], rtol=0, atol=1e-9)
     assert len(set(expect[:, 1].tolist())) >= 5                         # the fixture really tracks several objects
+
+
+def test_mask_head_oracle_deconv_against_explicit_sum():
+    """maskrcnn_up4conv_head (models.py:1173-1199) in the oracle: the Conv2DTranspose 2x2 / stride 2 step (TF kernel layout
+    [kh, kw, out, in], nn.py:402-412) against the definition out[2y+dy, 2x+dx, o] = sum_i x[y, x, i] W[dy, dx, o, i] + b[o],
+    and the whole head's shapes / class selection."""
+    import numpy as np
+    from types import SimpleNamespace
+    from oracle import frcnn
+    rng = np.random.default_rng(12)
+    md, ncls, R = 16, 5, 3
+    W = {}
+    for k in range(4):
+        W["maskrcnn/fcn%d/W" % k] = (rng.standard_normal((3, 3, md, md)) * 0.1).astype(np.float32)
+        W["maskrcnn/fcn%d/b" % k] = (rng.standard_normal(md) * 0.1).astype(np.float32)
+    W["maskrcnn/deconv/W"] = (rng.standard_normal((2, 2, md, md)) * 0.2).astype(np.float32)
+    W["maskrcnn/deconv/b"] = (rng.standard_normal(md) * 0.1).astype(np.float32)
+    W["maskrcnn/conv/W"] = (rng.standard_normal((1, 1, md, ncls - 1)) * 0.3).astype(np.float32)
+    W["maskrcnn/conv/b"] = (rng.standard_normal(ncls - 1) * 0.1).astype(np.float32)
+    feat = rng.standard_normal((R, md, 14, 14)).astype(np.float32)
+    logits = frcnn.maskrcnn_head(feat, W, ncls)
+    assert logits.shape == (R, ncls - 1, 28, 28)
+    # independent evaluation in float64 numpy
+    x = feat.astype(np.float64)
+    for k in range(4):
+        xp = np.pad(x, ((0, 0), (0, 0), (1, 1), (1, 1)))
+        w = W["maskrcnn/fcn%d/W" % k].astype(np.float64)
+        y = np.zeros((R, md, 14, 14))
+        for dy in range(3):
+            for dx in range(3):
+                y += np.einsum("rihw,io->rohw", xp[:, :, dy:dy + 14, dx:dx + 14], w[dy, dx])
+        x = np.maximum(y + W["maskrcnn/fcn%d/b" % k].astype(np.float64)[None, :, None, None], 0)
+    up = np.zeros((R, md, 28, 28))
+    wd = W["maskrcnn/deconv/W"].astype(np.float64)
+    for dy in range(2):
+        for dx in range(2):
+            up[:, :, dy::2, dx::2] = np.einsum("rihw,oi->rohw", x, wd[dy, dx])
+    up = np.maximum(up + W["maskrcnn/deconv/b"].astype(np.float64)[None, :, None, None], 0)
+    ref = np.einsum("rihw,io->rohw", up, W["maskrcnn/conv/W"][0, 0].astype(np.float64)) + W["maskrcnn/conv/b"][None, :, None, None]
+    assert np.abs(logits - ref).max() < 1e-4

@@ -72,3 +72,57 @@ def test_resnet101_feature_extractor_drop_in(r101):
     assert np.abs(got - r101["feats"]).max() <= 3e-5 * np.abs(r101["feats"]).max()
     with pytest.raises(NotImplementedError):
         FeatureExtractor("resnet101", image_size=(256, 128), state_dict={})
+
+
+def test_mask_head_matches_oracle():
+    """--add_mask (models.py:934-961, 1173-1199): ROIAlign 14x14 of the final boxes, 4 x conv3x3, 2x2/2 transposed conv,
+    conv1x1, own-class sigmoid -- final_masks and all class logits against the oracle on the 192x256 frame."""
+    from object_detection_tracking_b200 import _lib
+    from object_detection_tracking_b200.config import make_config
+    from object_detection_tracking_b200.engine import Detector
+    from object_detection_tracking_b200.synth import synth_frame, synth_weights
+    from oracle import frcnn
+    H, W = 192, 256
+    cfg = make_config(resnet_num_block=(1, 1, 2, 1), max_size=W, short_edge_size=H, add_mask=True)
+    Wt = synth_weights(cfg, 1234)
+    frame = synth_frame(H, W, 5).astype(np.float32)
+    det = Detector(cfg, 1, H, W, device=0, precision="split", use_cuda_graph=False)
+    det.load_weights(Wt)
+    out = det.detect_host(frame[None])
+    ref = frcnn.forward(cfg, Wt, frame, stages=True)
+    r = int(out["valid"][0])
+    assert r == ref["final_boxes"].shape[0] > 0
+    # final_masks: [R,28,28] sigmoid of the own-class logits; order may differ between near-tied scores -> match by box
+    masks = det.get_masks()[0]
+    d = np.abs(out["boxes"][0, :r, None, :] - ref["final_boxes"][None, :, :]).max(-1) + \\
+        10.0 * (out["labels"][0, :r, None] != ref["final_labels"][None, :])
+    match = d.argmin(1)
+    assert d.min(1).max() < 2e-3
+    assert np.abs(masks[:r] - ref["final_masks"][match]).max() < 2e-4
+    assert (masks[r:] == 0).all()
+    # all class logits of the live rows
+    ml = det.get_stage("mask_logits")                                   # [B*R, 196*4, ld, 1]
+    ld = ml.shape[2]
+    ml = ml.reshape(-1, 14, 14, 2, 2, ld)[:r, ..., :cfg.num_class - 1]  # [r, y, x, dy, dx, c]
+    got = ml.transpose(0, 5, 1, 3, 2, 4).reshape(r, cfg.num_class - 1, 28, 28)
+    refl = ref["mask_logits"][match]
+    assert np.abs(got - refl).max() <= 1e-4 * max(1.0, float(np.abs(refl).max()))
+
+
+def test_mask_head_graph_replay_and_backend_fetch():
+    from object_detection_tracking_b200.backend import Session, get_model
+    from object_detection_tracking_b200.config import make_config
+    from object_detection_tracking_b200.synth import synth_frame, synth_weights
+    H, W = 192, 256
+    cfg = make_config(resnet_num_block=(1, 1, 2, 1), max_size=W, short_edge_size=H, add_mask=True)
+    model = get_model(cfg, gpuid=0)
+    model.set_weights(synth_weights(cfg, 1234))
+    sess = Session()
+    frame = synth_frame(H, W, 5).astype(np.float32)
+    fetches = [model.final_boxes, model.final_labels, model.final_probs, model.final_masks]
+    a = sess.run(fetches, feed_dict=model.get_feed_dict_forward(frame))
+    b = sess.run(fetches, feed_dict=model.get_feed_dict_forward(frame))           # CUDA-graph replay
+    assert a[3].shape == (len(a[0]), 28, 28) and a[3].dtype == np.float32 and len(a[0]) > 0
+    assert ((a[3] > 0) & (a[3] < 1)).all()
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)
