@@ -94,8 +94,8 @@ def test_mask_head_matches_oracle():
     assert r == ref["final_boxes"].shape[0] > 0
     # final_masks: [R,28,28] sigmoid of the own-class logits; order may differ between near-tied scores -> match by box
     masks = det.get_masks()[0]
-    d = np.abs(out["boxes"][0, :r, None, :] - ref["final_boxes"][None, :, :]).max(-1) + \\
-        10.0 * (out["labels"][0, :r, None] != ref["final_labels"][None, :])
+    d = (np.abs(out["boxes"][0, :r, None, :] - ref["final_boxes"][None, :, :]).max(-1)
+         + 10.0 * (out["labels"][0, :r, None] != ref["final_labels"][None, :]))
     match = d.argmin(1)
     assert d.min(1).max() < 2e-3
     assert np.abs(masks[:r] - ref["final_masks"][match]).max() < 2e-4
