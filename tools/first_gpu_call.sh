@@ -16,3 +16,5 @@ echo "== bench =="
 timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_first.json 2> gpurun_out/bench_first.err; echo "bench rc=$?"; tail -c 1500 gpurun_out/bench_first.json
 echo "== aux timing (JDE tracker on the GPU cost, pair cost, resize) =="
 timeout 200 python tools/gpu_widen_timing.py > gpurun_out/widen_timing.jsonl 2> gpurun_out/widen_timing.err; echo "timing rc=$?"; cat gpurun_out/widen_timing.jsonl
+echo "== cuDNN library baseline for the main conv shapes =="
+timeout 200 python tools/cudnn_layer_baseline.py 8 > gpurun_out/cudnn_layers_b8.jsonl 2> gpurun_out/cudnn_layers.err; echo "cudnn rc=$?"; tail -5 gpurun_out/cudnn_layers_b8.jsonl
