@@ -121,7 +121,16 @@ class Tracker(object):
         self._dim = None
         self._user_cost = cost_fn
         self._cb = None
-        self.tracks = []
+        self._tracks = []
+        self._stale = False
+
+    @property
+    def tracks(self):
+        """The live tracks (deep_sort/tracker.py:38), materialised from the native state on first access after a
+        predict() / update(): the drivers read them once per frame, after update() (obj_detect_tracking.py:670)."""
+        if self._stale:
+            self._refresh()
+        return self._tracks
 
     def _create(self, dim):
         h = ctypes.c_void_p()
@@ -162,7 +171,7 @@ class Tracker(object):
     def predict(self):
         if self._h is not None:
             _lib.check(self._lib.b2_tracker_predict(self._h), "b2_tracker_predict")
-            self._refresh()
+            self._stale = True
 
     def update(self, detections):
         n = len(detections)
@@ -175,7 +184,7 @@ class Tracker(object):
         feat = np.ascontiguousarray([d.feature for d in detections], dtype=np.float32).reshape(n, self._dim)
         _lib.check(self._lib.b2_tracker_update(self._h, _lib.ptr(tlwh), _lib.ptr(conf), _lib.ptr(feat), n),
                    "b2_tracker_update")
-        self._refresh()
+        self._stale = True
 
     def _refresh(self):
         n = self._lib.b2_tracker_num_tracks(self._h)
@@ -186,8 +195,9 @@ class Tracker(object):
                                               _lib.ptr(tsu), _lib.ptr(mean), _lib.ptr(cov))
         if got != n:
             _lib.check(-1, "b2_tracker_get_tracks")
-        self.tracks = [Track(mean[k], cov[k], int(ids[k]), int(hits[k]), int(age[k]), int(tsu[k]), int(st[k]))
-                       for k in range(n)]
+        self._tracks = [Track(mean[k], cov[k], int(ids[k]), int(hits[k]), int(age[k]), int(tsu[k]), int(st[k]))
+                        for k in range(n)]
+        self._stale = False
 
 
 def linear_sum_assignment(cost_matrix):

@@ -59,3 +59,71 @@ def test_camera_pairs_cover_the_bubble_compare():
     dealt = [camera_pairs(8, r, 8) for r in range(8)]
     assert sorted(p for d in dealt for p in d) == sorted(allp)
     assert max(len(d) for d in dealt) - min(len(d) for d in dealt) <= 1
+
+
+def _c5_worker(rank, world, port, q, golden_path):
+    """One rank = one camera: contribute the camera's gallery, all-gather, then score this rank's share of the camera pairs."""
+    import os as _os
+    import torch
+    import torch.distributed as dist
+    from object_detection_tracking_b200 import reid
+    _os.environ["MASTER_ADDR"] = "127.0.0.1"
+    _os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = np.load(golden_path)
+    cams = load_cameras(g)
+    mine = cams[rank]
+    ids = sorted(mine)
+    local = torch.from_numpy(np.concatenate([mine[t][1] for t in ids], 0))
+    allf, counts = reid.allgather_gallery(local)
+    # the gallery of the OTHER camera as received over the wire replaces the local copy of it
+    other = 1 - rank
+    o_ids = sorted(cams[other])
+    off = sum(counts[:other])
+    recv = allf[off:off + counts[other]].numpy()
+    pos = 0
+    rebuilt = {}
+    for t in o_ids:
+        k = len(cams[other][t][1])
+        rebuilt[t] = (cams[other][t][0], recv[pos:pos + k])
+        pos += k
+    pair_cams = [mine, rebuilt] if rank == 0 else [rebuilt, mine]
+    res = []
+    for (i, j) in reid.camera_pairs(world, rank, world):
+        res.append(((i, j), reid.match_tracks(pair_cams[i], pair_cams[j], frame_offset=4, tol=50,
+                                              ignore_pairs=[list(g["ignore0"]), list(g["ignore1"])],
+                                              feature_dist_fn=feature_dist_checker)))
+    q.put((rank, counts, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_c5_exchange_then_pair_matching_world2_gloo(golden_dir):
+    """Config 5 on two ranks (gloo on the CPU; NCCL on the GPUs): all-gather of the per-camera galleries, the camera pairs
+    dealt to the ranks, each rank's matches equal to the reference's assignment."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    path = os.path.join(golden_dir, "reid_pairs.npz")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_c5_worker, args=(r, 2, port, q, path)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted((q.get(timeout=180) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = np.load(path)
+    c1, c2 = load_cameras(g)
+    ids1, ids2 = sorted(c1), sorted(c2)
+    ref = [(ids1[i], ids2[int(j)]) for i, j in enumerate(g["x"]) if j >= 0]
+    n1 = sum(len(c1[t][1]) for t in c1)
+    n2 = sum(len(c2[t][1]) for t in c2)
+    assert out[0][1] == out[1][1] == [n1, n2]
+    pairs = [r for rank_out in out for r in rank_out[2]]
+    assert [p[0] for p in pairs] == [(0, 1)]                 # one camera pair on two cameras, owned by rank 0
+    assert pairs[0][1] == ref
