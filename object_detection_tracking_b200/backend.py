@@ -157,6 +157,11 @@ class Mask_RCNN_FPN:
                 elif f is self.fpn_box_feat:
                     R = det.R
                     res.append(np.concatenate([out["feat"][b * R:b * R + int(valid[b])] for b in range(B)], axis=0))
+                elif f is self.final_masks:                                    # models.py:2379-2407: [sum R, 28, 28]
+                    if not getattr(self.config, "add_mask", False):
+                        raise KeyError("final_masks needs config.add_mask (models.py:2379)")
+                    m = det.get_masks()
+                    res.append(np.concatenate([m[b, :int(valid[b])] for b in range(B)], axis=0))
                 else:
                     raise KeyError("unknown fetch %r" % (f,))
         return res
