@@ -54,8 +54,12 @@ def main():
                     elif k in n:
                         print("%-18s new      %s (%d instructions)" % (f, k[:100], len(n[k])))
                     else:
-                        changed += 1
-                        print("%-18s REMOVED  %s" % (f, k[:100]))
+                        twins = [j for j in n if j not in o and n[j] == o[k]]
+                        if twins:      # e.g. a kernel that became a template instantiation
+                            print("%-18s renamed  %s -> %s (instruction-identical)" % (f, k[:100], twins[0][:100]))
+                        else:
+                            changed += 1
+                            print("%-18s REMOVED  %s" % (f, k[:100]))
                 print("%-18s %d kernels in %s, %d in %s" % (f, len(o), base, len(n), head))
         print("kernels altered or removed: %d" % changed)
     return 1 if changed else 0
