@@ -73,6 +73,8 @@ int b2_load_weights(b2_ctx* ctx, const char* const* names, const float* const* d
 /* One pass of the hot path over `batch` frames resident on the device.  All pointers are device
  * pointers; outputs: boxes [B,100,4] x1y1x2y2, probs [B,100], labels [B,100] (1-based), valid [B],
  * box_feat [B*100,C,7,7] fp32 (feat_mode 0) or [B*100,C] mean-pooled (feat_mode 1); any may be NULL.
+ * feat_mode 2 / 3 are the TMOT driver's other aggregations (obj_detect_tracking_multi_queuer_tmot.py:511-525): 2 = max over
+ * the 7x7 bins [B*100,C], 3 = "spatial" mean over the channels [B*100,49].
  * Asynchronous on the context stream unless `sync` != 0. */
 int b2_detect(b2_ctx* ctx, const void* frames_dev, float* boxes, float* probs, int32_t* labels, int32_t* valid,
               float* box_feat, int feat_mode, int sync);

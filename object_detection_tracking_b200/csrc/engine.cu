@@ -54,6 +54,26 @@ __global__ void pool_feat_kernel(const float* __restrict__ feat, int rows, int C
   out[idx] = s / 49.f;
 }
 
+// The TMOT driver's other embedding aggregations of fpn_box_feat (obj_detect_tracking_multi_queuer_tmot.py:511-525):
+// mode 2 "max" = amax over the 7x7 bins -> [rows][C]; mode 3 "spatial" = mean over the channels -> [rows][49].
+__global__ void agg_feat_kernel(const float* __restrict__ feat, int rows, int C, int mode, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (mode == 2) {
+    if (idx >= rows * C) return;
+    const float* f = feat + static_cast<size_t>(idx) * 49;
+    float m = f[0];
+    for (int i = 1; i < 49; ++i) m = fmaxf(m, f[i]);
+    out[idx] = m;
+  } else {
+    if (idx >= rows * 49) return;
+    const int r = idx / 49, bin = idx - r * 49;
+    const float* f = feat + static_cast<size_t>(r) * C * 49 + bin;
+    float s = 0.f;
+    for (int ch = 0; ch < C; ++ch) s += f[static_cast<size_t>(ch) * 49];
+    out[idx] = s / static_cast<float>(C);
+  }
+}
+
 // Mask head output (models.py:950-958): per final detection the logits of its own class, sigmoid, and the un-shuffle of
 // the 2x2 transposed-conv taps.  logits rows are ((roi * 196 + y * 14 + x) * 4 + dy * 2 + dx); out [B*R][28][28].
 __global__ void mask_select_kernel(const float* __restrict__ logits, int ld, const int* __restrict__ labels,
@@ -140,6 +160,7 @@ struct b2_ctx {
   float* head_logits = nullptr;
   float* box_feat = nullptr;
   float* box_feat_pooled = nullptr;
+  float* box_feat_agg = nullptr;   // feat_mode 2 / 3 scratch ([B*R][C] or [B*R][49]), allocated on first use
   // mask head (cfg.add_mask): ROIAlign 14 of the final boxes -> 4 x conv3x3 -> deconv -> conv1x1 -> sigmoid of own class
   Planes mask_a, mask_b, mask_up;
   float* mask_logits = nullptr;
@@ -1051,10 +1072,21 @@ static int copy_outputs(b2_ctx* c, float* boxes, float* probs, int32_t* labels, 
   if (labels) B2_CUDA(cudaMemcpyAsync(labels, c->post.final_labels, sizeof(int32_t) * B * R, kind, st));
   if (valid) B2_CUDA(cudaMemcpyAsync(valid, c->post.final_count, sizeof(int32_t) * B, kind, st));
   if (box_feat) {
-    if (feat_mode == 1)
+    B2_CHECK(feat_mode >= 0 && feat_mode <= 3, "feat_mode must be 0 (full), 1 (mean), 2 (max) or 3 (spatial)");
+    if (feat_mode == 1) {
       B2_CUDA(cudaMemcpyAsync(box_feat, c->box_feat_pooled, sizeof(float) * B * R * C, kind, st));
-    else
+    } else if (feat_mode >= 2) {
+      const int rows = B * R, n = feat_mode == 2 ? rows * C : rows * 49;
+      if (!c->box_feat_agg) {
+        c->box_feat_agg = c->alloc<float>(static_cast<size_t>(rows) * (C > 49 ? C : 49));
+        B2_CHECK(c->box_feat_agg != nullptr, "out of device memory (feature aggregation scratch)");
+      }
+      agg_feat_kernel<<<(n + 255) / 256, 256, 0, st>>>(c->box_feat, rows, C, feat_mode, c->box_feat_agg);
+      B2_CUDA(cudaGetLastError());
+      B2_CUDA(cudaMemcpyAsync(box_feat, c->box_feat_agg, sizeof(float) * n, kind, st));
+    } else {
       B2_CUDA(cudaMemcpyAsync(box_feat, c->box_feat, sizeof(float) * B * R * C * 49, kind, st));
+    }
   }
   return 0;
 }
@@ -1181,7 +1213,8 @@ int b2_submit_host(b2_ctx* c, const void* frames_host, float* boxes, float* prob
   uint8_t* d_labels = d_probs + nb_probs;
   uint8_t* d_valid = d_labels + nb_labels;
   uint8_t* d_feat = d_valid + nb_valid;
-  const size_t feat_bytes = feat_mode == 1 ? sizeof(float) * B * R * C : nb_feat;
+  const size_t feat_bytes = feat_mode == 1 || feat_mode == 2 ? sizeof(float) * B * R * C
+                            : feat_mode == 3 ? sizeof(float) * B * R * 49 : nb_feat;
   if (copy_outputs(c, boxes ? reinterpret_cast<float*>(d_boxes) : nullptr, probs ? reinterpret_cast<float*>(d_probs) : nullptr,
                    labels ? reinterpret_cast<int32_t*>(d_labels) : nullptr, valid ? reinterpret_cast<int32_t*>(d_valid) : nullptr,
                    box_feat ? reinterpret_cast<float*>(d_feat) : nullptr, feat_mode, cudaMemcpyDeviceToDevice)) return -1;

@@ -60,7 +60,7 @@ class Detector:
         B, R, C = self.batch, self.R, self.C
         shapes = dict(boxes=((B, R, 4), np.float32), probs=((B, R), np.float32), labels=((B, R), np.int32),
                       valid=((B,), np.int32),
-                      feat=(((B * R, C) if feat_mode == 1 else (B * R, C, 7, 7)), np.float32))
+                      feat=({0: (B * R, C, 7, 7), 1: (B * R, C), 2: (B * R, C), 3: (B * R, 49)}[feat_mode], np.float32))
         if pinned:
             import torch
             tmap = {np.float32: torch.float32, np.int32: torch.int32}

@@ -128,3 +128,27 @@ def test_detect_with_device_resize_equals_host_resize_path():
     assert int(a["valid"].sum()) > 0
     for k in ("valid", "labels", "boxes", "probs"):
         np.testing.assert_array_equal(a[k], b[k])
+
+
+def test_feature_aggregation_modes_match_host_aggregation():
+    """feat_mode 1 / 2 / 3 (mean, max, "spatial": obj_detect_tracking_multi_queuer_tmot.py:511-525) computed on the device
+    equal the same aggregation of the full [R,256,7,7] features done on the host."""
+    from object_detection_tracking_b200.config import make_config
+    from object_detection_tracking_b200.engine import Detector
+    from object_detection_tracking_b200.synth import synth_frame, synth_weights
+    H, W = 192, 256
+    cfg = make_config(resnet_num_block=(1, 1, 2, 1), max_size=W, short_edge_size=H)
+    det = Detector(cfg, 1, H, W, device=0, precision="split", use_cuda_graph=True)
+    det.load_weights(synth_weights(cfg, 1234))
+    frame = synth_frame(H, W, 5).astype(np.float32)[None]
+    full = det.detect_host(frame, feat_mode=0)
+    r = int(full["valid"][0])
+    assert r > 0
+    f = full["feat"][:r]
+    mean = det.detect_host(frame, feat_mode=1)["feat"][:r]
+    mx = det.detect_host(frame, feat_mode=2)["feat"][:r]
+    sp = det.detect_host(frame, feat_mode=3)["feat"][:r]
+    scale = float(np.abs(f).max())
+    assert np.abs(mean - f.mean(axis=(2, 3))).max() <= 1e-6 * scale
+    np.testing.assert_array_equal(mx, f.max(axis=(2, 3)))
+    assert sp.shape == (r, 49) and np.abs(sp - f.mean(axis=1).reshape(r, 49)).max() <= 1e-5 * scale
