@@ -1078,7 +1078,7 @@ static int copy_outputs(b2_ctx* c, float* boxes, float* probs, int32_t* labels, 
     } else if (feat_mode >= 2) {
       const int rows = B * R, n = feat_mode == 2 ? rows * C : rows * 49;
       if (!c->box_feat_agg) {
-        c->box_feat_agg = c->alloc<float>(static_cast<size_t>(rows) * (C > 49 ? C : 49));
+        c->box_feat_agg = c->alloc<float>(static_cast<size_t>(rows) * (C > 49 ? C : 49), /*zero=*/false);   // fully overwritten
         B2_CHECK(c->box_feat_agg != nullptr, "out of device memory (feature aggregation scratch)");
       }
       agg_feat_kernel<<<(n + 255) / 256, 256, 0, st>>>(c->box_feat, rows, C, feat_mode, c->box_feat_agg);
