@@ -116,3 +116,26 @@ def test_jde_needs_gpu_without_cost_fn():
     with pytest.raises(RuntimeError):
         trk.update(dets)                  # third: activated track -> embedding distance -> needs the GPU
     trk.close()
+
+
+def test_jde_tracker_other_parameters(golden_dir):
+    """Second reference run: short lost window (7.5 frames), tighter gates, alpha 0.6, confidence gate 0.6."""
+    from object_detection_tracking_b200.tmot import JDETracker, _IdGroup
+    g = np.load(os.path.join(golden_dir, "tmot_jde_b.npz"))
+    trk = JDETracker(0.6, track_max_second_lost=1.0, emb_max_dist=0.5, iou_max_dist1=0.6, iou_max_dist2=0.7,
+                     emb_smooth_alpha=0.6, frame_gap=4., frame_rate=30., cost_fn=cdist_cost, id_group=_IdGroup())
+    out_rows, list_rows = [], []
+    for f in range(60):
+        fr = g["f%d" % f]
+        for t in trk.update([(r[:4].astype(np.float64), float(r[4]), r[5:].copy()) for r in fr]):
+            out_rows.append([f, t.track_id] + t.tlwh.tolist() + [t.score, t.tracklet_len, t.start_frame])
+        for which in (1, 2):
+            for t in trk.get_tracks(which):
+                list_rows.append([f, which, t.track_id, t.state, int(t.is_activated), t.frame_id])
+    got = np.asarray(out_rows, dtype=np.float64)
+    assert got.shape == g["out"].shape
+    np.testing.assert_array_equal(got[:, :2], g["out"][:, :2])
+    np.testing.assert_array_equal(got[:, 6:], g["out"][:, 6:])
+    assert np.abs(got[:, 2:6] - g["out"][:, 2:6]).max() < 1e-8
+    np.testing.assert_array_equal(np.asarray(list_rows, dtype=np.int64), g["lists"])
+    trk.close()
