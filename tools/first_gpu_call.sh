@@ -18,3 +18,5 @@ echo "== aux timing (JDE tracker on the GPU cost, pair cost, resize) =="
 timeout 200 python tools/gpu_widen_timing.py > gpurun_out/widen_timing.jsonl 2> gpurun_out/widen_timing.err; echo "timing rc=$?"; cat gpurun_out/widen_timing.jsonl
 echo "== cuDNN library baseline for the main conv shapes =="
 timeout 200 python tools/cudnn_layer_baseline.py 8 > gpurun_out/cudnn_layers_b8.jsonl 2> gpurun_out/cudnn_layers.err; echo "cudnn rc=$?"; tail -5 gpurun_out/cudnn_layers_b8.jsonl
+echo "== two contexts in flight (experiment) =="
+timeout 300 python tools/ab_two_contexts.py 40 > gpurun_out/ab_two_contexts.jsonl 2> gpurun_out/ab_two_contexts.err; echo "rc=$?"; cat gpurun_out/ab_two_contexts.jsonl
