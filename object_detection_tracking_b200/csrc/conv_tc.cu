@@ -795,6 +795,14 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   // stage; 64-column tiles leave TMEM room for a ring of six chunk accumulators, so the MMA issuer can run a whole tile
   // ahead of the epilogue instead of stalling after two chunks (experiment hook until measured)
   if (split && getenv("B2_SHORTK_BN64") != nullptr && p.num_kb <= 4 && p.block_n == 128 && w.Cout_pad % 64 == 0) p.block_n = 64;
+  // experiment hook (round 2): layers whose 128-column tiling ends in a nearly empty last wave (res4 at batch 8: 460
+  // tiles on 148 SMs = 3.1 waves, the 16 tiles of the 4th round cost a whole tile time) switch to 64-column tiles (920
+  // tiles = 6.2 waves of half the work: 3.5 instead of 4 tile times), at the price of twice the A-operand L2 traffic
+  if (split && getenv("B2_BN64_TAIL") != nullptr && p.block_n == 128 && w.Cout_pad % 64 == 0) {
+    const int tiles128 = ((d.B * Ho * Wo + kBlockM - 1) / kBlockM) * (w.Cout_pad / 128);
+    const int full = tiles128 / num_sms, rem = tiles128 % num_sms;
+    if (full >= 1 && full < 8 && rem > 0 && rem * 3 < num_sms) p.block_n = 64;
+  }
   p.num_n_blocks = w.Cout_pad / p.block_n;
   B2_CHECK(p.num_n_blocks * p.block_n == w.Cout_pad, "conv_tc: Cout_pad not divisible by block_n");
   const int num_m_blocks = (p.M + kBlockM - 1) / kBlockM;
