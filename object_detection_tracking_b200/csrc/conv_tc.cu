@@ -318,6 +318,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+#ifdef B2_PDL
+  // Build variant (tools/build_variant.sh pdl -DB2_PDL=1), round-2 experiment: programmatic dependent launch.  The next
+  // conv of the stream may be scheduled onto SMs as they free up and run its prologue (barrier init, TMEM allocation,
+  // tensor-map prefetch -- everything above) while this grid is still in its last wave; it then waits here, before its
+  // first global-memory access, until the preceding grid has completed and flushed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
   const uint32_t tmem_base = *tmem_holder;
   if (tmem_base != 0) __trap();   // the MMA issuer addresses TMEM from column 0 / lane 0 (whole-TMEM allocation)
 
@@ -961,7 +969,33 @@ ConvPlan* conv_tc_plan_create(const ConvDesc& d, const ConvWeights& w, const Con
 
 void conv_tc_plan_destroy(ConvPlan* p) { delete p; }
 
+#ifdef B2_PDL
+template <typename K>
+static cudaError_t launch_pdl(K kernel, const ConvPlan* pl, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pl->grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = pl->smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, pl->tmA_hi, pl->tmA_lo, pl->tmB_hi, pl->tmB_lo, pl->tmO_hi, pl->tmO_lo, pl->tmR_hi,
+                            pl->tmR_lo, pl->p);
+}
+#endif
+
 int conv_tc_launch(const ConvPlan* pl, cudaStream_t stream) {
+#ifdef B2_PDL
+  if (getenv("B2_PDL_OFF") == nullptr) {
+    if (pl->split && pl->acc) B2_CUDA(launch_pdl(conv_tc_kernel<true, true>, pl, stream));
+    else if (pl->split) B2_CUDA(launch_pdl(conv_tc_kernel<true, false>, pl, stream));
+    else B2_CUDA(launch_pdl(conv_tc_kernel<false, false>, pl, stream));
+    return 0;
+  }
+#endif
   if (pl->split && pl->acc)
     conv_tc_kernel<true, true><<<pl->grid, kThreads, pl->smem_bytes, stream>>>(
         pl->tmA_hi, pl->tmA_lo, pl->tmB_hi, pl->tmB_lo, pl->tmO_hi, pl->tmO_lo, pl->tmR_hi, pl->tmR_lo, pl->p);
