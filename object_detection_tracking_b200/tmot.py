@@ -5,6 +5,7 @@ float64 host code, as in the reference.  No CPU fallback for the embedding dista
 from __future__ import annotations
 
 import ctypes
+import weakref
 
 import numpy as np
 
@@ -45,7 +46,11 @@ class _IdGroup(object):
     zeroes it (basetrack.py:13,34-37; multitracker.py:215).  Trackers created with the same group share a native counter."""
 
     def __init__(self):
-        self.anchor = None
+        self.members = []          # weak references to the trackers of the group that own a native handle
+
+    def live_handle(self):
+        self.members = [w for w in self.members if w() is not None and w()._h is not None]
+        return self.members[0]()._h if self.members else None
 
 
 _DEFAULT_GROUP = _IdGroup()
@@ -72,12 +77,10 @@ class JDETracker(object):
 
     def _create(self, dim):
         h = ctypes.c_void_p()
-        anchor = self._group.anchor._h if (self._group.anchor is not None and self._group.anchor._h is not None) else None
-        _lib.check(self._lib.b2_jde_create(ctypes.byref(h), int(self.device), *self._args, int(dim), self._precision, anchor),
-                   "b2_jde_create")
+        _lib.check(self._lib.b2_jde_create(ctypes.byref(h), int(self.device), *self._args, int(dim), self._precision,
+                                           self._group.live_handle()), "b2_jde_create")
         self._h, self._dim = h, dim
-        if self._group.anchor is None or self._group.anchor._h is None:
-            self._group.anchor = self
+        self._group.members.append(weakref.ref(self))
         if self._user_cost is not None:
             fn = self._user_cost
 

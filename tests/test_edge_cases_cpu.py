@@ -66,3 +66,21 @@ def test_jde_frames_without_detections_before_the_first_one():
     out = trk.update(det)
     assert len(out) == 1 and out[0].start_frame == 3 and out[0].frame_id == 4 and out[0].track_id == 1
     trk.close()
+
+
+def test_jde_id_counter_survives_the_first_tracker_of_a_group():
+    """BaseTrack._count outlives any single JDETracker: a tracker that joins after the first one was closed still draws
+    from the same counter as the remaining members."""
+    grp = tmot._IdGroup()
+    cost = lambda a, b: np.zeros((len(a), len(b)))
+    det = lambda x: [(np.array([x, 10., 40., 80.]), 0.9, np.ones(8, np.float32))]
+    a = tmot.JDETracker(0.5, id_group=grp, cost_fn=cost)
+    b = tmot.JDETracker(0.5, id_group=grp, cost_fn=cost)
+    a.update(det(10.))            # id 1
+    b.update(det(500.))           # id 2
+    a.close()
+    c = tmot.JDETracker(0.5, id_group=grp, cost_fn=cost)
+    c.update(det(900.))           # id 3: joined through b
+    assert [t.track_id for t in c.get_tracks(1)] == [3] and [t.track_id for t in b.get_tracks(1)] == [2]
+    b.close()
+    c.close()
