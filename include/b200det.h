@@ -101,6 +101,11 @@ int b2_submit_host(b2_ctx* ctx, const void* frames_host, float* boxes, float* pr
                    float* box_feat, int feat_mode, int slot);
 int b2_wait(b2_ctx* ctx, int slot);
 
+/* RCNN_FPN_givenbox (models.py:1816-1967, get_model_feat :121-131): final_box_features of GIVEN boxes -- backbone + FPN,
+ * ROIAlign 7x7 on the uncropped p2..p5, mean over the bins.  frame_host: one frame of the configured dtype / size (batch 1
+ * context), boxes_host [n,4] x1 y1 x2 y2 in frame pixels, feat_host [n, fpn_num_channel]. */
+int b2_box_features(b2_ctx* ctx, const void* frame_host, const float* boxes_host, int n, float* feat_host);
+
 /* final_masks of the last pass (needs cfg.add_mask): [batch][result_per_im][28][28] float32 (models.py:958-961; the
  * drivers paste them into the frame with fill_full_mask, obj_detect_tracking.py:719); rows >= valid[b] are zero. */
 int b2_get_masks(b2_ctx* ctx, float* masks_host, int64_t capacity_bytes);

@@ -167,6 +167,35 @@ class Mask_RCNN_FPN:
         return res
 
 
+class RCNN_FPN_givenbox(Mask_RCNN_FPN):
+    """Feature extractor for given boxes (reference: models.py:1816-1967): `model.image`, `model.boxes`,
+    `model.final_box_features`, `model.get_feed_dict(im, boxes)`; run with Session.run([model.final_box_features], fd)."""
+
+    def __init__(self, config, gpuid=0, precision="split", input_dtype="float32"):
+        super().__init__(config, gpuid, precision, input_dtype)
+        self.boxes = TensorHandle(self, "boxes:0")
+        self.final_box_features = TensorHandle(self, "final_box_features:0")
+
+    def get_feed_dict(self, im, boxes, is_train=False):          # models.py:1953-1967
+        return {self.image: im, self.boxes: boxes}
+
+    def _run(self, fetches, feed_dict):
+        img = np.asarray(feed_dict[self.image])
+        det = self._detector(1, img.shape[0], img.shape[1])
+        feats = det.box_features(img, feed_dict[self.boxes])
+        res = []
+        for f in fetches:
+            if f is not self.final_box_features:
+                raise KeyError("the given-box model has one output: final_box_features")
+            res.append(feats.copy())
+        return res
+
+
+def get_model_feat(config, gpuid=0, task=0, controller="/cpu:0", **kw):
+    """models.get_model_feat (models.py:121-131)."""
+    return RCNN_FPN_givenbox(config, gpuid=gpuid, **kw)
+
+
 class Mask_RCNN_FPN_multi(Mask_RCNN_FPN):
     """Fixed-batch model object (reference: models.py:1969-3487): post-processing follows the batch graph
     (combined_non_max_suppression semantics, `multi_semantics` in the C ABI)."""

@@ -160,6 +160,10 @@ struct b2_ctx {
   float* head_logits = nullptr;
   float* box_feat = nullptr;
   float* box_feat_pooled = nullptr;
+  float* given_boxes = nullptr;    // b2_box_features: [R][4] boxes + count of the current chunk
+  int* given_count = nullptr;
+  float* given_feat = nullptr;     // [R][C][7][7] and pooled [R][C]
+  float* given_pooled = nullptr;
   float* box_feat_agg = nullptr;   // feat_mode 2 / 3 scratch ([B*R][C] or [B*R][49]), allocated on first use
   // mask head (cfg.add_mask): ROIAlign 14 of the final boxes -> 4 x conv3x3 -> deconv -> conv1x1 -> sigmoid of own class
   Planes mask_a, mask_b, mask_up;
@@ -1237,6 +1241,47 @@ int b2_wait(b2_ctx* c, int slot) {
   B2_CHECK(c->slot_busy[slot], "b2_wait: nothing was submitted on this slot");
   B2_CUDA(cudaEventSynchronize(c->out_done[slot]));
   c->slot_busy[slot] = false;
+  return 0;
+}
+
+// RCNN_FPN_givenbox (models.py:1816-1967; get_model_feat :121-131): features of GIVEN boxes on one frame -- backbone + FPN,
+// ROIAlign 7x7 of the boxes on the uncropped p2..p5 (that graph skips slice_feature_and_anchors) and the mean over the
+// 7x7 bins (final_box_features [n, 256]).  The context must have batch 1; boxes are processed result_per_im at a time.
+int b2_box_features(b2_ctx* c, const void* frame_host, const float* boxes_host, int n, float* feat_host) {
+  B2_CHECK(c && frame_host && (n == 0 || (boxes_host && feat_host)), "b2_box_features: null argument");
+  B2_CHECK(c->cfg.batch == 1, "b2_box_features: the context must be created with batch 1 (the given-box graph takes one image)");
+  B2_CHECK(n >= 0, "b2_box_features: negative box count");
+  B2_CUDA(cudaSetDevice(c->device));
+  B2_CHECK(c->weights_loaded, "b2_box_features: weights not loaded");
+  const int R = c->cfg.result_per_im, C = c->cfg.fpn_num_channel;
+  if (!c->given_boxes) {
+    c->given_boxes = c->alloc<float>(static_cast<size_t>(R) * 4);
+    c->given_count = c->alloc<int>(1);
+    c->given_feat = c->alloc<float>(static_cast<size_t>(R) * C * 49);
+    c->given_pooled = c->alloc<float>(static_cast<size_t>(R) * C);
+    B2_CHECK(c->given_boxes && c->given_count && c->given_feat && c->given_pooled, "out of device memory (given-box buffers)");
+    B2_CUDA(cudaDeviceSynchronize());   // the zero fills of alloc() run on the legacy stream
+  }
+  B2_CUDA(cudaMemcpyAsync(c->img, frame_host, c->img_bytes, cudaMemcpyHostToDevice, c->stream));
+  if (enqueue(c, B2_PHASE_BACKBONE | B2_PHASE_FPN, false)) return -1;
+  RoiAlignParams rg = c->roi2;
+  for (int i = 0; i < 4; ++i) { rg.H[i] = c->pfh[i]; rg.W[i] = c->pfw[i]; }   // uncropped levels
+  rg.B = 1; rg.rois_per_image = R;
+  rg.boxes = c->given_boxes; rg.count = c->given_count;
+  rg.out_hi = nullptr; rg.out_lo = nullptr; rg.out_nchw = c->given_feat; rg.out_res = 7;
+  for (int off = 0; off < n; off += R) {
+    const int m = n - off < R ? n - off : R;
+    B2_CUDA(cudaMemcpyAsync(c->given_boxes, boxes_host + static_cast<size_t>(off) * 4, sizeof(float) * m * 4,
+                            cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(c->given_count, &m, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));   // `m` lives on this stack frame
+    if (roialign_launch(rg, c->stream)) return -1;
+    pool_feat_kernel<<<(m * C + 255) / 256, 256, 0, c->stream>>>(c->given_feat, m, C, c->given_pooled);
+    B2_CUDA(cudaGetLastError());
+    B2_CUDA(cudaMemcpyAsync(feat_host + static_cast<size_t>(off) * C, c->given_pooled, sizeof(float) * m * C,
+                            cudaMemcpyDeviceToHost, c->stream));
+  }
+  B2_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

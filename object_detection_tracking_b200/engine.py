@@ -95,6 +95,17 @@ class Detector:
                    "b2_detect_host_resize")
         return out
 
+    def box_features(self, frame, boxes) -> np.ndarray:
+        """RCNN_FPN_givenbox (models.py:1816-1967): [n, 256] mean-pooled ROI features of the given boxes on one frame
+        (batch-1 context)."""
+        frame = np.ascontiguousarray(frame, dtype=self._np_dtype())
+        assert frame.shape == (self.height, self.width, 3), frame.shape
+        boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 4)
+        out = np.empty((len(boxes), self.C), dtype=np.float32)
+        _lib.check(self.lib.b2_box_features(self._ctx, _lib.ptr(frame), _lib.ptr(boxes), len(boxes), _lib.ptr(out)),
+                   "b2_box_features")
+        return out
+
     def get_masks(self) -> np.ndarray:
         """final_masks of the last pass (config.add_mask): [B, result_per_im, 28, 28] float32 (models.py:958-961)."""
         out = np.empty((self.batch, int(self.cfg.result_per_im), 28, 28), dtype=np.float32)

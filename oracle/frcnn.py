@@ -335,6 +335,20 @@ def forward(cfg, W, img_hwc_f32: np.ndarray, stages: bool = True) -> dict:
     return out
 
 
+def forward_givenbox(cfg, W, img_hwc_f32: np.ndarray, boxes: np.ndarray) -> np.ndarray:
+    """RCNN_FPN_givenbox.build_forward (models.py:1900-1950): backbone + FPN, multilevel_roi_align of the given boxes on
+    the UNCROPPED p2..p5 (no slice_feature_and_anchors in that graph), mean over the 7x7 bins -> [n, 256]."""
+    x = preprocess(img_hwc_f32)
+    with torch.no_grad():
+        p23456 = fpn(backbone(x, W, cfg), W)
+    feats = [p[0].numpy() for p in p23456[:4]]
+    boxes = np.asarray(boxes, dtype=np.float32).reshape(-1, 4)
+    if not len(boxes):
+        return np.zeros((0, feats[0].shape[0]), np.float32)
+    roi, _ = multilevel_roi_align(feats, boxes, 7, cfg.anchor_strides)
+    return roi.mean(axis=(2, 3)).astype(np.float32)
+
+
 # ------------------------------------------------------------------------------------------------
 # Batch graph: Mask_RCNN_FPN_multi (models.py:1969-3487).  Same layers; the post-processing differs
 # because it is built on tf.image.combined_non_max_suppression (zero-padded, no score threshold).

@@ -157,3 +157,28 @@ def test_feature_aggregation_modes_match_host_aggregation():
     assert np.abs(mean - f.mean(axis=(2, 3))).max() <= 1e-6 * scale
     np.testing.assert_array_equal(mx, f.max(axis=(2, 3)))
     assert sp.shape == (r, 49) and np.abs(sp - f.mean(axis=1).reshape(r, 49)).max() <= 1e-5 * scale
+
+
+def test_given_box_features_match_oracle():
+    """RCNN_FPN_givenbox (models.py:1816-1967) through get_model_feat / Session.run: 130 boxes (two chunks of 100), some
+    touching the frame border where the uncropped levels matter."""
+    from object_detection_tracking_b200.backend import Session, get_model_feat
+    from object_detection_tracking_b200.config import make_config
+    from object_detection_tracking_b200.synth import synth_frame, synth_weights
+    from oracle import frcnn
+    H, W = 192, 256
+    cfg = make_config(resnet_num_block=(1, 1, 2, 1), max_size=W, short_edge_size=H)
+    Wt = synth_weights(cfg, 1234)
+    frame = synth_frame(H, W, 5).astype(np.float32)
+    rng = np.random.default_rng(6)
+    xy = rng.uniform(0, [W - 20, H - 20], (130, 2))
+    wh = rng.uniform(6, [W / 1.5, H / 1.5], (130, 2))
+    boxes = np.concatenate([xy, np.minimum(xy + wh, [W, H])], 1).astype(np.float32)
+    boxes[:4] = [[0, 0, W, H], [W - 30, H - 30, W, H], [0, H - 12, 40, H], [W - 9, 0, W, 50]]
+    model = get_model_feat(cfg, gpuid=0)
+    model.set_weights(Wt)
+    got, = Session().run([model.final_box_features], feed_dict=model.get_feed_dict(frame, boxes))
+    ref = frcnn.forward_givenbox(cfg, Wt, frame, boxes)
+    assert got.shape == ref.shape == (130, 256)
+    assert np.abs(got - ref).max() <= 2e-5 * np.abs(ref).max()
+    assert Session().run([model.final_box_features], feed_dict=model.get_feed_dict(frame, np.zeros((0, 4))))[0].shape == (0, 256)
