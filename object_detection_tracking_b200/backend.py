@@ -93,6 +93,14 @@ class Mask_RCNN_FPN:
         with np.load(path) as z:
             self.set_weights({k: z[k] for k in z.files})
 
+    def load_pb(self, path: str):
+        """Frozen graph written by the reference's pack() (models.py:134-191): the variables are Const nodes under their
+        checkpoint names; read without TensorFlow (pbreader.py), then the same manifest check as load_npz."""
+        from .pbreader import read_frozen_graph
+        consts = read_frozen_graph(path)
+        prefix = "model_%s/" % self.gpuid           # graphs re-exported after import_graph_def carry it (models.py:211)
+        self.set_weights({(k[len(prefix):] if k.startswith(prefix) else k): v for k, v in consts.items()})
+
     # -- feed dicts -----------------------------------------------------------------------------------
     def get_feed_dict_forward(self, imgdata):
         """models.py:1629-1636: {image placeholder: float32 HWC BGR frame}."""
@@ -311,4 +319,7 @@ def get_model(config, gpuid=0, task=0, controller="/cpu:0", is_multi=False, **kw
     if getattr(config, "is_efficientdet", False):
         return EfficientDet(config, gpuid=gpuid, **kw)                  # models.py:112-113
     cls = Mask_RCNN_FPN_multi if is_multi else Mask_RCNN_FPN
-    return cls(config, gpuid=gpuid, **kw)
+    model = cls(config, gpuid=gpuid, **kw)
+    if getattr(config, "is_load_from_pb", False):                       # models.py:102-109 Mask_RCNN_FPN_frozen(config.load_from)
+        model.load_pb(config.load_from)
+    return model
