@@ -268,6 +268,13 @@ class EfficientDet:
         with np.load(path) as z:
             self.set_weights({k: z[k] for k in z.files})
 
+    def load_pb(self, path: str):
+        """Frozen EfficientDet graph (EfficientDet_frozen, models.py:103-104): Const nodes under the checkpoint variable
+        names, read without TensorFlow (pbreader.py)."""
+        from .pbreader import read_frozen_graph
+        prefix = "model_%s/" % self.gpuid
+        self.set_weights({(k[len(prefix):] if k.startswith(prefix) else k): v for k, v in read_frozen_graph(path).items()})
+
     def get_feed_dict_forward(self, imgdata):
         """wrapper :105-111: {image placeholder (uint8 [h,w,3] BGR): frame}."""
         return {self.image: imgdata}
@@ -317,7 +324,10 @@ def get_model(config, gpuid=0, task=0, controller="/cpu:0", is_multi=False, **kw
     """models.get_model (models.py:97-119).  `controller`/`task` are TF device-placement arguments with
     no meaning here; kept for signature compatibility."""
     if getattr(config, "is_efficientdet", False):
-        return EfficientDet(config, gpuid=gpuid, **kw)                  # models.py:112-113
+        model = EfficientDet(config, gpuid=gpuid, **kw)                 # models.py:112-113
+        if getattr(config, "is_load_from_pb", False):                   # EfficientDet_frozen (models.py:103-104)
+            model.load_pb(config.load_from)
+        return model
     cls = Mask_RCNN_FPN_multi if is_multi else Mask_RCNN_FPN
     model = cls(config, gpuid=gpuid, **kw)
     if getattr(config, "is_load_from_pb", False):                       # models.py:102-109 Mask_RCNN_FPN_frozen(config.load_from)
