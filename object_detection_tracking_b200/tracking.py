@@ -295,3 +295,47 @@ def preprocess_detections(final_boxes, final_probs, final_labels, box_feats, tar
     xywh, confs, f = _select_detections(final_boxes, final_probs, final_labels, box_feats, targetid2class, tracking_objs,
                                         min_confidence, scale, is_coco_model, coco_to_actev_mapping)
     return [(xywh[k], confs[k], f[k]) for k in range(len(confs))]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Per-video post-processing of the track table (deep_sort/utils.py:47-113; obj_detect_tracking.py:800-801).
+# Rows are [frame, track id, x, y, w, h, ...]; host numpy, once per video -- not on the per-frame path.
+# ----------------------------------------------------------------------------------------------------------------
+def linear_inter_bbox(tracking_data, frame_gap):
+    """deep_sort/utils.py:47-91: fills the frames a track skipped (detection runs every `frame_gap` frames) by linear
+    interpolation between its neighbouring rows, rounded to 2 decimals, unless the hole is longer than 10 * frame_gap."""
+    tracking_data = np.asarray(tracking_data)
+    if tracking_data.shape[0] == 0:
+        return tracking_data
+    ids = tracking_data[:, 1].astype(np.int64)
+    extra = []
+    for tid in np.unique(ids):
+        rows = tracking_data[ids == tid]
+        frames = rows[:, 0]
+        for k in range(len(rows) - 1):
+            f0, f1 = frames[k], frames[k + 1]
+            if f1 - f0 <= 1 or f1 - f0 > 10 * frame_gap:
+                continue
+            missing = np.arange(int(f0) + 1, int(np.ceil(f1)))
+            missing = missing[(missing > f0) & (missing < f1)]
+            if not len(missing):
+                continue
+            ratio = (missing - f0) / (f1 - f0)
+            vals = np.around(rows[k, 2:][None, :] + (rows[k + 1, 2:] - rows[k, 2:])[None, :] * ratio[:, None], decimals=2)
+            extra.append(np.concatenate([missing[:, None].astype(np.float64), np.full((len(missing), 1), float(tid)), vals], 1))
+    if extra:
+        tracking_data = np.concatenate([tracking_data] + extra, axis=0)
+    order = np.lexsort((tracking_data[:, 1], tracking_data[:, 0]))
+    return tracking_data[order]
+
+
+def filter_short_objs(tracking_data):
+    """deep_sort/utils.py:94-113: drops tracks with fewer than two rows; rows sorted by (frame, id)."""
+    tracking_data = np.asarray(tracking_data)
+    if tracking_data.shape[0] == 0:
+        return tracking_data
+    ids = tracking_data[:, 1].astype(np.int64)
+    uniq, counts = np.unique(ids, return_counts=True)
+    keep = np.isin(ids, uniq[counts >= 2])
+    out = tracking_data[keep]
+    return out[np.lexsort((out[:, 1], out[:, 0]))]

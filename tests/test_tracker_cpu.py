@@ -146,3 +146,16 @@ def test_create_obj_infos_matches_reference(golden_dir):
     assert len(tm) == len(g["actev_conf"])
     np.testing.assert_array_equal(np.asarray([t[0] for t in tm], dtype=np.float64), g["actev_tlwh"])
     np.testing.assert_array_equal([t[1] for t in tm], g["actev_conf"])
+
+
+def test_track_table_post_processing_matches_reference(golden_dir):
+    """linear_inter_bbox / filter_short_objs (deep_sort/utils.py:47-113) against the reference functions' output."""
+    from object_detection_tracking_b200.tracking import filter_short_objs, linear_inter_bbox
+    g = np.load(os.path.join(golden_dir, "track_post.npz"))
+    inter = linear_inter_bbox(g["data"], 8)
+    assert inter.shape == g["inter"].shape and inter.shape[0] > g["data"].shape[0]
+    np.testing.assert_allclose(inter, g["inter"], rtol=0, atol=1e-9)
+    filt = filter_short_objs(inter)
+    assert filt.shape == g["filt"].shape and filt.shape[0] < inter.shape[0]
+    np.testing.assert_allclose(filt, g["filt"], rtol=0, atol=1e-9)
+    assert linear_inter_bbox(np.zeros((0, 7)), 8).shape == (0, 7) and filter_short_objs(np.zeros((0, 7))).shape == (0, 7)
