@@ -7,7 +7,7 @@ set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 echo "== widened pieces (tests/test_zz_widen_gpu.py) =="
-timeout 300 python -m pytest tests/test_zz_widen_gpu.py -m gpu -q --timeout=120 2>&1 | tee gpurun_out/widen_tests.log | tail -25
+timeout 300 python -m pytest tests/test_zz_widen_gpu.py -m gpu -q --runxfail --timeout=120 2>&1 | tee gpurun_out/widen_tests.log | tail -25
 echo "== opt-in engines (tests/test_zz_unverified_gpu.py, B2_RUN_UNVERIFIED=1) =="
 B2_RUN_UNVERIFIED=1 timeout 400 python -m pytest tests/test_zz_unverified_gpu.py -m gpu -q --timeout=150 2>&1 | tee gpurun_out/unverified_tests.log | tail -25
 echo "== regular suite =="
