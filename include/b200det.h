@@ -276,6 +276,19 @@ int b2_distance_matrix(int device, const float* a, int na, const float* b, int n
  * else 9999.  Host code, float64. */
 int b2_track_pair_cost(int device, const float* a, const int32_t* seg_a, int N, const float* b, const int32_t* seg_b,
                        int M, int D, const uint8_t* gate, float fill, int precision, float* out);
+/* The same with the galleries already in device memory.  b_dev may be PEER memory of another GPU of the node (opened with
+ * b2_gallery_open): the conversion kernel that builds the GEMM's fp16 operand planes then reads the peer gallery over
+ * NVLink directly -- the multi-camera exchange without a staged all-gather copy (one process per GPU; each rank scores its
+ * share of the camera pairs against the other ranks' galleries in place).
+ * b2_gallery_create uploads a gallery [rows, D] into a cudaMalloc'ed buffer and returns the 64-byte CUDA IPC handle other
+ * ranks pass to b2_gallery_open (exchange the handles with any host-side channel, e.g. torch.distributed objects);
+ * b2_gallery_close unmaps a peer gallery, b2_gallery_free releases an own one (after the peers have closed it). */
+int b2_track_pair_cost_dev(int device, const float* a_dev, const int32_t* seg_a, int N, const float* b_dev,
+                           const int32_t* seg_b, int M, int D, const uint8_t* gate, float fill, int precision, float* out);
+int b2_gallery_create(int device, const float* feats_host, int rows, int D, float** dev_out, uint8_t handle_out[64]);
+int b2_gallery_open(int device, const uint8_t handle[64], float** peer_out);
+int b2_gallery_close(int device, float* peer);
+int b2_gallery_free(int device, float* dev);
 int b2_track_spatial_dist(const int32_t* frames1, const double* pts1, const int32_t* seg1, int N, const int32_t* frames2,
                           const double* pts2, const int32_t* seg2, int M, int frame_offset, double tol, double* out);
 

@@ -100,6 +100,11 @@ SYMBOLS = [
     ("b2_effdet_step_info", c_int, [c_void_p, c_int, ctypes.c_char_p, c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int)]),
     ("b2_distance_matrix", c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     ("b2_track_pair_cost", c_int, [c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_float, c_int, c_void_p]),
+    ("b2_track_pair_cost_dev", c_int, [c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_float, c_int, c_void_p]),
+    ("b2_gallery_create", c_int, [c_int, c_void_p, c_int, c_int, POINTER(c_void_p), c_void_p]),
+    ("b2_gallery_open", c_int, [c_int, c_void_p, POINTER(c_void_p)]),
+    ("b2_gallery_close", c_int, [c_int, c_void_p]),
+    ("b2_gallery_free", c_int, [c_int, c_void_p]),
     ("b2_track_spatial_dist", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_double, c_void_p]),
     ("b2_op_conv2d", c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 18 + [c_void_p]),
 ]

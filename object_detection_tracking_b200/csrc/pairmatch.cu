@@ -7,6 +7,7 @@
 // Here: ONE tensor-core GEMM over the concatenated galleries ([Sa,D] x [Sb,D]^T on conv_tc_kernel) and one segmented
 // min kernel; the trajectory distance is plain host code (float64, as the reference).
 #include <math.h>
+#include <string.h>
 
 #include <algorithm>
 #include <map>
@@ -42,8 +43,11 @@ using namespace b2;
 
 extern "C" {
 
-int b2_track_pair_cost(int device, const float* a, const int32_t* seg_a, int N, const float* b, const int32_t* seg_b,
-                       int M, int D, const uint8_t* gate, float fill, int precision, float* out) {
+// Shared body: `a` / `b` are host pointers (a_dev == 0: uploaded first) or device pointers -- b may be PEER memory of
+// another GPU opened through b2_gallery_open: rows_to_planes then reads it over NVLink while converting to the fp16 operand
+// planes, i.e. the "exchange" is the operand load of the GEMM's first stage, no staged copy of the peer gallery exists.
+static int pair_cost_impl(int device, const float* a, bool a_dev, const int32_t* seg_a, int N, const float* b, bool b_dev,
+                          const int32_t* seg_b, int M, int D, const uint8_t* gate, float fill, int precision, float* out) {
   B2_CHECK(N >= 0 && M >= 0 && D > 0, "b2_track_pair_cost: bad argument");
   if (N == 0 || M == 0) return 0;
   B2_CHECK(a && seg_a && b && seg_b && out, "b2_track_pair_cost: null argument");
@@ -64,8 +68,10 @@ int b2_track_pair_cost(int device, const float* a, const int32_t* seg_a, int N, 
   int *d_sa, *d_sb;
   unsigned char* d_gate = nullptr;
   __half *a_hi, *a_lo, *b_hi, *b_lo;
-  B2_CUDA(mem.alloc(&d_a, static_cast<size_t>(Sa) * D));
-  B2_CUDA(mem.alloc(&d_b, static_cast<size_t>(Sb) * D));
+  if (a_dev) d_a = const_cast<float*>(a);
+  else B2_CUDA(mem.alloc(&d_a, static_cast<size_t>(Sa) * D));
+  if (b_dev) d_b = const_cast<float*>(b);
+  else B2_CUDA(mem.alloc(&d_b, static_cast<size_t>(Sb) * D));
   B2_CUDA(mem.alloc(&d_dots, static_cast<size_t>(Sp) * Np));
   B2_CUDA(mem.alloc(&d_out, static_cast<size_t>(N) * M));
   B2_CUDA(mem.alloc(&d_bias, Np, true));
@@ -81,8 +87,8 @@ int b2_track_pair_cost(int device, const float* a, const int32_t* seg_a, int N, 
     B2_CUDA(mem.alloc(&d_gate, static_cast<size_t>(N) * M));
     B2_CUDA(cudaMemcpy(d_gate, gate, static_cast<size_t>(N) * M, cudaMemcpyHostToDevice));
   }
-  B2_CUDA(cudaMemcpy(d_a, a, sizeof(float) * Sa * D, cudaMemcpyHostToDevice));
-  B2_CUDA(cudaMemcpy(d_b, b, sizeof(float) * Sb * D, cudaMemcpyHostToDevice));
+  if (!a_dev) B2_CUDA(cudaMemcpy(d_a, a, sizeof(float) * Sa * D, cudaMemcpyHostToDevice));
+  if (!b_dev) B2_CUDA(cudaMemcpy(d_b, b, sizeof(float) * Sb * D, cudaMemcpyHostToDevice));
   B2_CUDA(cudaMemcpy(d_sa, seg_a, sizeof(int) * (N + 1), cudaMemcpyHostToDevice));
   B2_CUDA(cudaMemcpy(d_sb, seg_b, sizeof(int) * (M + 1), cudaMemcpyHostToDevice));
   if (rows_to_planes(d_a, Sa, D, a_hi, a_lo, Dp, d_na2, st) || rows_to_planes(d_b, Sb, D, b_hi, b_lo, Dp, d_nb2, st)) return -1;
@@ -103,6 +109,63 @@ int b2_track_pair_cost(int device, const float* a, const int32_t* seg_a, int N, 
   conv_tc_plan_destroy(plan);
   if (rc) return -1;
   B2_CUDA(e);
+  return 0;
+}
+
+int b2_track_pair_cost(int device, const float* a, const int32_t* seg_a, int N, const float* b, const int32_t* seg_b,
+                       int M, int D, const uint8_t* gate, float fill, int precision, float* out) {
+  return pair_cost_impl(device, a, false, seg_a, N, b, false, seg_b, M, D, gate, fill, precision, out);
+}
+
+int b2_track_pair_cost_dev(int device, const float* a_dev, const int32_t* seg_a, int N, const float* b_dev,
+                           const int32_t* seg_b, int M, int D, const uint8_t* gate, float fill, int precision, float* out) {
+  return pair_cost_impl(device, a_dev, true, seg_a, N, b_dev, true, seg_b, M, D, gate, fill, precision, out);
+}
+
+// ---- galleries in device memory that other processes of the node can map (one process per GPU) ----
+int b2_gallery_create(int device, const float* feats_host, int rows, int D, float** dev_out, uint8_t handle_out[64]) {
+  B2_CHECK(dev_out && handle_out && rows >= 0 && D > 0 && (rows == 0 || feats_host), "b2_gallery_create: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  *dev_out = nullptr;
+  B2_CUDA(cudaSetDevice(device));
+  float* p = nullptr;
+  B2_CUDA(cudaMalloc(&p, std::max<size_t>(static_cast<size_t>(rows) * D, 1) * sizeof(float)));
+  cudaError_t e = rows ? cudaMemcpy(p, feats_host, static_cast<size_t>(rows) * D * sizeof(float), cudaMemcpyHostToDevice)
+                       : cudaSuccess;
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    B2_CUDA(e);
+  }
+  memcpy(handle_out, &h, 64);
+  *dev_out = p;
+  return 0;
+}
+
+int b2_gallery_open(int device, const uint8_t handle[64], float** peer_out) {
+  B2_CHECK(handle && peer_out, "b2_gallery_open: null argument");
+  *peer_out = nullptr;
+  B2_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  void* p = nullptr;
+  B2_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));   // enables P2P (NVLink) access to the owner GPU
+  *peer_out = static_cast<float*>(p);
+  return 0;
+}
+
+int b2_gallery_close(int device, float* peer) {
+  if (!peer) return 0;
+  B2_CUDA(cudaSetDevice(device));
+  B2_CUDA(cudaIpcCloseMemHandle(peer));
+  return 0;
+}
+
+int b2_gallery_free(int device, float* dev) {
+  if (!dev) return 0;
+  B2_CUDA(cudaSetDevice(device));
+  B2_CUDA(cudaFree(dev));
   return 0;
 }
 

@@ -232,3 +232,122 @@ def camera_pairs(n_cameras, rank=0, world_size=1):
     all-gather every GPU scores its share of the pairs (28 pairs on 8 cameras) independently."""
     pairs = [(i, j) for i in range(n_cameras - 1) for j in range(i + 1, n_cameras)]
     return pairs[rank::world_size]
+
+
+# ---- multi-camera exchange over peer memory (one process per GPU; SURVEY 8e) --------------------------------------------
+class SharedGallery(object):
+    """One camera's crop embeddings [rows, D] in device memory that the other ranks of the node can map.  Instead of
+    all-gathering every gallery into every GPU, each rank opens the galleries of the cameras it has to score against and
+    the operand-conversion kernel of the distance GEMM reads them over NVLink in place (b2_track_pair_cost_dev)."""
+
+    def __init__(self, feats, device=0):
+        feats = np.ascontiguousarray(feats, dtype=np.float32).reshape(len(feats), -1)
+        self.rows, self.dim, self.device = int(feats.shape[0]), int(feats.shape[1]), int(device)
+        self._lib = _lib.load()
+        self._ptr = c_void_p(0)
+        self._handle = (ctypes.c_uint8 * 64)()
+        _lib.check(self._lib.b2_gallery_create(self.device, _lib.ptr(feats), self.rows, self.dim, ctypes.byref(self._ptr),
+                                               self._handle), "b2_gallery_create")
+        self._peers = {}
+
+    @property
+    def ptr(self):
+        return self._ptr
+
+    @property
+    def handle(self) -> bytes:
+        return bytes(self._handle)
+
+    def open_peer(self, handle: bytes):
+        """Maps another rank's gallery; returns its device pointer on this rank."""
+        if handle not in self._peers:
+            buf = (ctypes.c_uint8 * 64).from_buffer_copy(handle)
+            p = c_void_p(0)
+            _lib.check(self._lib.b2_gallery_open(self.device, buf, ctypes.byref(p)), "b2_gallery_open")
+            self._peers[handle] = p
+        return self._peers[handle]
+
+    def close(self):
+        for p in self._peers.values():
+            self._lib.b2_gallery_close(self.device, p)
+        self._peers = {}
+        if self._ptr.value:
+            self._lib.b2_gallery_free(self.device, self._ptr)
+            self._ptr = c_void_p(0)
+
+
+def pair_cost_device(ptr1, seg1, ptr2, seg2, dim, spatial_dist=None, device=0, precision="split"):
+    """compute_feature_dist (multi_video_reid.py:308-324) on galleries that already live in (own or peer) device memory."""
+    seg1 = np.ascontiguousarray(seg1, dtype=np.int32)
+    seg2 = np.ascontiguousarray(seg2, dtype=np.int32)
+    N, M = len(seg1) - 1, len(seg2) - 1
+    gate = None if spatial_dist is None else np.ascontiguousarray(np.asarray(spatial_dist) < 9999., dtype=np.uint8)
+    out = np.zeros((N, M), dtype=np.float32)
+    _lib.check(_lib.load().b2_track_pair_cost_dev(int(device), ptr1, _lib.ptr(seg1), N, ptr2, _lib.ptr(seg2), M, int(dim),
+                                                  _lib.ptr(gate), 999.0, {"fp16": 0, "split": 1}[precision], _lib.ptr(out)),
+               "b2_track_pair_cost_dev")
+    return out.astype(np.float64)
+
+
+def match_cameras_p2p(tracks, device=0, group=None, frame_offsets=None, tol=50, cost_limit=998., precision="split",
+                      ignore_pairs=None):
+    """Config 5 on N ranks = N cameras (one process per GPU): every rank publishes its camera's gallery (SharedGallery),
+    the 64-byte handles and the small host-side metadata (track ids, crop counts, trajectories) travel through
+    torch.distributed objects, and each rank scores its share of the camera pairs (`camera_pairs`) reading the other
+    camera's gallery over NVLink.  `tracks` is this rank's {track_id: (boxes [K,>=3], features [K',D])}.
+    `frame_offsets` / `ignore_pairs` are keyed by the camera pair (i, j).
+    Returns {(cam_i, cam_j): [(track id in i, track id in j), ...]} for the pairs this rank owns."""
+    import torch.distributed as dist
+    from .tmot import lapjv
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ids, _, _, _, feats, seg = _pack_tracks(tracks) if tracks else ([], None, None, None, np.zeros((0, 1), np.float32),
+                                                                    np.zeros(1, np.int32))
+    gal = SharedGallery(feats, device)
+    meta = dict(handle=gal.handle, ids=ids, seg=seg, dim=gal.dim, rows=gal.rows,
+                traj={t: np.asarray(tracks[t][0], dtype=np.float64) for t in ids})
+    metas = [None] * world
+    dist.all_gather_object(metas, meta, group=group)
+    result = {}
+    try:
+        for (i, j) in camera_pairs(world, rank, world):
+            mi, mj = metas[i], metas[j]
+            if not mi["ids"] or not mj["ids"]:
+                result[(i, j)] = []
+                continue
+            ti = {t: (mi["traj"][t], None) for t in mi["ids"]}
+            tj = {t: (mj["traj"][t], None) for t in mj["ids"]}
+            off = 0 if frame_offsets is None else frame_offsets.get((i, j), 0)
+            fr_i, pt_i, sg_i = _pack_traj(ti)
+            fr_j, pt_j, sg_j = _pack_traj(tj)
+            spatial = np.zeros((len(mi["ids"]), len(mj["ids"])), dtype=np.float64)
+            _lib.check(_lib.load().b2_track_spatial_dist(_lib.ptr(fr_i), _lib.ptr(pt_i), _lib.ptr(sg_i), len(mi["ids"]),
+                                                         _lib.ptr(fr_j), _lib.ptr(pt_j), _lib.ptr(sg_j), len(mj["ids"]),
+                                                         int(off), float(tol), _lib.ptr(spatial)), "b2_track_spatial_dist")
+            ign = (ignore_pairs or {}).get((i, j))
+            if ign:                                      # multi_video_reid.py:299-303
+                for a, t1 in enumerate(mi["ids"]):
+                    for b, t2 in enumerate(mj["ids"]):
+                        if t1 in ign[0] and t2 in ign[1]:
+                            spatial[a, b] = 9999.
+            pi = gal.ptr if i == rank else gal.open_peer(mi["handle"])
+            pj = gal.ptr if j == rank else gal.open_peer(mj["handle"])
+            feat = pair_cost_device(pi, mi["seg"], pj, mj["seg"], mi["dim"], spatial, device, precision)
+            _, x, _ = lapjv(feat, extend_cost=True, cost_limit=cost_limit)
+            result[(i, j)] = [(mi["ids"][a], mj["ids"][int(b)]) for a, b in enumerate(x) if b >= 0]
+    finally:
+        dist.barrier(group=group)          # nobody frees a gallery a peer may still be reading
+        gal.close()
+    return result
+
+
+def _pack_traj(tracks):
+    ids = sorted(tracks.keys())
+    frames, pts, seg = [], [], [0]
+    for t in ids:
+        d = np.asarray(tracks[t][0], dtype=np.float64)
+        d = d.reshape(len(d), -1)
+        frames.append(d[:, 0].astype(np.int32))
+        pts.append(d[:, -2:])
+        seg.append(seg[-1] + len(d))
+    return (np.ascontiguousarray(np.concatenate(frames)), np.ascontiguousarray(np.concatenate(pts)),
+            np.asarray(seg, np.int32))

@@ -1,0 +1,53 @@
+"""Config 5 over peer memory (reid.match_cameras_p2p): two processes, two GPUs of one node, galleries mapped through CUDA
+IPC and read over NVLink by the distance GEMM's operand conversion.  Needs >= 2 GPUs (skipped on the single-GPU boxes)
+and is opt-in until its first run (B2_RUN_UNVERIFIED=1; `gpurun --gpus 2`)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.unverified]
+
+
+def _worker(rank, world, port, q, golden_path):
+    import torch
+    import torch.distributed as dist
+    from object_detection_tracking_b200 import reid
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)       # host-side channel for handles / metadata
+    g = np.load(golden_path)
+    name = ("c1", "c2")[rank]
+    cam = {int(t): (g["%s_t%d_rows" % (name, t)], g["%s_t%d_feat" % (name, t)]) for t in g[name + "_ids"]}
+    res = reid.match_cameras_p2p(cam, device=rank, frame_offsets={(0, 1): 4}, tol=50,
+                                 ignore_pairs={(0, 1): ([int(v) for v in g["ignore0"]], [int(v) for v in g["ignore1"]])})
+    q.put((rank, {k: v for k, v in res.items()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_cameras_two_gpus_peer_memory(golden_dir):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    path = os.path.join(golden_dir, "reid_pairs.npz")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, path)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = np.load(path)
+    ids1, ids2 = sorted(int(t) for t in g["c1_ids"]), sorted(int(t) for t in g["c2_ids"])
+    ref = [(ids1[i], ids2[int(j)]) for i, j in enumerate(g["x"]) if j >= 0]
+    assert out[0] == {(0, 1): ref} and out[1] == {}
