@@ -20,3 +20,5 @@ echo "== cuDNN library baseline for the main conv shapes =="
 timeout 200 python tools/cudnn_layer_baseline.py 8 > gpurun_out/cudnn_layers_b8.jsonl 2> gpurun_out/cudnn_layers.err; echo "cudnn rc=$?"; tail -5 gpurun_out/cudnn_layers_b8.jsonl
 echo "== two contexts in flight (experiment) =="
 timeout 300 python tools/ab_two_contexts.py 40 > gpurun_out/ab_two_contexts.jsonl 2> gpurun_out/ab_two_contexts.err; echo "rc=$?"; cat gpurun_out/ab_two_contexts.jsonl
+# Two-GPU test of the peer-memory exchange (config 5) needs its own call:
+#   gpurun --gpus 2 --timeout 600 -- 'B2_RUN_UNVERIFIED=1 timeout 400 python -m pytest tests/test_zz_multi_gpu.py -m gpu -q --runxfail'
