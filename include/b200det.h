@@ -100,6 +100,10 @@ int b2_resize_frames(int device, const uint8_t* frames_u8, int n, int src_h, int
 int b2_submit_host(b2_ctx* ctx, const void* frames_host, float* boxes, float* probs, int32_t* labels, int32_t* valid,
                    float* box_feat, int feat_mode, int slot);
 int b2_wait(b2_ctx* ctx, int slot);
+/* b2_submit_host for uint8 source frames [batch, src_h, src_w, 3] resized on the device (see b2_detect_host_resize); the
+ * source frames must not exceed the network input's float32 byte size (<= 4 source pixels per input pixel). */
+int b2_submit_host_resize(b2_ctx* ctx, const uint8_t* frames_u8, int src_h, int src_w, float* boxes, float* probs,
+                          int32_t* labels, int32_t* valid, float* box_feat, int feat_mode, int slot);
 
 /* RCNN_FPN_givenbox (models.py:1816-1967, get_model_feat :121-131): final_box_features of GIVEN boxes -- backbone + FPN,
  * ROIAlign 7x7 on the uncropped p2..p5, mean over the bins.  frame_host: one frame of the configured dtype / size (batch 1

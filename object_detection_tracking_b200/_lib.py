@@ -51,6 +51,7 @@ SYMBOLS = [
     ("b2_resize_frames", c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     ("b2_submit_host", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
     ("b2_wait", c_int, [c_void_p, c_int]),
+    ("b2_submit_host_resize", c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
     ("b2_box_features", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     ("b2_get_masks", c_int, [c_void_p, c_void_p, c_int64]),
     ("b2_stage_shape", c_int, [c_void_p, c_char_p, POINTER(c_int64), POINTER(c_int32)]),

@@ -1176,8 +1176,10 @@ int b2_resize_frames(int device, const uint8_t* frames_u8, int n, int src_h, int
 // staging[slot] -> image, the pass, and the D2H of the results into the caller's (pinned) buffers, and returns without
 // waiting; b2_wait(slot) blocks until that slot's results have landed.  With two slots the upload of batch i+1 overlaps
 // the pass of batch i.  Host buffers must stay valid (and should be page-locked) until b2_wait returns.
-int b2_submit_host(b2_ctx* c, const void* frames_host, float* boxes, float* probs, int32_t* labels, int32_t* valid,
-                   float* box_feat, int feat_mode, int slot) {
+// src_h == 0: frames_host are network-input frames (b2_submit_host).  src_h > 0: uint8 source frames [B, src_h, src_w, 3]
+// that the resize kernel turns into the float32 network input on the compute stream (b2_submit_host_resize).
+static int submit_impl(b2_ctx* c, const void* frames_host, int src_h, int src_w, float* boxes, float* probs, int32_t* labels,
+                       int32_t* valid, float* box_feat, int feat_mode, int slot) {
   B2_CHECK(c && frames_host, "b2_submit_host: null argument");
   B2_CHECK(slot == 0 || slot == 1, "b2_submit_host: slot must be 0 or 1");
   B2_CUDA(cudaSetDevice(c->device));
@@ -1202,11 +1204,17 @@ int b2_submit_host(b2_ctx* c, const void* frames_host, float* boxes, float* prob
     }
     if (c->cfg.use_cuda_graph && ensure_graph(c)) return -1;   // capture before anything is in flight
   }
+  const size_t in_bytes = src_h > 0 ? static_cast<size_t>(B) * src_h * src_w * 3 : c->img_bytes;
   B2_CUDA(cudaStreamWaitEvent(c->copy_stream, c->staged_free[slot], 0));      // the previous use of this staging buffer
-  B2_CUDA(cudaMemcpyAsync(c->stage_in[slot], frames_host, c->img_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+  B2_CUDA(cudaMemcpyAsync(c->stage_in[slot], frames_host, in_bytes, cudaMemcpyHostToDevice, c->copy_stream));
   B2_CUDA(cudaEventRecord(c->h2d_done[slot], c->copy_stream));
   B2_CUDA(cudaStreamWaitEvent(c->stream, c->h2d_done[slot], 0));
-  B2_CUDA(cudaMemcpyAsync(c->img, c->stage_in[slot], c->img_bytes, cudaMemcpyDeviceToDevice, c->stream));
+  if (src_h > 0) {
+    if (resize_u8_launch(static_cast<const uint8_t*>(c->stage_in[slot]), B, src_h, src_w, static_cast<float*>(c->img),
+                         c->cfg.height, c->cfg.width, c->stream)) return -1;
+  } else {
+    B2_CUDA(cudaMemcpyAsync(c->img, c->stage_in[slot], c->img_bytes, cudaMemcpyDeviceToDevice, c->stream));
+  }
   B2_CUDA(cudaEventRecord(c->staged_free[slot], c->stream));
   if (run_all(c)) return -1;
   // results -> this slot's device staging (a few tens of microseconds), then off the compute stream: the download runs
@@ -1233,6 +1241,22 @@ int b2_submit_host(b2_ctx* c, const void* frames_host, float* boxes, float* prob
   B2_CUDA(cudaEventRecord(c->out_done[slot], ds));
   c->slot_busy[slot] = true;
   return 0;
+}
+
+int b2_submit_host(b2_ctx* c, const void* frames_host, float* boxes, float* probs, int32_t* labels, int32_t* valid,
+                   float* box_feat, int feat_mode, int slot) {
+  return submit_impl(c, frames_host, 0, 0, boxes, probs, labels, valid, box_feat, feat_mode, slot);
+}
+
+// The streaming form of b2_detect_host_resize: uint8 source frames in (they must fit the staging buffer, i.e. at most four
+// source pixels per network-input pixel), resized on the device, pipelined like b2_submit_host.
+int b2_submit_host_resize(b2_ctx* c, const uint8_t* frames_u8, int src_h, int src_w, float* boxes, float* probs,
+                          int32_t* labels, int32_t* valid, float* box_feat, int feat_mode, int slot) {
+  B2_CHECK(c && src_h > 0 && src_w > 0, "b2_submit_host_resize: bad argument");
+  B2_CHECK(c->cfg.input_dtype == 0, "b2_submit_host_resize: the context must be created with input_dtype = 0 (float32 frames)");
+  B2_CHECK(static_cast<size_t>(c->cfg.batch) * src_h * src_w * 3 <= c->img_bytes,
+           "b2_submit_host_resize: source frames larger than the staging buffer (more than 4 source pixels per input pixel)");
+  return submit_impl(c, frames_u8, src_h, src_w, boxes, probs, labels, valid, box_feat, feat_mode, slot);
 }
 
 int b2_wait(b2_ctx* c, int slot) {

@@ -127,6 +127,20 @@ class Detector:
                                            _lib.ptr(out["feat"]) if want_feat else c_void_p(0), feat_mode, int(slot)),
                    "b2_submit_host")
 
+    def submit_host_resize(self, frames_u8, out: dict, slot: int, feat_mode: int = 0, want_feat: bool = True):
+        """submit_host for uint8 source frames [B,h,w,3] that are resized on the device (detect_host_resize, pipelined)."""
+        if isinstance(frames_u8, np.ndarray):
+            frames_u8 = np.ascontiguousarray(frames_u8, dtype=np.uint8)
+        assert frames_u8.shape[0] == self.batch and frames_u8.shape[3] == 3, frames_u8.shape
+        if not hasattr(self, "_inflight"):
+            self._inflight = {}
+        self._inflight[int(slot)] = (frames_u8, out)
+        _lib.check(self.lib.b2_submit_host_resize(self._ctx, _lib.ptr(frames_u8), int(frames_u8.shape[1]),
+                                                  int(frames_u8.shape[2]), _lib.ptr(out["boxes"]), _lib.ptr(out["probs"]),
+                                                  _lib.ptr(out["labels"]), _lib.ptr(out["valid"]),
+                                                  _lib.ptr(out["feat"]) if want_feat else c_void_p(0), feat_mode, int(slot)),
+                   "b2_submit_host_resize")
+
     def wait(self, slot: int):
         _lib.check(self.lib.b2_wait(self._ctx, int(slot)), "b2_wait")
         getattr(self, "_inflight", {}).pop(int(slot), None)

@@ -182,3 +182,28 @@ def test_given_box_features_match_oracle():
     assert got.shape == ref.shape == (130, 256)
     assert np.abs(got - ref).max() <= 2e-5 * np.abs(ref).max()
     assert Session().run([model.final_box_features], feed_dict=model.get_feed_dict(frame, np.zeros((0, 4))))[0].shape == (0, 256)
+
+
+def test_pipelined_resize_ingest_equals_synchronous_call():
+    """b2_submit_host_resize / b2_wait (two slots) == b2_detect_host_resize on the same uint8 source batches."""
+    from object_detection_tracking_b200.config import make_config
+    from object_detection_tracking_b200.engine import Detector
+    from object_detection_tracking_b200.synth import synth_frame, synth_weights
+    cfg = make_config(resnet_num_block=(1, 1, 2, 1), max_size=256, short_edge_size=144)
+    det = Detector(cfg, 2, 144, 256, device=0, precision="split", use_cuda_graph=True)
+    det.load_weights(synth_weights(cfg, 1234))
+    batches = [np.stack([synth_frame(216, 384, 10 * j + i) for i in range(2)]) for j in range(3)]
+    ref = [{k: v.copy() for k, v in det.detect_host_resize(b).items()} for b in batches]
+    outs = [det.alloc_outputs(), det.alloc_outputs()]
+    got = []
+    det.submit_host_resize(batches[0], outs[0], 0)
+    for j in range(1, 3):
+        det.submit_host_resize(batches[j], outs[j & 1], j & 1)
+        det.wait((j - 1) & 1)
+        got.append({k: v.copy() for k, v in outs[(j - 1) & 1].items()})
+    det.wait(0)
+    got.append({k: v.copy() for k, v in outs[0].items()})
+    for a, b in zip(got, ref):
+        assert int(b["valid"].sum()) > 0
+        for k in ("valid", "labels", "boxes", "probs"):
+            np.testing.assert_array_equal(a[k], b[k])
