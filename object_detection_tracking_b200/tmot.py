@@ -127,24 +127,30 @@ class JDETracker(object):
         got = self._lib.b2_jde_update(self._h, _lib.ptr(tlwh), _lib.ptr(conf), _lib.ptr(feat), n)
         if got < 0:
             _lib.check(got, "b2_jde_update")
-        return self.get_tracks(0)
+        return self.get_tracks(0, full=False)
 
-    def get_tracks(self, which=0):
-        """which: 0 = the list update() returns, 1 = tracked_stracks, 2 = lost_stracks."""
+    def get_tracks(self, which=0, full=True):
+        """which: 0 = the list update() returns, 1 = tracked_stracks, 2 = lost_stracks.  full=False skips the Kalman
+        state (mean / covariance stay None): what the drivers read per frame is the id, the boxes and the confidence."""
         if self._h is None:
             return []
         n = self._lib.b2_jde_get_tracks(self._h, which, 0, *([None] * 12))
-        ids, st, act, fid, sf, tl = (np.zeros(n, np.int32) for _ in range(6))
+        if n == 0:
+            return []
+        ints = np.zeros((6, n), np.int32)                       # ids, state, is_activated, frame_id, start_frame, tracklet_len
         tlwh, dtlwh = np.zeros((n, 4)), np.zeros((n, 4))
         dconf, score = np.zeros(n), np.zeros(n)
-        mean, cov = np.zeros((n, 8)), np.zeros((n, 8, 8))
-        got = self._lib.b2_jde_get_tracks(self._h, which, n, *[_lib.ptr(a) for a in (ids, st, act, fid, sf, tl, tlwh, dtlwh,
-                                                                                     dconf, score, mean, cov)])
+        mean, cov = (np.zeros((n, 8)), np.zeros((n, 8, 8))) if full else (None, None)
+        got = self._lib.b2_jde_get_tracks(self._h, which, n, *[_lib.ptr(a) for a in (ints[0], ints[1], ints[2], ints[3], ints[4],
+                                                                                     ints[5], tlwh, dtlwh, dconf, score, mean, cov)])
         if got != n:
             _lib.check(-1, "b2_jde_get_tracks")
-        return [STrack(track_id=int(ids[k]), state=int(st[k]), is_activated=bool(act[k]), frame_id=int(fid[k]),
-                       start_frame=int(sf[k]), tracklet_len=int(tl[k]), tlwh=tlwh[k].copy(), cur_det_tlwh=dtlwh[k].copy(),
-                       cur_det_conf=float(dconf[k]), score=float(score[k]), mean=mean[k].copy(), covariance=cov[k].copy())
+        ids, st, act, fid, sf, tl = ints.tolist()
+        dconf_l, score_l = dconf.tolist(), score.tolist()
+        # the arrays are fresh per call, so row views do not alias anything that outlives this list
+        return [STrack(track_id=ids[k], state=st[k], is_activated=bool(act[k]), frame_id=fid[k], start_frame=sf[k],
+                       tracklet_len=tl[k], tlwh=tlwh[k], cur_det_tlwh=dtlwh[k], cur_det_conf=dconf_l[k], score=score_l[k],
+                       mean=mean[k] if full else None, covariance=cov[k] if full else None)
                 for k in range(n)]
 
     @property
