@@ -207,3 +207,45 @@ def test_pipelined_resize_ingest_equals_synchronous_call():
         assert int(b["valid"].sum()) > 0
         for k in ("valid", "labels", "boxes", "probs"):
             np.testing.assert_array_equal(a[k], b[k])
+
+
+def test_detect_then_track_loop_end_to_end():
+    """The per-frame loop of obj_detect_tracking.py:597-696 with every piece swapped in: sess.run on the model object,
+    create_obj_infos, pre-tracker NMS, native Tracker with the GPU appearance metric; and the TMOT variant
+    (preprocess_detections + JDETracker).  The same frame is fed repeatedly, so every detection must keep its track id."""
+    from object_detection_tracking_b200.backend import Session, get_model
+    from object_detection_tracking_b200.config import make_config
+    from object_detection_tracking_b200.synth import synth_frame, synth_weights
+    from object_detection_tracking_b200.tmot import JDETracker, _IdGroup
+    from object_detection_tracking_b200.tracking import (GpuNearestNeighborDistanceMetric, Tracker, create_obj_infos,
+                                                         non_max_suppression, preprocess_detections)
+    H, W = 192, 256
+    cfg = make_config(resnet_num_block=(1, 1, 2, 1), max_size=W, short_edge_size=H)
+    model = get_model(cfg, gpuid=0)
+    model.set_weights(synth_weights(cfg, 1234))
+    sess = Session()
+    frame = synth_frame(H, W, 5).astype(np.float32)
+    id2class = {i: "class%d" % i for i in range(1, cfg.num_class)}
+    tracker = Tracker(GpuNearestNeighborDistanceMetric("cosine", 0.5, 5), max_iou_distance=0.5)
+    jde = JDETracker(0.0, id_group=_IdGroup())
+    seen, seen_jde, target = [], [], None
+    for f in range(5):
+        boxes, labels, probs, feats = sess.run([model.final_boxes, model.final_labels, model.final_probs, model.fpn_box_feat],
+                                               feed_dict=model.get_feed_dict_forward(frame))
+        assert len(feats) == len(boxes) > 0                                  # obj_detect_tracking.py:648
+        if target is None:
+            target = id2class[int(np.bincount(labels).argmax())]            # the most frequent class of this frame
+        dets = create_obj_infos(f, boxes, probs, labels, feats, id2class, [target], 0.0, 0, 1.0)
+        keep = non_max_suppression(np.array([d.tlwh for d in dets]), 0.85, np.array([d.confidence for d in dets]))
+        dets = [dets[i] for i in keep]
+        tracker.predict()
+        tracker.update(dets)
+        seen.append(sorted(t.track_id for t in tracker.tracks if t.is_confirmed() and t.time_since_update <= 1))
+        tm = preprocess_detections(boxes, probs, labels, feats, id2class, [target], 0.0, 1.0)
+        tm = [tm[i] for i in non_max_suppression(np.array([d[0] for d in tm]), 0.85, np.array([d[1] for d in tm]))]
+        seen_jde.append(sorted(t.track_id for t in jde.update(tm)))
+    n = len(dets)
+    assert n > 0 and seen[1] == seen[-1] == list(range(1, n + 1))            # n_init = 1: confirmed at the first match
+    assert seen_jde[0] == [] and seen_jde[1] == seen_jde[-1] == list(range(1, n + 1))   # activated at the second frame
+    tracker.close()
+    jde.close()
