@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -1381,6 +1382,143 @@ int b2_set_stage(b2_ctx* c, const char* name, const void* src, int64_t bytes) {
   return 0;
 }
 
+// ---- persistent workspace for the small per-frame GEMM calls (experiment, B2_WS=1) -----------------------------
+// b2_cosine_cost / b2_distance_matrix are called once per frame (per cascade level) by the trackers; as written they
+// allocate ~12 device buffers, encode the tensor maps and free everything again on every call.  With B2_WS set they run
+// out of one grow-only workspace per device with the GEMM plans cached per padded shape: a call is then three uploads,
+// four launches and one download on a private stream.  Operands are padded to the plan's shape with whatever the buffers
+// hold (finite leftovers of earlier calls): padded rows / columns only produce outputs nobody reads.
+struct DistWs {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  size_t cap_a = 0, cap_b = 0, cap_rows = 0, cap_cols = 0, cap_dp = 0;
+  float *d_a = nullptr, *d_b = nullptr, *d_dots = nullptr, *d_out = nullptr, *d_bias = nullptr, *d_na2 = nullptr, *d_nb2 = nullptr;
+  int* d_off = nullptr;
+  __half *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
+  std::map<std::vector<int>, ConvPlan*> plans;   // key: Sp, Np, Dp, split
+  int num_sms = 148;
+};
+static std::map<int, DistWs> g_dist_ws;
+static std::mutex g_dist_ws_mutex;   // one call at a time per process (the trackers are single-threaded per stream)
+
+static void dist_ws_release(DistWs& w) {
+  for (auto& kv : w.plans) conv_tc_plan_destroy(kv.second);
+  w.plans.clear();
+  void* ptrs[] = {w.d_a, w.d_b, w.d_dots, w.d_out, w.d_bias, w.d_na2, w.d_nb2, w.d_off, w.a_hi, w.a_lo, w.b_hi, w.b_lo};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  w.d_a = w.d_b = w.d_dots = w.d_out = w.d_bias = w.d_na2 = w.d_nb2 = nullptr;
+  w.d_off = nullptr;
+  w.a_hi = w.a_lo = w.b_hi = w.b_lo = nullptr;
+}
+
+// Makes the workspace of `device` hold Sp x Dp (A side), Np x Dp (B side), Sp x Np (products) and `aux` ints / floats.
+static int dist_ws_reserve(DistWs** out, int device, int S, int N, int D, int Sp, int Np, int Dp, int aux) {
+  DistWs& w = g_dist_ws[device];
+  if (w.device < 0) {
+    w.device = device;
+    cudaDeviceProp prop;
+    B2_CUDA(cudaGetDeviceProperties(&prop, device));
+    w.num_sms = prop.multiProcessorCount;
+    B2_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+  }
+  const size_t need_a = static_cast<size_t>(S) * D, need_b = static_cast<size_t>(N) * D;
+  if (need_a > w.cap_a || need_b > w.cap_b || static_cast<size_t>(Sp) > w.cap_rows || static_cast<size_t>(Np) > w.cap_cols ||
+      static_cast<size_t>(Dp) > w.cap_dp || static_cast<size_t>(aux) > w.cap_rows + w.cap_cols) {
+    B2_CUDA(cudaStreamSynchronize(w.stream));
+    dist_ws_release(w);                                   // the plans hold the old addresses
+    auto grow = [](size_t cap, size_t need, size_t floor_) {   // only the dimension that overflowed grows (x2 head room)
+      return need > cap ? std::max(need * 2, floor_) : std::max(cap, floor_);
+    };
+    w.cap_a = grow(w.cap_a, need_a, 1);
+    w.cap_b = grow(w.cap_b, need_b, 1);
+    w.cap_rows = grow(w.cap_rows, static_cast<size_t>(Sp), 256);
+    w.cap_cols = grow(w.cap_cols, static_cast<size_t>(Np), 256);
+    w.cap_dp = std::max(w.cap_dp, static_cast<size_t>(Dp));
+    B2_CUDA(cudaMalloc(&w.d_a, w.cap_a * 4));
+    B2_CUDA(cudaMalloc(&w.d_b, w.cap_b * 4));
+    B2_CUDA(cudaMalloc(&w.d_dots, w.cap_rows * w.cap_cols * 4));
+    B2_CUDA(cudaMalloc(&w.d_out, w.cap_rows * w.cap_cols * 4));
+    B2_CUDA(cudaMalloc(&w.d_bias, w.cap_cols * 4));
+    B2_CUDA(cudaMalloc(&w.d_na2, w.cap_rows * 4));
+    B2_CUDA(cudaMalloc(&w.d_nb2, w.cap_cols * 4));
+    B2_CUDA(cudaMalloc(&w.d_off, (w.cap_rows + w.cap_cols + 1) * 4));
+    B2_CUDA(cudaMalloc(&w.a_hi, w.cap_rows * w.cap_dp * 2));
+    B2_CUDA(cudaMalloc(&w.a_lo, w.cap_rows * w.cap_dp * 2));
+    B2_CUDA(cudaMalloc(&w.b_hi, w.cap_cols * w.cap_dp * 2));
+    B2_CUDA(cudaMalloc(&w.b_lo, w.cap_cols * w.cap_dp * 2));
+    B2_CUDA(cudaMemsetAsync(w.d_bias, 0, w.cap_cols * 4, w.stream));
+    B2_CUDA(cudaMemsetAsync(w.a_hi, 0, w.cap_rows * w.cap_dp * 2, w.stream));
+    B2_CUDA(cudaMemsetAsync(w.a_lo, 0, w.cap_rows * w.cap_dp * 2, w.stream));
+    B2_CUDA(cudaMemsetAsync(w.b_hi, 0, w.cap_cols * w.cap_dp * 2, w.stream));
+    B2_CUDA(cudaMemsetAsync(w.b_lo, 0, w.cap_cols * w.cap_dp * 2, w.stream));
+    B2_CUDA(cudaStreamSynchronize(w.stream));
+  }
+  *out = &w;
+  return 0;
+}
+
+// the [Sp rows] x [Np columns] GEMM over K = Dp on the workspace operand planes (row stride Dp)
+static int dist_ws_gemm(DistWs& w, int Sp, int Np, int Dp, bool split) {
+  const std::vector<int> key = {Sp, Np, Dp, split ? 1 : 0};
+  auto it = w.plans.find(key);
+  if (it == w.plans.end()) {
+    ConvDesc d;
+    d.B = 1; d.in_H = 1; d.in_W = Sp; d.Cin = Dp; d.in_pitch_H = 1; d.in_pitch_W = Sp; d.in_ld = Dp;
+    d.Cout = Np; d.out_H = 1; d.out_W = Sp; d.ldc = Np;
+    ConvWeights cw;
+    cw.w_hi = w.b_hi; cw.w_lo = split ? w.b_lo : nullptr; cw.bias = w.d_bias; cw.Cout_pad = Np; cw.K = Dp;
+    ConvIO io;
+    io.in_hi = w.a_hi; io.in_lo = split ? w.a_lo : nullptr; io.out_f32 = w.d_dots;
+    ConvPlan* plan = conv_tc_plan_create(d, cw, io, split, w.num_sms);
+    B2_CHECK(plan != nullptr, std::string("distance workspace plan: ") + last_error());
+    it = w.plans.emplace(key, plan).first;
+  }
+  return conv_tc_launch(it->second, w.stream);
+}
+
+static int cosine_cost_ws(int device, const float* gallery, const int32_t* seg_offsets, int T, const float* dets, int N, int D,
+                          bool split, float* cost) {
+  std::lock_guard<std::mutex> lock(g_dist_ws_mutex);
+  const int S = seg_offsets[T];
+  const int Dp = (D + 63) / 64 * 64, Np = (N + 15) / 16 * 16, Sp = (S + 127) / 128 * 128;
+  DistWs* w = nullptr;
+  if (dist_ws_reserve(&w, device, S, N, D, Sp, Np, Dp, T + 1)) return -1;
+  cudaStream_t st = w->stream;
+  B2_CUDA(cudaMemcpyAsync(w->d_a, gallery, sizeof(float) * S * D, cudaMemcpyHostToDevice, st));
+  B2_CUDA(cudaMemcpyAsync(w->d_b, dets, sizeof(float) * N * D, cudaMemcpyHostToDevice, st));
+  B2_CUDA(cudaMemcpyAsync(w->d_off, seg_offsets, sizeof(int) * (T + 1), cudaMemcpyHostToDevice, st));
+  if (cosine_normalize_rows(w->d_a, S, D, w->a_hi, w->a_lo, Dp, st) || cosine_normalize_rows(w->d_b, N, D, w->b_hi, w->b_lo, Dp, st))
+    return -1;
+  if (dist_ws_gemm(*w, Sp, Np, Dp, split)) return -1;
+  if (cosine_segmin(w->d_dots, Np, w->d_off, T, N, w->d_out, st)) return -1;
+  B2_CUDA(cudaMemcpyAsync(cost, w->d_out, sizeof(float) * T * N, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+static int distance_matrix_ws(int device, const float* a, int na, const float* b, int nb, int D, int metric, bool split,
+                              float* out) {
+  std::lock_guard<std::mutex> lock(g_dist_ws_mutex);
+  const int Dp = (D + 63) / 64 * 64, Np = (nb + 15) / 16 * 16, Sp = (na + 127) / 128 * 128;
+  DistWs* w = nullptr;
+  if (dist_ws_reserve(&w, device, na, nb, D, Sp, Np, Dp, 0)) return -1;
+  cudaStream_t st = w->stream;
+  B2_CUDA(cudaMemcpyAsync(w->d_a, a, sizeof(float) * na * D, cudaMemcpyHostToDevice, st));
+  B2_CUDA(cudaMemcpyAsync(w->d_b, b, sizeof(float) * nb * D, cudaMemcpyHostToDevice, st));
+  if (metric == 0) {
+    if (cosine_normalize_rows(w->d_a, na, D, w->a_hi, w->a_lo, Dp, st) || cosine_normalize_rows(w->d_b, nb, D, w->b_hi, w->b_lo, Dp, st))
+      return -1;
+  } else {
+    if (rows_to_planes(w->d_a, na, D, w->a_hi, w->a_lo, Dp, w->d_na2, st) || rows_to_planes(w->d_b, nb, D, w->b_hi, w->b_lo, Dp, w->d_nb2, st))
+      return -1;
+  }
+  if (dist_ws_gemm(*w, Sp, Np, Dp, split)) return -1;
+  if (distance_finish(w->d_dots, Np, na, nb, metric, w->d_na2, w->d_nb2, w->d_out, st)) return -1;
+  B2_CUDA(cudaMemcpyAsync(out, w->d_out, sizeof(float) * na * nb, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 // ---- DeepSORT appearance cost ---------------------------------------------------------------
 int b2_cosine_cost(int device, const float* gallery, const int32_t* seg_offsets, int T, const float* dets, int N,
                    int D, int precision, float* cost) {
@@ -1390,6 +1528,7 @@ int b2_cosine_cost(int device, const float* gallery, const int32_t* seg_offsets,
   const int S = seg_offsets[T];
   B2_CHECK(S > 0 && D > 0, "b2_cosine_cost: empty gallery");
   const bool split = precision == 1;
+  if (getenv("B2_WS") != nullptr) return cosine_cost_ws(device, gallery, seg_offsets, T, dets, N, D, split, cost);
   const int Dp = (D + 63) / 64 * 64, Np = (N + 15) / 16 * 16, Sp = (S + 127) / 128 * 128;
   cudaStream_t st = nullptr;
   float *d_g = nullptr, *d_d = nullptr, *d_dots = nullptr, *d_cost = nullptr, *d_bias = nullptr;
@@ -1445,6 +1584,7 @@ int b2_distance_matrix(int device, const float* a, int na, const float* b, int n
   if (na <= 0 || nb <= 0) return 0;
   B2_CUDA(cudaSetDevice(device));
   const bool split = precision == 1;
+  if (getenv("B2_WS") != nullptr) return distance_matrix_ws(device, a, na, b, nb, D, metric, split, out);
   const int Dp = (D + 63) / 64 * 64, Np = (nb + 15) / 16 * 16, Sp = (na + 127) / 128 * 128;
   cudaStream_t st = nullptr;
   float *d_a = nullptr, *d_b = nullptr, *d_dots = nullptr, *d_out = nullptr, *d_bias = nullptr, *d_na2 = nullptr,

@@ -249,3 +249,34 @@ def test_detect_then_track_loop_end_to_end():
     assert seen_jde[0] == [] and seen_jde[1] == seen_jde[-1] == list(range(1, n + 1))   # activated at the second frame
     tracker.close()
     jde.close()
+
+
+def test_distance_calls_from_the_persistent_workspace_equal_the_per_call_path():
+    """B2_WS=1 (grow-only workspace + cached GEMM plans for b2_cosine_cost / b2_distance_matrix) returns the same bits as the
+    allocate-per-call path, across growing and shrinking shapes and both metrics (each mode in its own process: the switch is
+    read from the environment)."""
+    import subprocess
+    import sys
+    import tempfile
+    code = (
+        "import numpy as np, sys; sys.path.insert(0, %r)\\n"
+        "from object_detection_tracking_b200.engine import cosine_cost\\n"
+        "from object_detection_tracking_b200.reid import compute_distance_matrix\\n"
+        "rng = np.random.default_rng(0); out = {}\\n"
+        "for k, (T, per, N, D) in enumerate([(5, 3, 7, 64), (40, 5, 90, 256), (3, 2, 4, 256), (100, 5, 100, 256), (9, 4, 33, 48)]):\\n"
+        "    gal = np.abs(rng.standard_normal((T * per, D))).astype(np.float32) + 0.1\\n"
+        "    seg = (np.arange(T + 1) * per).astype(np.int32)\\n"
+        "    det = np.abs(rng.standard_normal((N, D))).astype(np.float32) + 0.1\\n"
+        "    out['cos%%d' %% k] = cosine_cost(gal, seg, det)\\n"
+        "    out['euc%%d' %% k] = compute_distance_matrix(gal, det, 'euclidean').numpy()\\n"
+        "    out['cdm%%d' %% k] = compute_distance_matrix(det, gal, 'cosine').numpy()\\n"
+        "np.savez(sys.argv[1], **out)\\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for i, env in enumerate([{}, {"B2_WS": "1"}]):
+            path = os.path.join(tmp, "o%d.npz" % i)
+            subprocess.run([sys.executable, "-c", code, path], check=True, env=dict(os.environ, **env), timeout=300)
+            res.append(dict(np.load(path)))
+    assert set(res[0]) == set(res[1]) and len(res[0]) == 15
+    for k in res[0]:
+        np.testing.assert_array_equal(res[0][k], res[1][k])

@@ -20,3 +20,7 @@ echo "=== accuracy of the short-K chunk variant (boxes vs the fp32 oracle on the
 B2_ACC_KB_SHORTK=2 timeout 600 python tools/gpu_pipeline_probe.py 720 1280 tcgen05 split > gpurun_out/pipe_shortk2.log 2>&1
 grep -E "c[45] rel|proposals gpu|final gpu" gpurun_out/pipe_shortk2.log
 timeout 300 python tools/ab_two_contexts.py 40 | tee gpurun_out/ab_two_contexts.jsonl
+echo "=== trackers with the persistent distance workspace (B2_WS=1) vs per-call allocation"
+timeout 200 python tools/gpu_tracker_probe.py > gpurun_out/tracker_nows.log 2>&1; tail -2 gpurun_out/tracker_nows.log
+B2_WS=1 timeout 200 python tools/gpu_tracker_probe.py > gpurun_out/tracker_ws.log 2>&1; tail -2 gpurun_out/tracker_ws.log
+timeout 200 python tools/gpu_widen_timing.py | head -1; B2_WS=1 timeout 200 python tools/gpu_widen_timing.py | head -1
