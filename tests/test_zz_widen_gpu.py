@@ -259,18 +259,18 @@ def test_distance_calls_from_the_persistent_workspace_equal_the_per_call_path():
     import sys
     import tempfile
     code = (
-        "import numpy as np, sys; sys.path.insert(0, %r)\\n"
-        "from object_detection_tracking_b200.engine import cosine_cost\\n"
-        "from object_detection_tracking_b200.reid import compute_distance_matrix\\n"
-        "rng = np.random.default_rng(0); out = {}\\n"
-        "for k, (T, per, N, D) in enumerate([(5, 3, 7, 64), (40, 5, 90, 256), (3, 2, 4, 256), (100, 5, 100, 256), (9, 4, 33, 48)]):\\n"
-        "    gal = np.abs(rng.standard_normal((T * per, D))).astype(np.float32) + 0.1\\n"
-        "    seg = (np.arange(T + 1) * per).astype(np.int32)\\n"
-        "    det = np.abs(rng.standard_normal((N, D))).astype(np.float32) + 0.1\\n"
-        "    out['cos%%d' %% k] = cosine_cost(gal, seg, det)\\n"
-        "    out['euc%%d' %% k] = compute_distance_matrix(gal, det, 'euclidean').numpy()\\n"
-        "    out['cdm%%d' %% k] = compute_distance_matrix(det, gal, 'cosine').numpy()\\n"
-        "np.savez(sys.argv[1], **out)\\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        "import numpy as np, sys; sys.path.insert(0, %r)\n"
+        "from object_detection_tracking_b200.engine import cosine_cost\n"
+        "from object_detection_tracking_b200.reid import compute_distance_matrix\n"
+        "rng = np.random.default_rng(0); out = {}\n"
+        "for k, (T, per, N, D) in enumerate([(5, 3, 7, 64), (40, 5, 90, 256), (3, 2, 4, 256), (100, 5, 100, 256), (9, 4, 33, 48)]):\n"
+        "    gal = np.abs(rng.standard_normal((T * per, D))).astype(np.float32) + 0.1\n"
+        "    seg = (np.arange(T + 1) * per).astype(np.int32)\n"
+        "    det = np.abs(rng.standard_normal((N, D))).astype(np.float32) + 0.1\n"
+        "    out['cos%%d' %% k] = cosine_cost(gal, seg, det)\n"
+        "    out['euc%%d' %% k] = compute_distance_matrix(gal, det, 'euclidean').numpy()\n"
+        "    out['cdm%%d' %% k] = compute_distance_matrix(det, gal, 'cosine').numpy()\n"
+        "np.savez(sys.argv[1], **out)\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = []
     with tempfile.TemporaryDirectory() as tmp:
         for i, env in enumerate([{}, {"B2_WS": "1"}]):
