@@ -4,7 +4,8 @@
 `deep_sort.nn_matching.NearestNeighborDistanceMetric` (deep_sort/nn_matching.py:99-177), so
 `Tracker(metric)` (deep_sort/tracker.py:40-48, obj_detect_tracking.py:553-558) takes it unchanged.
 `distance()` replaces the per-track Python loop of tiny NumPy GEMMs (:174-177) by ONE tensor-core GEMM
-over the concatenated galleries plus a segmented row-min (b2_cosine_cost).  No CPU fallback.
+over the concatenated galleries plus a segmented row-min (b2_cosine_cost; the 'euclidean' metric of the same class,
+nn_matching.py:57-75, runs as b2_track_pair_cost).  No CPU fallback.
 """
 from __future__ import annotations
 
@@ -15,9 +16,9 @@ from .engine import cosine_cost
 
 class GpuNearestNeighborDistanceMetric(object):
     def __init__(self, metric, matching_threshold, budget=None, device=0, precision="split"):
-        if metric != "cosine":
-            raise ValueError("Invalid metric; the B200 path implements 'cosine' (the metric the drivers use, "
-                             "obj_detect_tracking.py:553)")
+        if metric not in ("cosine", "euclidean"):
+            raise ValueError("Invalid metric; must be either 'euclidean' or 'cosine'")       # nn_matching.py:123-129
+        self.metric = metric
         self.matching_threshold = matching_threshold
         self.budget = budget
         self.samples = {}
@@ -46,7 +47,19 @@ class GpuNearestNeighborDistanceMetric(object):
             rows.append(g)
             seg[i + 1] = seg[i] + g.shape[0]
         gallery = np.concatenate(rows, axis=0)
-        cost[:, :] = cosine_cost(gallery, seg, feats, device=self.device, precision=self.precision)
+        if self.metric == "cosine":
+            cost[:, :] = cosine_cost(gallery, seg, feats, device=self.device, precision=self.precision)
+        else:
+            # _nn_euclidean_distance (nn_matching.py:57-75): min over the gallery rows of the squared distance, clamped
+            # at 0 -- the track-pair cost with every detection as a one-row segment (one GEMM + segmented min)
+            from . import _lib
+            det_seg = np.arange(N + 1, dtype=np.int32)
+            out = np.zeros((T, N), dtype=np.float32)
+            _lib.check(_lib.load().b2_track_pair_cost(int(self.device), _lib.ptr(gallery), _lib.ptr(seg), T, _lib.ptr(feats),
+                                                      _lib.ptr(det_seg), N, feats.shape[1], None, 0.0,
+                                                      {"fp16": 0, "split": 1}[self.precision], _lib.ptr(out)),
+                       "b2_track_pair_cost")
+            cost[:, :] = out
         return cost
 
 

@@ -280,3 +280,26 @@ def test_distance_calls_from_the_persistent_workspace_equal_the_per_call_path():
     assert set(res[0]) == set(res[1]) and len(res[0]) == 15
     for k in res[0]:
         np.testing.assert_array_equal(res[0][k], res[1][k])
+
+
+def test_euclidean_nearest_neighbor_metric():
+    """NearestNeighborDistanceMetric('euclidean') (deep_sort/nn_matching.py:8-28,57-75,156-177): min over a track's gallery
+    rows of the squared euclidean distance, clamped at 0."""
+    from object_detection_tracking_b200.tracking import GpuNearestNeighborDistanceMetric
+    rng = np.random.default_rng(14)
+    D = 128
+    m = GpuNearestNeighborDistanceMetric("euclidean", 0.3, budget=4)
+    feats = rng.standard_normal((30, D)).astype(np.float32)
+    m.partial_fit(feats, [i % 6 for i in range(30)], list(range(6)))          # budget keeps the last 4 per target
+    q = rng.standard_normal((11, D)).astype(np.float32)
+    got = m.distance(q, [4, 0, 2])
+    ref = np.zeros((3, 11))
+    for r, t in enumerate([4, 0, 2]):
+        g = np.asarray(m.samples[t], dtype=np.float64)
+        assert len(g) == 4
+        d = (g * g).sum(1)[:, None] + (q.astype(np.float64) ** 2).sum(1)[None, :] - 2 * g @ q.astype(np.float64).T
+        ref[r] = np.maximum(0.0, d.min(axis=0))
+    assert got.shape == (3, 11) and got.dtype == np.float64
+    assert np.abs(got - ref).max() <= 5e-6 * np.abs(ref).max()
+    with pytest.raises(ValueError):
+        GpuNearestNeighborDistanceMetric("manhattan", 0.3)
