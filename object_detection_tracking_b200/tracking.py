@@ -50,17 +50,39 @@ class GpuNearestNeighborDistanceMetric(object):
         if self.metric == "cosine":
             cost[:, :] = cosine_cost(gallery, seg, feats, device=self.device, precision=self.precision)
         else:
-            # _nn_euclidean_distance (nn_matching.py:57-75): min over the gallery rows of the squared distance, clamped
-            # at 0 -- the track-pair cost with every detection as a one-row segment (one GEMM + segmented min)
-            from . import _lib
-            det_seg = np.arange(N + 1, dtype=np.int32)
-            out = np.zeros((T, N), dtype=np.float32)
-            _lib.check(_lib.load().b2_track_pair_cost(int(self.device), _lib.ptr(gallery), _lib.ptr(seg), T, _lib.ptr(feats),
-                                                      _lib.ptr(det_seg), N, feats.shape[1], None, 0.0,
-                                                      {"fp16": 0, "split": 1}[self.precision], _lib.ptr(out)),
-                       "b2_track_pair_cost")
-            cost[:, :] = out
+            cost[:, :] = euclidean_cost(gallery, seg, feats, device=self.device, precision=self.precision)
         return cost
+
+
+def euclidean_cost(gallery, seg, feats, device=0, precision="split"):
+    """_nn_euclidean_distance (nn_matching.py:57-75) for every (track, detection): min over the track's gallery rows of
+    the squared distance, clamped at 0 -- the track-pair cost with every detection as a one-row segment (one GEMM +
+    segmented min on the GPU).  float32 [T, N]."""
+    from . import _lib
+    gallery = np.ascontiguousarray(gallery, dtype=np.float32)
+    feats = np.ascontiguousarray(feats, dtype=np.float32)
+    seg = np.ascontiguousarray(seg, dtype=np.int32)
+    T, N = len(seg) - 1, len(feats)
+    det_seg = np.arange(N + 1, dtype=np.int32)
+    out = np.zeros((T, N), dtype=np.float32)
+    _lib.check(_lib.load().b2_track_pair_cost(int(device), _lib.ptr(gallery), _lib.ptr(seg), T, _lib.ptr(feats),
+                                              _lib.ptr(det_seg), N, feats.shape[1], None, 0.0,
+                                              {"fp16": 0, "split": 1}[precision], _lib.ptr(out)),
+               "b2_track_pair_cost")
+    return out
+
+
+def _metric_kind(metric):
+    """'cosine' / 'euclidean' of a NearestNeighborDistanceMetric-like object: ours carries `.metric`, the reference's
+    class only keeps the chosen function in `._metric` (nn_matching.py:123-129)."""
+    kind = getattr(metric, "metric", None)
+    if kind is None:
+        fn = getattr(metric, "_metric", None)
+        name = getattr(fn, "__name__", "")
+        kind = "euclidean" if "euclid" in name else "cosine"
+    if kind not in ("cosine", "euclidean"):
+        raise ValueError("Invalid metric; must be either 'euclidean' or 'cosine'")
+    return kind
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -133,6 +155,11 @@ class Tracker(object):
         self._h = None
         self._dim = None
         self._user_cost = cost_fn
+        if cost_fn is None and _metric_kind(metric) == "euclidean":
+            # the reference Tracker asks metric.distance() (tracker.py:98-104), so the metric kind is honoured there; the
+            # native cascade's built-in cost is the cosine one, the euclidean one is installed as its cost function
+            dev, prec = self.device, getattr(metric, "precision", precision)
+            self._user_cost = lambda gal, seg, dets: euclidean_cost(gal, seg, dets, device=dev, precision=prec)
         self._cb = None
         self._tracks = []
         self._stale = False

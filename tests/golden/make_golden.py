@@ -46,6 +46,20 @@ def cosine():
              dets=dets, cost=cost)
 
 
+def euclid():
+    """NearestNeighborDistanceMetric('euclidean') of the reference on signed features (nn_matching.py:5-28,57-75)."""
+    rng = np.random.default_rng(17)
+    T, N, D, budget = 9, 13, 128, 4
+    m = nn_matching.NearestNeighborDistanceMetric("euclidean", 0.3, budget)
+    feats = rng.standard_normal((60, D)).astype(np.float32)
+    targets = np.asarray([i % T for i in range(60)])
+    m.partial_fit(feats, targets, list(range(T)))
+    dets = rng.standard_normal((N, D)).astype(np.float32)
+    order = [4, 0, 2, 8, 1]
+    np.savez(os.path.join(HERE, "deepsort_euclid.npz"), feats=feats, targets=targets, dets=dets,
+             order=np.asarray(order), cost=m.distance(dets, order), budget=budget, T=T)
+
+
 def tracker_run():
     """8 frames of synthetic moving objects through the reference Tracker (this fork's defaults,
     tracker.py:40) -> per-frame (track_id, tlwh) of confirmed tracks."""

@@ -82,6 +82,14 @@ def test_nn_matching_restatement_matches_reference_golden(golden_dir):
     assert cost.dtype == np.float64
 
 
+def test_nn_matching_euclidean_restatement_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "deepsort_euclid.npz"))
+    m = nn_matching.NearestNeighborDistanceMetric("euclidean", 0.3, int(g["budget"]))
+    m.partial_fit(g["feats"], g["targets"], list(range(int(g["T"]))))
+    cost = m.distance(g["dets"], g["order"].tolist())
+    np.testing.assert_array_equal(cost, g["cost"])
+
+
 def test_oracle_forward_small_is_deterministic_and_shaped():
     from object_detection_tracking_b200.config import make_config
     from object_detection_tracking_b200.synth import synth_frame, synth_weights
