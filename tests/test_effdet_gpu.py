@@ -227,6 +227,39 @@ def test_backbone_5x5_stride2_and_wider_trunk():
     eng.close()
 
 
+def test_d7_full_size_matches_oracle():
+    """BASELINE configs[2]: EfficientDet-D7 (EfficientNet-b6 trunk, 8 BiFPN cells of 384 filters, 5-deep heads) at
+    1536x1536 on one 1080x1920 frame, whole-frame detect against the oracle (efficientdet_wrapper.py:40-61,367-474)."""
+    import json
+    import os
+    cfg, eng, out, ref, feats, img, scale, frame, _ = _full_case("efficientdet-d7", 1536, 1536, 1080, 1920)
+    try:
+        np.testing.assert_array_equal(eng.stage("image"), img)
+        rec = {"config": "C3", "final": len(out["final_probs"]), "final_ref": len(ref["final_probs"])}
+        rec["c_rel"] = [float(np.abs(eng.stage("c%d" % l) - feats[l].transpose(1, 2, 0)).max() / np.abs(feats[l]).max())
+                        for l in (3, 4, 5)]
+        rec["fpn_rel"] = [float(np.abs(eng.stage("fpn%d" % l) - ref["fpn"][l].transpose(1, 2, 0)).max() /
+                                max(1.0, np.abs(ref["fpn"][l]).max())) for l in range(3, 8)]
+        rec["cls_rel"] = [float(np.abs(eng.stage("cls%d" % l) - ref["cls_out"][l]).max() / max(1.0, np.abs(ref["cls_out"][l]).max()))
+                          for l in range(3, 8)]
+        n = min(rec["final"], rec["final_ref"])
+        rec["labels_equal"] = bool(np.array_equal(out["final_labels"][:n], ref["final_labels"][:n]))
+        rec["box_maxabs"] = float(np.abs(out["final_boxes"][:n] - ref["final_boxes"][:n]).max())
+        rec["prob_maxabs"] = float(np.abs(out["final_probs"][:n] - ref["final_probs"][:n]).max())
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(root, "gpurun_out", "baseline_parity.jsonl"), "a") as f:
+            f.write(json.dumps(rec) + "\n")
+        assert max(rec["c_rel"]) < 5e-5 and max(rec["fpn_rel"]) < 1e-4 and max(rec["cls_rel"]) < 1e-4, rec
+        assert rec["final"] == rec["final_ref"] > 0
+        np.testing.assert_array_equal(out["final_labels"], ref["final_labels"])
+        np.testing.assert_array_equal(out["levels"], ref["levels"])
+        assert rec["box_maxabs"] <= 1e-3 and rec["prob_maxabs"] <= 1e-5
+        assert np.abs(out["fpn_box_feat"] - ref["fpn_box_feat"]).max() <= 1e-4 * max(1.0, np.abs(ref["fpn_box_feat"]).max())
+    finally:
+        eng.close()
+
+
 def test_efficientdet_model_object_drop_in():
     # the reference call surface: models.get_model(config) -> EfficientDet; sess.run(fetches, feed_dict)
     from types import SimpleNamespace

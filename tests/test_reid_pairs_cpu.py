@@ -1,7 +1,7 @@
 """Multi-camera track-pair matching (BASELINE config 5, multi_video_reid.py:260-324, 486-534): the native trajectory
 distance and the assignment step against fixtures produced by the REFERENCE's own compute_spatial_dist /
 compute_feature_dist (tests/golden/make_golden_tmot.py: reid_pairs).  The feature distance itself is GPU work
-(b2_track_pair_cost; tests/test_zz_widen_gpu.py) -- here a float64 numpy checker stands in for it."""
+(b2_track_pair_cost; tests/test_widen_gpu.py) -- here a float64 numpy checker stands in for it."""
 import os
 
 import numpy as np

@@ -1,13 +1,12 @@
-"""GPU parity tests of engines written in a session WITHOUT GPU access (round 1, budget exhausted): they build new
-launch sequences (new tensor-map geometries on conv_tc_kernel), so they are opt-in until they have passed once on a B200:
-    B2_RUN_UNVERIFIED=1 python -m pytest tests/test_zz_unverified_gpu.py -m gpu -x -q
-After the first green run the `unverified` marker is to be removed (the tests then join the default -m gpu suite)."""
+"""GPU parity of the two engines that build their own launch sequences on conv_tc_kernel beyond the detector: the vehicle
+ReID ResNet-101 (torchreid/models/resnet.py:441-455) against reference-generated activations (resnet101_reid.npz), and the
+Mask-RCNN head (--add_mask, models.py:934-961,1173-1199) against oracle.frcnn.maskrcnn_head.  First B200 run: round 2, 5/5 green."""
 import os
 
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.unverified]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")

@@ -1,7 +1,7 @@
 """Native TMOT / JDE association (csrc/tmot.cpp, host code) against fixtures produced by the REFERENCE's own
 tmot/multitracker.py + tmot/matching.py + tmot/kalman_filter.py (tests/golden/make_golden_tmot.py; lap / cython_bbox /
 numba.jit stubbed there as documented).  The embedding distance is supplied by a float64 numpy checker here; the product
-path computes it with b2_distance_matrix on the GPU (tests/test_zz_widen_gpu.py)."""
+path computes it with b2_distance_matrix on the GPU (tests/test_widen_gpu.py)."""
 import os
 
 import numpy as np

@@ -1,19 +1,13 @@
 """GPU parity of the section-8f widening that composes already-verified kernels (the tensor-core GEMM behind
 b2_distance_matrix) with small new ones: TMOT embedding distance, the JDE tracker with its embedding cost on the GPU, and
-the multi-camera track-pair cost (b2_track_pair_cost).  NOTE: written in a session whose GPU budget was exhausted -- these
-tests had not yet run on a B200 when they were committed (the file sorts last so that an issue here cannot mask the
-verified suites)."""
+the multi-camera track-pair cost (b2_track_pair_cost), device-side frame resize, given-box features, the detect -> track
+loop.  First B200 run: round 2, 12/12 green (gpurun_out/widen_tests.log -> profiles/r2_first_gpu_call.txt)."""
 import os
 
 import numpy as np
 import pytest
 
-# Non-strict xfail: these tests compose kernels that are verified (the GEMM behind b2_distance_matrix) with small new
-# ones and have no hang potential of their own, so they RUN in the default -m gpu suite -- a pass is reported as XPASS,
-# a numerical surprise as XFAIL -- but they cannot turn the suite red before their first run on a B200.  Remove the
-# xfail mark after that run.
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first run on a B200 pending (written after the round-1 GPU budget was spent)")]
+pytestmark = pytest.mark.gpu
 
 
 def cdist64(a, b):
