@@ -201,6 +201,8 @@ int b2_jde_create(b2_jde** out, int device, double conf_thres, double track_max_
 void b2_jde_destroy(b2_jde* trk);
 int b2_jde_set_cost_fn(b2_jde* trk, b2_appearance_cost_fn fn, void* user);
 int b2_jde_reset(b2_jde* trk);
+/* zeroes only the id counter `trk` shares with its group (multitracker.py:215: reset() of ANY tracker sets BaseTrack._count = 0) */
+int b2_jde_reset_ids(b2_jde* trk);
 int b2_jde_update(b2_jde* trk, const double* tlwh, const double* conf, const float* features, int n);
 int b2_jde_get_tracks(b2_jde* trk, int which, int cap, int32_t* ids, int32_t* state, int32_t* is_activated,
                       int32_t* frame_id, int32_t* start_frame, int32_t* tracklet_len, double* tlwh, double* det_tlwh,
@@ -220,6 +222,10 @@ int b2_reid_create_model(b2_reid** out, int device, int batch, int precision, in
 void b2_reid_destroy(b2_reid* ctx);
 int b2_reid_load_weights(b2_reid* ctx, const char* const* names, const float* const* data, const int64_t* numel, int n);
 int b2_reid_embed(b2_reid* ctx, const uint8_t* crops_host, int n, float* feats_host);
+/* Same, with the [n, feat_dim] features left in device memory of the context's GPU (`feats_dev`: e.g. this camera's slice of
+ * the gallery buffer the NCCL all-gather of config 5 sends, multi_video_reid.py:448-476) -- a gallery never crosses PCIe. */
+int b2_reid_embed_dev(b2_reid* ctx, const uint8_t* crops_host, int n, float* feats_dev);
+int b2_reid_feat_dim(b2_reid* ctx);   /* 512 (osnet_x1_0) / 2048 (resnet101) */
 int b2_reid_num_launches(b2_reid* ctx);
 /* Stage-addressable activation of the last pass as fp32 NHWC (parity tests): "conv1", "maxpool", "conv2.0", ... */
 int b2_reid_get_activation(b2_reid* ctx, const char* name, float* dst_host, int64_t capacity_bytes, int64_t shape[4]);

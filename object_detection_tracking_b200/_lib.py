@@ -81,6 +81,7 @@ SYMBOLS = [
     ("b2_jde_destroy", None, [c_void_p]),
     ("b2_jde_set_cost_fn", c_int, [c_void_p, c_void_p, c_void_p]),
     ("b2_jde_reset", c_int, [c_void_p]),
+    ("b2_jde_reset_ids", c_int, [c_void_p]),
     ("b2_jde_update", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     ("b2_jde_get_tracks", c_int, [c_void_p, c_int, c_int] + [c_void_p] * 12),
     ("b2_reid_create", c_int, [POINTER(c_void_p), c_int, c_int, c_int]),
@@ -88,6 +89,8 @@ SYMBOLS = [
     ("b2_reid_destroy", None, [c_void_p]),
     ("b2_reid_load_weights", c_int, [c_void_p, POINTER(c_char_p), POINTER(c_void_p), POINTER(c_int64), c_int]),
     ("b2_reid_embed", c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    ("b2_reid_embed_dev", c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    ("b2_reid_feat_dim", c_int, [c_void_p]),
     ("b2_reid_num_launches", c_int, [c_void_p]),
     ("b2_reid_get_activation", c_int, [c_void_p, c_char_p, c_void_p, c_int64, POINTER(c_int64)]),
     ("b2_effdet_create", c_int, [POINTER(c_void_p), POINTER(B2EffdetConfig), c_int]),

@@ -32,20 +32,22 @@ namespace b2 {
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;                 // fp16 elements = one 128-byte swizzle row
-constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
+constexpr int kBlockK = 64;                 // fp16 elements = one 128-byte swizzle row (p.bk: 64, or 32 = 64-byte rows)
+constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB at bk = 64
 constexpr int kUmmaK = 16;
 constexpr int kEpiHalves = 2;               // column halves of a tile handled by separate epilogue warp quartets
 constexpr int kEpiWarps = 4 * kEpiHalves;   // warps 4..: TMEM lane quarter = warp & 3, column half = (warp - 4) >> 2
 constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kTmemCols = 512;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 constexpr int kSmemBudget = 224 * 1024;     // pipeline stages + epilogue staging (alignment slack and barriers on top)
 
 struct ConvTcParams {
   int M, Ho, Wo, HoWo;
   int stride, dil, lower_h, lower_w;
   int S, cin_blocks, num_kb;
+  int bk;            // K elements per pipeline stage: 64 (128-byte swizzle rows) or 32 (64-byte rows, twice the stages)
+  uint32_t a_bytes;  // bytes of one A plane per stage = 128 * bk * 2
   int block_n, num_n_blocks, num_tiles;
   int a_mode;   // 0 = A is a plain [M][Cin] matrix (2D tiled TMA), 1 = im2col TMA
   uint32_t idesc;
@@ -64,6 +66,7 @@ struct ConvTcParams {
   int acc_ring;      // ACC: chunk accumulators in the TMEM ring (2 for 128-column tiles, 6 for 64-column tiles)
   int acc_stride;    // ACC: TMEM columns per accumulator (ring at 0.., the two correction accumulators after it)
   int dbg_nodrain;   // perf experiment only (wrong results): skip the TMEM reads of the ACC drain
+  int l2_prefetch;   // experiment: the producer prefetches the next tile's A operand (and residual tile) into L2
   int epi_mode;      // 0 = direct global loads/stores per thread, 1 = TMA-staged (residual in, result out)
   int epi_grp;       // staged: 16-column chunks per fence / barrier / store group (1 or 2)
   int epi_slots;     // staged: group slots in each column half's staging ring (2, or 3 when a residual is prefetched)
@@ -82,16 +85,18 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 
 // 16 consecutive output channels of one pixel (v = accumulator value): bias, residual, activation, store
 // (fp16 hi/lo planes or fp32) straight to global memory.
-template <bool SPLIT>
+template <bool SPLIT, bool BIAS = true>
 __device__ __forceinline__ void epilogue_chunk16(const ConvTcParams& p, float (&v)[16], size_t opix, size_t rpix, int n) {
-  const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+  if (BIAS) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float4 b = __ldg(b4 + j);
-    v[4 * j + 0] += b.x;
-    v[4 * j + 1] += b.y;
-    v[4 * j + 2] += b.z;
-    v[4 * j + 3] += b.w;
+    for (int j = 0; j < 4; ++j) {
+      float4 b = __ldg(b4 + j);
+      v[4 * j + 0] += b.x;
+      v[4 * j + 1] += b.y;
+      v[4 * j + 2] += b.z;
+      v[4 * j + 3] += b.w;
+    }
   }
   if (p.res_hi != nullptr) {
     const uint4* r4 = reinterpret_cast<const uint4*>(p.res_hi + rpix * p.ldr + n);
@@ -126,7 +131,7 @@ __device__ __forceinline__ void epilogue_chunk16(const ConvTcParams& p, float (&
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
   } else if (p.relu == 2) {   // swish: x * sigmoid(x)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));   // MUFU ex2 + rcp: ~2 ulp
+    for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], 1.f / (1.f + expf(-v[j])));   // x * sigmoid(x) as the other kernels compute it (the MUFU-only form cost ~3 ulp per swish: D7 c5 off by 3e-5 at 1536^2)
   }
   if (p.out_f32 != nullptr) {
     float4* o = reinterpret_cast<float4*>(p.out_f32 + opix * p.ldc + n);
@@ -155,17 +160,19 @@ __device__ __forceinline__ void epilogue_chunk16(const ConvTcParams& p, float (&
 
 // Same math on a chunk whose residual sits in (and whose result goes back to) a swizzled shared-memory staging box:
 // hi0 / hi1 (lo0 / lo1 for the lo plane) point at this thread's two 16-byte cells (channels 0-7 and 8-15 of the chunk).
-template <bool SPLIT>
+template <bool SPLIT, bool BIAS = true>
 __device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, float (&v)[16], uint4* hi0, uint4* hi1,
                                                       uint4* lo0, uint4* lo1, int n, bool has_res, bool has_res_lo) {
-  const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+  if (BIAS) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float4 b = __ldg(b4 + j);
-    v[4 * j + 0] += b.x;
-    v[4 * j + 1] += b.y;
-    v[4 * j + 2] += b.z;
-    v[4 * j + 3] += b.w;
+    for (int j = 0; j < 4; ++j) {
+      float4 b = __ldg(b4 + j);
+      v[4 * j + 0] += b.x;
+      v[4 * j + 1] += b.y;
+      v[4 * j + 2] += b.z;
+      v[4 * j + 3] += b.w;
+    }
   }
   if (has_res) {
     uint4 r[2] = {*hi0, *hi1};
@@ -198,7 +205,7 @@ __device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, flo
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
   } else if (p.relu == 2) {   // swish: x * sigmoid(x)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));   // MUFU ex2 + rcp: ~2 ulp
+    for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], 1.f / (1.f + expf(-v[j])));   // x * sigmoid(x) as the other kernels compute it (the MUFU-only form cost ~3 ulp per swish: D7 c5 off by 3e-5 at 1536^2)
   }
   uint32_t hi[8];
 #pragma unroll
@@ -329,8 +336,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const uint32_t tmem_base = *tmem_holder;
   if (tmem_base != 0) __trap();   // the MMA issuer addresses TMEM from column 0 / lane 0 (whole-TMEM allocation)
 
-  const uint32_t a_lo_off = kABytes;
-  const uint32_t b_hi_off = SPLIT ? 2 * kABytes : kABytes;
+  const uint32_t a_lo_off = p.a_bytes;
+  const uint32_t b_hi_off = SPLIT ? 2 * p.a_bytes : p.a_bytes;
   const uint32_t b_lo_off = b_hi_off + p.b_bytes;
   // accumulator stage s: acc0 at column s*256, acc1 (split) at s*256 + 128
   const uint32_t acc_stage_cols = 256;
@@ -360,6 +367,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           ch = p.lower_h + pp * p.stride;
           cw = p.lower_w + qq * p.stride;
         }
+        if (p.l2_prefetch) {
+          // next tile of this CTA: pull its A operand (every K-block, both planes) and its residual tile into L2 while
+          // this tile is being processed, so that the stage loads later hit L2 instead of HBM
+          const int nt = tile + gridDim.x;
+          if (nt < p.num_tiles) {
+            const int nm_blk = nt / p.num_n_blocks;
+            const int nn0 = (nt - nm_blk * p.num_n_blocks) * p.block_n;
+            const int nm0 = nm_blk * kBlockM;
+            if (nm_blk != m_blk || p.l2_prefetch > 1) {
+              int nimg = 0, nch = 0, ncw = 0;
+              if (p.a_mode == 1) {
+                nimg = nm0 / p.HoWo;
+                const int rem = nm0 - nimg * p.HoWo;
+                const int pp = rem / p.Wo;
+                nch = p.lower_h + pp * p.stride;
+                ncw = p.lower_w + (rem - pp * p.Wo) * p.stride;
+              }
+              if (elect_one()) {
+                int ptap = 0, pcb = 0;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                  if (p.a_mode == 1) {
+                    const int r = ptap / p.S;
+                    const int s = ptap - r * p.S;
+                    tma_prefetch_im2col_4d(&tmA_hi, pcb * p.bk, ncw, nch, nimg, static_cast<uint16_t>(s * p.dil),
+                                           static_cast<uint16_t>(r * p.dil));
+                    if (SPLIT) tma_prefetch_im2col_4d(&tmA_lo, pcb * p.bk, ncw, nch, nimg, static_cast<uint16_t>(s * p.dil),
+                                                      static_cast<uint16_t>(r * p.dil));
+                  } else {
+                    tma_prefetch_2d(&tmA_hi, pcb * p.bk, nm0);
+                    if (SPLIT) tma_prefetch_2d(&tmA_lo, pcb * p.bk, nm0);
+                  }
+                  if (++pcb == p.cin_blocks) {
+                    pcb = 0;
+                    ++ptap;
+                  }
+                }
+              }
+              __syncwarp();
+            }
+            if (p.epi_mode == 1 && p.res_hi != nullptr) {
+              const int ebox = p.epi_wide ? 32 : 16;
+              if (elect_one()) {
+                for (int c = 0; c < p.block_n; c += ebox) {
+                  tma_prefetch_2d(&tmR_hi, nn0 + c, nm0);
+                  if (SPLIT && p.res_lo != nullptr) tma_prefetch_2d(&tmR_lo, nn0 + c, nm0);
+                }
+              }
+              __syncwarp();
+            }
+          }
+        }
         int tap = 0, cb = 0;   // K-block = (filter tap, 64-channel block)
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -371,14 +429,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               const int s = tap - r * p.S;
               const uint16_t ow = static_cast<uint16_t>(s * p.dil);
               const uint16_t oh = static_cast<uint16_t>(r * p.dil);
-              tma_load_im2col_4d(st, &tmA_hi, &full_bar[stage], cb * kBlockK, cw, ch, img, ow, oh);
-              if (SPLIT) tma_load_im2col_4d(st + a_lo_off, &tmA_lo, &full_bar[stage], cb * kBlockK, cw, ch, img, ow, oh);
+              tma_load_im2col_4d(st, &tmA_hi, &full_bar[stage], cb * p.bk, cw, ch, img, ow, oh);
+              if (SPLIT) tma_load_im2col_4d(st + a_lo_off, &tmA_lo, &full_bar[stage], cb * p.bk, cw, ch, img, ow, oh);
             } else {
-              tma_load_2d(st, &tmA_hi, &full_bar[stage], cb * kBlockK, m0);
-              if (SPLIT) tma_load_2d(st + a_lo_off, &tmA_lo, &full_bar[stage], cb * kBlockK, m0);
+              tma_load_2d(st, &tmA_hi, &full_bar[stage], cb * p.bk, m0);
+              if (SPLIT) tma_load_2d(st + a_lo_off, &tmA_lo, &full_bar[stage], cb * p.bk, m0);
             }
-            tma_load_2d(st + b_hi_off, &tmB_hi, &full_bar[stage], kb * kBlockK, n0);
-            if (SPLIT) tma_load_2d(st + b_lo_off, &tmB_lo, &full_bar[stage], kb * kBlockK, n0);
+            tma_load_2d(st + b_hi_off, &tmB_hi, &full_bar[stage], kb * p.bk, n0);
+            if (SPLIT) tma_load_2d(st + b_lo_off, &tmB_lo, &full_bar[stage], kb * p.bk, n0);
           }
           __syncwarp();
           if (++cb == p.cin_blocks) {
@@ -409,7 +467,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       // shared-memory matrix descriptor (K-major, 128-byte swizzle): low word = start address >> 4 (14 bits) | LBO 1 << 16,
       // high word = SBO 1024 >> 4 | descriptor version 1 << 14 | SWIZZLE_128B 2 << 29; offsets inside the stage and the
       // K advance (32 bytes per UMMA_K) add to the address field without carry (all of shared memory is < 2^18 bytes)
-      constexpr uint64_t kDescHi = static_cast<uint64_t>((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+      // (bk = 32: rows of 64 bytes, SBO 512, layout type 4 = SWIZZLE_64B; the K advance of 32 bytes per UMMA_K is the same)
+      const uint64_t kDescHi = static_cast<uint64_t>(p.bk == 64 ? ((1024u >> 4) | (1u << 14) | (2u << 29))
+                                                                 : ((512u >> 4) | (1u << 14) | (4u << 29))) << 32;
+      const int ksteps = p.bk / kUmmaK;
       // this CTA owns the whole TMEM of its SM (512 columns, one CTA per SM): the allocation starts at column 0, lane 0
       // (checked after the allocation), so the accumulator addresses are plain constants here
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -436,7 +497,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              const uint32_t ko = k * (kUmmaK * 2 >> 4);   // 32 bytes along K inside the 128B swizzle row, in 16-byte units
+              if (k >= ksteps) break;
+              const uint32_t ko = k * (kUmmaK * 2 >> 4);   // 32 bytes along K inside the swizzle row, in 16-byte units
               const uint64_t a_hi = kDescHi | (d_a_hi + ko);
               const uint64_t b_hi = kDescHi | (d_b_hi + ko);
               const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
@@ -484,6 +546,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ring, own named barrier, own elected TMA thread); together they halve the time per tile of the epilogue, which
     // bounds the short-K layers and -- in ACC mode, where the same warps must keep draining chunk accumulators --
     // stalls the MMA issuer for as long as a tile's output stage takes.
+#ifdef B2_BIAS_INIT
+    // ACC: the running sums start from the bias (loaded while the first chunk is still being multiplied) instead of
+    // zero, which takes 4 dependent L1/L2 loads + 16 adds per chunk out of the output stage
+    constexpr bool kBiasInChunk = !ACC;
+#else
+    constexpr bool kBiasInChunk = true;
+#endif
     const int ew = warp & 3;
     const int hf = (warp - 4) >> 2;
     const int row = ew * 32 + lane;
@@ -573,7 +642,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       auto chunk_out = [&](int c, float (&v)[16]) {
         const int n = n0 + (c_beg + c) * 16;
         if (!staged) {
-          if (valid) epilogue_chunk16<SPLIT>(p, v, opix, rpix, n);
+          if (valid) epilogue_chunk16<SPLIT, kBiasInChunk>(p, v, opix, rpix, n);
           return;
         }
         const int u = grp == 2 ? (c & 1) : 0;      // position inside the group
@@ -600,7 +669,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             c1 = (1 ^ sw) << 4;
             lo_off = kEpiPlaneBytes;
           }
-          epilogue_chunk16_smem<SPLIT>(p, v, reinterpret_cast<uint4*>(hp + c0), reinterpret_cast<uint4*>(hp + c1),
+          epilogue_chunk16_smem<SPLIT, kBiasInChunk>(p, v, reinterpret_cast<uint4*>(hp + c0), reinterpret_cast<uint4*>(hp + c1),
                                        reinterpret_cast<uint4*>(hp + lo_off + c0), reinterpret_cast<uint4*>(hp + lo_off + c1), n,
                                        has_res, res_lo);
         }
@@ -638,8 +707,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
       if (ACC) {
         float sums[kAccMaxChunks * 16];
+        if (kBiasInChunk) {
 #pragma unroll
-        for (int i = 0; i < kAccMaxChunks * 16; ++i) sums[i] = 0.0f;
+          for (int i = 0; i < kAccMaxChunks * 16; ++i) sums[i] = 0.0f;
+        } else {
+#pragma unroll
+          for (int c = 0; c < kAccMaxChunks; ++c) {
+            if (c < my_n) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + (c_beg + c) * 16);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 b = __ldg(b4 + j);
+                sums[c * 16 + 4 * j + 0] = b.x;
+                sums[c * 16 + 4 * j + 1] = b.y;
+                sums[c * 16 + 4 * j + 2] = b.z;
+                sums[c * 16 + 4 * j + 3] = b.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) sums[c * 16 + i] = 0.0f;
+            }
+          }
+        }
         const int nq = (p.num_kb + p.acc_kb - 1) / p.acc_kb;
         for (int q = 0; q < nq; ++q) {
           const int cbuf = ecbuf;
@@ -656,6 +745,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
         acc_fold<true>(sums, tmem_base + lane_off + (p.acc_ring + as) * p.acc_stride + c_beg * 16, my_n, &tmem_empty[as], lane);
+#ifdef B2_ROLL_OUT
+        // one copy of the output-stage body, executed my_n times: unrolled over the (statically indexed) running sums it
+        // is ~37 KB of straight-line code per tile, and ncu's stall sampling showed the epilogue warps waiting for
+        // instruction fetch (no_inst) for a third of the output stage
+#pragma unroll 1
+        for (int c = 0; c < my_n; ++c) {
+          float v[16];
+#pragma unroll
+          for (int k = 0; k < kAccMaxChunks; ++k) {
+            if (c == k) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = sums[(ACC ? k : 0) * 16 + i];
+            }
+          }
+          chunk_out(c, v);
+        }
+#else
 #pragma unroll
         for (int c = 0; c < kAccMaxChunks; ++c) {
           if (c < my_n) {
@@ -665,6 +771,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             chunk_out(c, v);
           }
         }
+#endif
       } else {
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
@@ -781,6 +888,13 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
                       int num_sms, int force_a_mode) {
   B2_CHECK(conv_tc_init() == 0, "conv_tc_init failed");
   B2_CHECK(d.Cin % kBlockK == 0, "conv_tc: Cin must be a multiple of 64");
+  // experiment hook (round 2): half-size pipeline stages (32 K-elements, 64-byte swizzle rows) in split precision.  A
+  // split-precision stage of 64 K-elements is 64 KB, so only 2-3 stages fit beside the epilogue ring and the operand
+  // latency (TMA issue -> data: 1-2 us under load) is not covered; half stages keep the same bytes resident with twice
+  // the stages in flight (B2_BK32=1: every split layer, =2: only layers with a residual ring)
+  int bk = kBlockK;
+  if (const char* e = getenv("B2_BK32"))
+    if (split && (atoi(e) == 1 || (atoi(e) == 2 && io.res_hi != nullptr))) bk = 32;
   B2_CHECK(w.Cout_pad % 16 == 0, "conv_tc: Cout_pad must be a multiple of 16");
   B2_CHECK(w.K == d.R * d.S * d.Cin, "conv_tc: packed weight K mismatch");
   B2_CHECK(!split || (io.in_lo && w.w_lo), "conv_tc: split precision needs lo planes");
@@ -796,7 +910,9 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   p.lower_h = -d.pad_t;
   p.lower_w = -d.pad_l;
   p.S = d.S;
-  p.cin_blocks = d.Cin / kBlockK;
+  p.bk = bk;
+  p.a_bytes = static_cast<uint32_t>(kBlockM) * bk * 2;
+  p.cin_blocks = d.Cin / bk;
   p.num_kb = d.R * d.S * p.cin_blocks;
   p.block_n = pick_block_n(w.Cout_pad, split);
   // short-K layers in split precision (K <= 256: at most four accumulation chunks per tile) are bound by the output
@@ -816,8 +932,8 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   const int num_m_blocks = (p.M + kBlockM - 1) / kBlockM;
   p.num_tiles = num_m_blocks * p.num_n_blocks;
   p.idesc = make_idesc_f16(kBlockM, p.block_n);
-  p.b_bytes = static_cast<uint32_t>(p.block_n) * kBlockK * 2;
-  p.stage_bytes = (kABytes + p.b_bytes) * (split ? 2 : 1);
+  p.b_bytes = static_cast<uint32_t>(p.block_n) * bk * 2;
+  p.stage_bytes = (p.a_bytes + p.b_bytes) * (split ? 2 : 1);
   // TMA-staged epilogue: fp16 plane output with a 1:1 row mapping (no placement offset, no shifted residual)
   {
     const bool one_to_one = d.off_h == 0 && d.off_w == 0 && d.out_H == Ho && d.out_W == Wo;
@@ -876,17 +992,20 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   pl->split = split;
   // accurate accumulation: on by default in split precision when K spans more than one chunk
   p.dbg_nodrain = getenv("B2_ACC_NODRAIN") != nullptr;
+  p.l2_prefetch = getenv("B2_L2_PREFETCH") ? atoi(getenv("B2_L2_PREFETCH")) : 0;
   p.acc_kb = d.acc_kb > 0 ? d.acc_kb : kAccChunkKb;
   if (const char* e = getenv("B2_ACC_KB")) p.acc_kb = atoi(e) > 0 ? atoi(e) : kAccChunkKb;   // experiment hook
+  const int kb_per_64 = kBlockK / bk;   // acc_kb counts 64-element K-blocks in the interface; the kernel counts stages
   // experiment hook (round 2): two K-blocks per chunk on the K <= 256 layers only.  A 4-K-block tile then has two
   // chunks = exactly the ring, so the MMA issuer can finish tile i+1 while the epilogue warps are still in the output
   // stage of tile i (with one K-block per chunk it stalls after two of four), and the drains per tile halve; costs
   // 8 instead of 4 truncating accumulation steps on those layers (all layers at 2: boxes 1.07e-3 px instead of 7.3e-4)
-  if (const char* e = getenv("B2_ACC_KB_SHORTK")) if (p.num_kb <= 4 && atoi(e) > 0) p.acc_kb = atoi(e);
+  if (const char* e = getenv("B2_ACC_KB_SHORTK")) if (p.num_kb <= 4 * kb_per_64 && atoi(e) > 0) p.acc_kb = atoi(e);
+  p.acc_kb *= kb_per_64;
   pl->acc = split && d.acc_kb >= 0 && p.num_kb > p.acc_kb && getenv("B2_NO_ACC") == nullptr;
   p.acc_stride = p.block_n == 64 ? 64 : 128;
   p.acc_ring = p.block_n == 64 ? kAccRingMax : 2;   // (ring + 2 correction accumulators) * stride <= 512 columns
-  if (const char* e = getenv("B2_ACC_MIN_KB")) pl->acc = pl->acc && p.num_kb > atoi(e);   // experiment hook
+  if (const char* e = getenv("B2_ACC_MIN_KB")) pl->acc = pl->acc && p.num_kb > atoi(e) * kb_per_64;   // experiment hook
   pl->grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   pl->smem_bytes = static_cast<size_t>(p.num_stages) * p.stage_bytes + epi_bytes + 1024 /*align*/ + 512 /*barriers*/;
   const int in_ld = d.in_ld > 0 ? d.in_ld : d.Cin;
@@ -898,6 +1017,7 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
     p.a_mode = force_a_mode;
   }
   const size_t in_bytes = static_cast<size_t>(d.B) * d.in_pitch_H * d.in_pitch_W * in_ld * 2;
+  const CUtensorMapSwizzle op_swz = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   for (int plane = 0; plane < (split ? 2 : 1); ++plane) {
     CUtensorMap* mA = plane == 0 ? &pl->tmA_hi : &pl->tmA_lo;
     CUtensorMap* mB = plane == 0 ? &pl->tmB_hi : &pl->tmB_lo;
@@ -905,7 +1025,7 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
     const __half* b = plane == 0 ? w.w_hi : w.w_lo;
     if (p.a_mode == 0) {
       if (encode_2d(mA, a, d.Cin, static_cast<uint64_t>(d.B) * d.in_H * d.in_W, static_cast<uint64_t>(in_ld) * 2,
-                    kBlockK, kBlockM))
+                    bk, kBlockM, op_swz))
         return -1;
     } else {
       cuuint64_t dims[4] = {static_cast<cuuint64_t>(d.Cin), static_cast<cuuint64_t>(d.in_W),
@@ -918,8 +1038,8 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
       int upper[2] = {d.pad_r - (d.S - 1) * d.dil, d.pad_b - (d.R - 1) * d.dil};
       cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(d.stride), static_cast<cuuint32_t>(d.stride), 1};
       CUresult r = g_encode_im2col(mA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(a), dims, strides,
-                                   lower, upper, kBlockK, kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   lower, upper, bk, kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   op_swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeIm2col failed: " + std::to_string(static_cast<int>(r)) + " (Cin=" +
@@ -928,7 +1048,7 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
       }
       small_tensor_fixup(mA, in_bytes);
     }
-    if (encode_2d(mB, b, w.K, w.Cout_pad, static_cast<uint64_t>(w.K) * 2, kBlockK, p.block_n)) return -1;
+    if (encode_2d(mB, b, w.K, w.Cout_pad, static_cast<uint64_t>(w.K) * 2, bk, p.block_n, op_swz)) return -1;
   }
   if (!split) {
     pl->tmA_lo = pl->tmA_hi;

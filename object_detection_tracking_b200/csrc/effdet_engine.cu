@@ -152,9 +152,15 @@ EConv* add_pw(b2_effdet* c, const std::string& wname, const std::string& biasnam
   ConvDesc& d = L->d;
   d.B = 1; d.in_H = in.H; d.in_W = in.W; d.Cin = in.C; d.in_pitch_H = in.H; d.in_pitch_W = in.W; d.in_ld = in.C;
   d.Cout = cout_real; d.relu = act;
-  // chunked re-accumulation (conv_tc ACC) only for long reductions: up to K = 512 the truncation bias of the tensor-core
-  // accumulator stays far inside the parity bar and the per-K-block drains would dominate these short-K layers
-  d.acc_kb = in.C <= 512 ? -1 : 0;
+  // chunked re-accumulation (conv_tc ACC) on every layer with more than one K-block.  Round 1 switched it off up to
+  // K = 512 for speed; at D7 depth (EfficientNet-b6: 45 blocks, then 8 BiFPN cells and 5-deep heads at 1536^2) the
+  // truncation bias of up to 32 tensor-core accumulation steps per layer then compounds to 3e-5 relative on c5 -- six
+  // times the rounding noise of a float32 evaluation -- and boxes leave the 1e-3 px bar.  B2_EFFDET_ACC_MIN_K restores
+  // a threshold for throughput experiments.
+  {
+    static const int min_k = getenv("B2_EFFDET_ACC_MIN_K") ? atoi(getenv("B2_EFFDET_ACC_MIN_K")) : 0;
+    d.acc_kb = in.C <= min_k ? -1 : 0;
+  }
   d.out_H = in.H; d.out_W = in.W; d.ldc = out_f32 ? ldc32 : out.C;
   L->w.Cout_pad = pad16(cout_real);
   L->w.K = in.C;

@@ -321,13 +321,19 @@ int build_plan(b2_ctx* c) {
   // ---- input + stem + pool (phase 0) ----
   c->img_bytes = static_cast<size_t>(B) * H * W * 3 * (cfg.input_dtype == 1 ? 1 : 4);
   c->img = c->alloc<uint8_t>(c->img_bytes);
-  B2_CHECK(c->alloc_planes(c->stem_u, B, c->c1h + 3, c->c1w, 64), "alloc stem operand");
+  // compact stem operand [B][c1h + 3][c1w + 3][16]; conv0 reads 64-channel pixels out of it with a pixel stride of 16 (stem.cu)
+  B2_CHECK(c->alloc_planes(c->stem_u, B, c->c1h + 3, c->c1w + 3, 16), "alloc stem operand");
   B2_CHECK(c->alloc_planes(c->c1, B, c->c1h, c->c1w, 64), "alloc c1");
   B2_CHECK(c->alloc_planes(c->pool, B, c->ch[0], c->cw[0], 64), "alloc pool");
   c->steps.push_back({0, 1, nullptr});
   // conv0 as a 4x1 VALID conv over the packed operand (see stem.cu), BN + ReLU in the epilogue
-  add_conv(c, 0, "conv0", c->stem_u, c->c1h + 3, c->c1w, 4, 1, 1, 0, 0, 0, 0, 64, true, false, true, c->c1, 0, 0,
-           nullptr, 0, nullptr, 0, 5, 1);
+  {
+    Planes view = c->stem_u;
+    view.C = 64;                       // one GEMM pixel = 4 consecutive operand pixels
+    Layer* L0 = add_conv(c, 0, "conv0", view, c->c1h + 3, c->c1w, 4, 1, 1, 0, 0, 0, 0, 64, true, false, true, c->c1, 0, 0,
+                         nullptr, 0, nullptr, 0, 5, 1);
+    L0->d.in_ld = 16;
+  }
   c->steps.push_back({0, 2, nullptr});
   reg_planes(c, "c1", c->c1);
   reg_planes(c, "pool", c->pool);
@@ -622,8 +628,8 @@ int run_step(b2_ctx* c, const b2_ctx::Step& s) {
       if (cfg.conv_impl == 0) return conv_tc_launch(s.layer->plan, st);
       return conv_simt_launch(s.layer->d, s.layer->w, s.layer->io, c->split, st);
     case 1:
-      return stem_pack_launch(c->img, cfg.input_dtype == 1, cfg.batch, cfg.height, cfg.width, c->stem_u.hi,
-                              c->stem_u.lo, c->stem_u.H, c->stem_u.W, 0, st);
+      return stem_pack16_launch(c->img, cfg.input_dtype == 1, cfg.batch, cfg.height, cfg.width, c->stem_u.hi,
+                                c->stem_u.lo, c->stem_u.H, c->stem_u.W, st);
     case 2:
       return maxpool_launch(c->c1.hi, c->c1.lo, cfg.batch, c->c1h, c->c1w, 64, c->pool.hi, c->pool.lo, c->ch[0],
                             c->cw[0], st);
@@ -675,9 +681,9 @@ int run_step_half(b2_ctx* c, const b2_ctx::Step& s, int h, cudaStream_t st) {
     case 0:
       return conv_tc_launch(s.layer->part_plan[h], st);
     case 1:
-      return stem_pack_launch(static_cast<const uint8_t*>(c->img) + static_cast<size_t>(h) * (c->img_bytes / c->nsplit),
-                              cfg.input_dtype == 1, hb, cfg.height, cfg.width, c->stem_u.hi + off(c->stem_u),
-                              lo(c->stem_u), c->stem_u.H, c->stem_u.W, 0, st);
+      return stem_pack16_launch(static_cast<const uint8_t*>(c->img) + static_cast<size_t>(h) * (c->img_bytes / c->nsplit),
+                                cfg.input_dtype == 1, hb, cfg.height, cfg.width, c->stem_u.hi + off(c->stem_u),
+                                lo(c->stem_u), c->stem_u.H, c->stem_u.W, st);
     case 2:
       return maxpool_launch(c->c1.hi + off(c->c1), lo(c->c1), hb, c->c1h, c->c1w, 64, c->pool.hi + off(c->pool),
                             lo(c->pool), c->ch[0], c->cw[0], st);
@@ -815,14 +821,14 @@ int load_layer(b2_ctx* c, Layer* L, const WeightSet& ws) {
       }
   } else if (L->kind == 5) {
     // stem: reference HWIO [7,7,3,64] re-indexed for the packed operand (stem.cu):
-    // W'[o][r][s*12 + ry*6 + sx*3 + c] = W[2r+ry][2s+sx][c][o]
+    // W'[o][r][s*16 + ry*6 + sx*3 + c] = W[2r+ry][2s+sx][c][o]   (12 real + 4 zero channels per width tap s)
     const float* w = ws.get(L->name + "/W", 7 * 7 * 3 * 64);
     if (!w || bn_fold(ws, L->name, Cout, scale, shift)) return -1;
     for (int r = 0; r < 4; ++r)
-      for (int ch = 0; ch < 48; ++ch) {
-        const int s4 = ch / 12, r12 = ch % 12, ry = r12 / 6, sx = (r12 % 6) / 3, cc = r12 % 3;
+      for (int ch = 0; ch < 64; ++ch) {
+        const int s4 = ch / 16, r12 = ch % 16, ry = r12 / 6, sx = (r12 % 6) / 3, cc = r12 % 3;
         const int rr = 2 * r + ry, ss = 2 * s4 + sx;
-        if (rr >= 7 || ss >= 7) continue;
+        if (r12 >= 12 || rr >= 7 || ss >= 7) continue;
         const float* src = w + (static_cast<size_t>(rr * 7 + ss) * 3 + cc) * 64;
         for (int o = 0; o < Cout; ++o)
           packed[static_cast<size_t>(o) * K + static_cast<size_t>(r) * Cin + ch] = static_cast<float>(src[o] * scale[o]);
@@ -1028,7 +1034,7 @@ int b2_step_info(b2_ctx* c, int idx, char* name, int name_cap, double* flops, do
     const double K = static_cast<double>(d.R) * d.S * d.Cin;
     *flops = 2.0 * M * K * d.Cout;
     const double in_px = static_cast<double>(d.B) * d.in_H * d.in_W;
-    *bytes = in_px * d.Cin * esz + K * d.Cout * esz + M * d.Cout * (s.layer->io.out_f32 ? 4.0 : esz) +
+    *bytes = in_px * (d.in_ld > 0 && d.in_ld < d.Cin ? d.in_ld : d.Cin) * esz + K * d.Cout * esz + M * d.Cout * (s.layer->io.out_f32 ? 4.0 : esz) +
              (s.layer->io.res_hi ? M * d.Cout * esz / (d.res_shift ? 4.0 : 1.0) : 0.0);
     nm += " [" + std::to_string(d.in_H) + "x" + std::to_string(d.in_W) + "x" + std::to_string(d.Cin) + " " +
           std::to_string(d.R) + "x" + std::to_string(d.S) + "/" + std::to_string(d.stride) + " d" +
@@ -1382,12 +1388,14 @@ int b2_set_stage(b2_ctx* c, const char* name, const void* src, int64_t bytes) {
   return 0;
 }
 
-// ---- persistent workspace for the small per-frame GEMM calls (experiment, B2_WS=1) -----------------------------
-// b2_cosine_cost / b2_distance_matrix are called once per frame (per cascade level) by the trackers; as written they
-// allocate ~12 device buffers, encode the tensor maps and free everything again on every call.  With B2_WS set they run
-// out of one grow-only workspace per device with the GEMM plans cached per padded shape: a call is then three uploads,
-// four launches and one download on a private stream.  Operands are padded to the plan's shape with whatever the buffers
-// hold (finite leftovers of earlier calls): padded rows / columns only produce outputs nobody reads.
+// ---- workspace for the small per-frame GEMM calls ------------------------------------------------------------------
+// b2_cosine_cost / b2_distance_matrix are called once per frame (per cascade level) by the trackers.  They run out of ONE
+// grow-only workspace per device with the GEMM plans cached per padded shape: a call is three uploads, four launches and
+// one download on a private stream (round 1 allocated ~12 device buffers, encoded the tensor maps and freed everything
+// again on every call: 48 ms per JDE frame against 1.7 ms for numpy, profiles/r2_widen_timing_before_ws.jsonl).  Operands
+// are padded to the plan's shape with whatever the buffers hold (finite leftovers of earlier calls): padded rows / columns
+// only produce outputs nobody reads.  B2_NO_WS=1 (test hook) runs every call in a private workspace that is released
+// when the call returns -- same code, no reuse; tests compare the two bit for bit.
 struct DistWs {
   int device = -1;
   cudaStream_t stream = nullptr;
@@ -1397,43 +1405,59 @@ struct DistWs {
   __half *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
   std::map<std::vector<int>, ConvPlan*> plans;   // key: Sp, Np, Dp, split
   int num_sms = 148;
+  bool transient = false;   // B2_NO_WS: owned by one call
+  DistWs() = default;
+  DistWs(const DistWs&) = delete;
+  DistWs& operator=(const DistWs&) = delete;
+  void release() {
+    for (auto& kv : plans) conv_tc_plan_destroy(kv.second);
+    plans.clear();
+    void* ptrs[] = {d_a, d_b, d_dots, d_out, d_bias, d_na2, d_nb2, d_off, a_hi, a_lo, b_hi, b_lo};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    d_a = d_b = d_dots = d_out = d_bias = d_na2 = d_nb2 = nullptr;
+    d_off = nullptr;
+    a_hi = a_lo = b_hi = b_lo = nullptr;
+    cap_a = cap_b = cap_rows = cap_cols = cap_dp = 0;
+  }
+  ~DistWs() {
+    if (!transient) return;   // the per-device workspaces live as long as the process (no CUDA calls at exit)
+    release();
+    if (stream) cudaStreamDestroy(stream);
+  }
 };
 static std::map<int, DistWs> g_dist_ws;
+static std::map<int, int> g_num_sms;
 static std::mutex g_dist_ws_mutex;   // one call at a time per process (the trackers are single-threaded per stream)
 
-static void dist_ws_release(DistWs& w) {
-  for (auto& kv : w.plans) conv_tc_plan_destroy(kv.second);
-  w.plans.clear();
-  void* ptrs[] = {w.d_a, w.d_b, w.d_dots, w.d_out, w.d_bias, w.d_na2, w.d_nb2, w.d_off, w.a_hi, w.a_lo, w.b_hi, w.b_lo};
-  for (void* p : ptrs) if (p) cudaFree(p);
-  w.d_a = w.d_b = w.d_dots = w.d_out = w.d_bias = w.d_na2 = w.d_nb2 = nullptr;
-  w.d_off = nullptr;
-  w.a_hi = w.a_lo = w.b_hi = w.b_lo = nullptr;
-}
-
-// Makes the workspace of `device` hold Sp x Dp (A side), Np x Dp (B side), Sp x Np (products) and `aux` ints / floats.
-static int dist_ws_reserve(DistWs** out, int device, int S, int N, int D, int Sp, int Np, int Dp, int aux) {
-  DistWs& w = g_dist_ws[device];
+// Makes `w` (on `device`) hold S x D / N x D raw rows, Sp x Dp / Np x Dp operand planes, Sp x Np products, `aux` ints.
+static int dist_ws_reserve(DistWs& w, int device, int S, int N, int D, int Sp, int Np, int Dp, int aux) {
   if (w.device < 0) {
     w.device = device;
-    cudaDeviceProp prop;
-    B2_CUDA(cudaGetDeviceProperties(&prop, device));
-    w.num_sms = prop.multiProcessorCount;
+    auto it = g_num_sms.find(device);
+    if (it == g_num_sms.end()) {
+      int n = 0;
+      B2_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
+      it = g_num_sms.emplace(device, n).first;
+    }
+    w.num_sms = it->second;
     B2_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
   }
   const size_t need_a = static_cast<size_t>(S) * D, need_b = static_cast<size_t>(N) * D;
   if (need_a > w.cap_a || need_b > w.cap_b || static_cast<size_t>(Sp) > w.cap_rows || static_cast<size_t>(Np) > w.cap_cols ||
       static_cast<size_t>(Dp) > w.cap_dp || static_cast<size_t>(aux) > w.cap_rows + w.cap_cols) {
     B2_CUDA(cudaStreamSynchronize(w.stream));
-    dist_ws_release(w);                                   // the plans hold the old addresses
-    auto grow = [](size_t cap, size_t need, size_t floor_) {   // only the dimension that overflowed grows (x2 head room)
-      return need > cap ? std::max(need * 2, floor_) : std::max(cap, floor_);
+    const size_t o_a = w.cap_a, o_b = w.cap_b, o_r = w.cap_rows, o_c = w.cap_cols, o_d = w.cap_dp;
+    w.release();                                          // the plans hold the old addresses
+    const size_t head = w.transient ? 1 : 2;              // only the dimension that overflowed grows (x2 head room)
+    auto grow = [head](size_t cap, size_t need, size_t floor_) {
+      return need > cap ? std::max(need * head, floor_) : std::max(cap, floor_);
     };
-    w.cap_a = grow(w.cap_a, need_a, 1);
-    w.cap_b = grow(w.cap_b, need_b, 1);
-    w.cap_rows = grow(w.cap_rows, static_cast<size_t>(Sp), 256);
-    w.cap_cols = grow(w.cap_cols, static_cast<size_t>(Np), 256);
-    w.cap_dp = std::max(w.cap_dp, static_cast<size_t>(Dp));
+    w.cap_a = grow(o_a, need_a, 1);
+    w.cap_b = grow(o_b, need_b, 1);
+    w.cap_rows = grow(o_r, static_cast<size_t>(Sp), w.transient ? 128 : 256);
+    w.cap_cols = grow(o_c, static_cast<size_t>(Np), w.transient ? 16 : 256);
+    if (static_cast<size_t>(aux) > w.cap_rows + w.cap_cols) w.cap_rows = static_cast<size_t>(aux);
+    w.cap_dp = std::max(o_d, static_cast<size_t>(Dp));
     B2_CUDA(cudaMalloc(&w.d_a, w.cap_a * 4));
     B2_CUDA(cudaMalloc(&w.d_b, w.cap_b * 4));
     B2_CUDA(cudaMalloc(&w.d_dots, w.cap_rows * w.cap_cols * 4));
@@ -1453,7 +1477,6 @@ static int dist_ws_reserve(DistWs** out, int device, int S, int N, int D, int Sp
     B2_CUDA(cudaMemsetAsync(w.b_lo, 0, w.cap_cols * w.cap_dp * 2, w.stream));
     B2_CUDA(cudaStreamSynchronize(w.stream));
   }
-  *out = &w;
   return 0;
 }
 
@@ -1476,45 +1499,41 @@ static int dist_ws_gemm(DistWs& w, int Sp, int Np, int Dp, bool split) {
   return conv_tc_launch(it->second, w.stream);
 }
 
-static int cosine_cost_ws(int device, const float* gallery, const int32_t* seg_offsets, int T, const float* dets, int N, int D,
-                          bool split, float* cost) {
-  std::lock_guard<std::mutex> lock(g_dist_ws_mutex);
+static int cosine_cost_run(DistWs& w, int device, const float* gallery, const int32_t* seg_offsets, int T, const float* dets,
+                           int N, int D, bool split, float* cost) {
   const int S = seg_offsets[T];
   const int Dp = (D + 63) / 64 * 64, Np = (N + 15) / 16 * 16, Sp = (S + 127) / 128 * 128;
-  DistWs* w = nullptr;
-  if (dist_ws_reserve(&w, device, S, N, D, Sp, Np, Dp, T + 1)) return -1;
-  cudaStream_t st = w->stream;
-  B2_CUDA(cudaMemcpyAsync(w->d_a, gallery, sizeof(float) * S * D, cudaMemcpyHostToDevice, st));
-  B2_CUDA(cudaMemcpyAsync(w->d_b, dets, sizeof(float) * N * D, cudaMemcpyHostToDevice, st));
-  B2_CUDA(cudaMemcpyAsync(w->d_off, seg_offsets, sizeof(int) * (T + 1), cudaMemcpyHostToDevice, st));
-  if (cosine_normalize_rows(w->d_a, S, D, w->a_hi, w->a_lo, Dp, st) || cosine_normalize_rows(w->d_b, N, D, w->b_hi, w->b_lo, Dp, st))
+  if (dist_ws_reserve(w, device, S, N, D, Sp, Np, Dp, T + 1)) return -1;
+  cudaStream_t st = w.stream;
+  B2_CUDA(cudaMemcpyAsync(w.d_a, gallery, sizeof(float) * S * D, cudaMemcpyHostToDevice, st));
+  B2_CUDA(cudaMemcpyAsync(w.d_b, dets, sizeof(float) * N * D, cudaMemcpyHostToDevice, st));
+  B2_CUDA(cudaMemcpyAsync(w.d_off, seg_offsets, sizeof(int) * (T + 1), cudaMemcpyHostToDevice, st));
+  if (cosine_normalize_rows(w.d_a, S, D, w.a_hi, w.a_lo, Dp, st) || cosine_normalize_rows(w.d_b, N, D, w.b_hi, w.b_lo, Dp, st))
     return -1;
-  if (dist_ws_gemm(*w, Sp, Np, Dp, split)) return -1;
-  if (cosine_segmin(w->d_dots, Np, w->d_off, T, N, w->d_out, st)) return -1;
-  B2_CUDA(cudaMemcpyAsync(cost, w->d_out, sizeof(float) * T * N, cudaMemcpyDeviceToHost, st));
+  if (dist_ws_gemm(w, Sp, Np, Dp, split)) return -1;
+  if (cosine_segmin(w.d_dots, Np, w.d_off, T, N, w.d_out, st)) return -1;
+  B2_CUDA(cudaMemcpyAsync(cost, w.d_out, sizeof(float) * T * N, cudaMemcpyDeviceToHost, st));
   B2_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 
-static int distance_matrix_ws(int device, const float* a, int na, const float* b, int nb, int D, int metric, bool split,
-                              float* out) {
-  std::lock_guard<std::mutex> lock(g_dist_ws_mutex);
+static int distance_matrix_run(DistWs& w, int device, const float* a, int na, const float* b, int nb, int D, int metric,
+                               bool split, float* out) {
   const int Dp = (D + 63) / 64 * 64, Np = (nb + 15) / 16 * 16, Sp = (na + 127) / 128 * 128;
-  DistWs* w = nullptr;
-  if (dist_ws_reserve(&w, device, na, nb, D, Sp, Np, Dp, 0)) return -1;
-  cudaStream_t st = w->stream;
-  B2_CUDA(cudaMemcpyAsync(w->d_a, a, sizeof(float) * na * D, cudaMemcpyHostToDevice, st));
-  B2_CUDA(cudaMemcpyAsync(w->d_b, b, sizeof(float) * nb * D, cudaMemcpyHostToDevice, st));
+  if (dist_ws_reserve(w, device, na, nb, D, Sp, Np, Dp, 0)) return -1;
+  cudaStream_t st = w.stream;
+  B2_CUDA(cudaMemcpyAsync(w.d_a, a, sizeof(float) * na * D, cudaMemcpyHostToDevice, st));
+  B2_CUDA(cudaMemcpyAsync(w.d_b, b, sizeof(float) * nb * D, cudaMemcpyHostToDevice, st));
   if (metric == 0) {
-    if (cosine_normalize_rows(w->d_a, na, D, w->a_hi, w->a_lo, Dp, st) || cosine_normalize_rows(w->d_b, nb, D, w->b_hi, w->b_lo, Dp, st))
+    if (cosine_normalize_rows(w.d_a, na, D, w.a_hi, w.a_lo, Dp, st) || cosine_normalize_rows(w.d_b, nb, D, w.b_hi, w.b_lo, Dp, st))
       return -1;
   } else {
-    if (rows_to_planes(w->d_a, na, D, w->a_hi, w->a_lo, Dp, w->d_na2, st) || rows_to_planes(w->d_b, nb, D, w->b_hi, w->b_lo, Dp, w->d_nb2, st))
+    if (rows_to_planes(w.d_a, na, D, w.a_hi, w.a_lo, Dp, w.d_na2, st) || rows_to_planes(w.d_b, nb, D, w.b_hi, w.b_lo, Dp, w.d_nb2, st))
       return -1;
   }
-  if (dist_ws_gemm(*w, Sp, Np, Dp, split)) return -1;
-  if (distance_finish(w->d_dots, Np, na, nb, metric, w->d_na2, w->d_nb2, w->d_out, st)) return -1;
-  B2_CUDA(cudaMemcpyAsync(out, w->d_out, sizeof(float) * na * nb, cudaMemcpyDeviceToHost, st));
+  if (dist_ws_gemm(w, Sp, Np, Dp, split)) return -1;
+  if (distance_finish(w.d_dots, Np, na, nb, metric, w.d_na2, w.d_nb2, w.d_out, st)) return -1;
+  B2_CUDA(cudaMemcpyAsync(out, w.d_out, sizeof(float) * na * nb, cudaMemcpyDeviceToHost, st));
   B2_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
@@ -1524,56 +1543,19 @@ int b2_cosine_cost(int device, const float* gallery, const int32_t* seg_offsets,
                    int D, int precision, float* cost) {
   B2_CHECK(gallery && seg_offsets && dets && cost, "b2_cosine_cost: null argument");
   if (T <= 0 || N <= 0) return 0;
+  B2_CHECK(D > 0 && seg_offsets[0] == 0, "b2_cosine_cost: seg_offsets must start at 0");
+  for (int t = 0; t < T; ++t)
+    B2_CHECK(seg_offsets[t + 1] >= seg_offsets[t], "b2_cosine_cost: seg_offsets must be non-decreasing");
+  B2_CHECK(seg_offsets[T] > 0, "b2_cosine_cost: empty gallery");
   B2_CUDA(cudaSetDevice(device));
-  const int S = seg_offsets[T];
-  B2_CHECK(S > 0 && D > 0, "b2_cosine_cost: empty gallery");
   const bool split = precision == 1;
-  if (getenv("B2_WS") != nullptr) return cosine_cost_ws(device, gallery, seg_offsets, T, dets, N, D, split, cost);
-  const int Dp = (D + 63) / 64 * 64, Np = (N + 15) / 16 * 16, Sp = (S + 127) / 128 * 128;
-  cudaStream_t st = nullptr;
-  float *d_g = nullptr, *d_d = nullptr, *d_dots = nullptr, *d_cost = nullptr, *d_bias = nullptr;
-  int* d_off = nullptr;
-  __half *g_hi = nullptr, *g_lo = nullptr, *q_hi = nullptr, *q_lo = nullptr;
-  B2_CUDA(cudaMalloc(&d_g, sizeof(float) * S * D));
-  B2_CUDA(cudaMalloc(&d_d, sizeof(float) * N * D));
-  B2_CUDA(cudaMalloc(&d_dots, sizeof(float) * Sp * Np));
-  B2_CUDA(cudaMalloc(&d_cost, sizeof(float) * T * N));
-  B2_CUDA(cudaMalloc(&d_bias, sizeof(float) * Np));
-  B2_CUDA(cudaMalloc(&d_off, sizeof(int) * (T + 1)));
-  B2_CUDA(cudaMalloc(&g_hi, sizeof(__half) * Sp * Dp));
-  B2_CUDA(cudaMalloc(&g_lo, sizeof(__half) * Sp * Dp));
-  B2_CUDA(cudaMalloc(&q_hi, sizeof(__half) * Np * Dp));
-  B2_CUDA(cudaMalloc(&q_lo, sizeof(__half) * Np * Dp));
-  B2_CUDA(cudaMemset(g_hi, 0, sizeof(__half) * Sp * Dp));
-  B2_CUDA(cudaMemset(g_lo, 0, sizeof(__half) * Sp * Dp));
-  B2_CUDA(cudaMemset(q_hi, 0, sizeof(__half) * Np * Dp));
-  B2_CUDA(cudaMemset(q_lo, 0, sizeof(__half) * Np * Dp));
-  B2_CUDA(cudaMemset(d_bias, 0, sizeof(float) * Np));
-  B2_CUDA(cudaMemcpy(d_g, gallery, sizeof(float) * S * D, cudaMemcpyHostToDevice));
-  B2_CUDA(cudaMemcpy(d_d, dets, sizeof(float) * N * D, cudaMemcpyHostToDevice));
-  B2_CUDA(cudaMemcpy(d_off, seg_offsets, sizeof(int) * (T + 1), cudaMemcpyHostToDevice));
-  if (cosine_normalize_rows(d_g, S, D, g_hi, g_lo, Dp, st)) return -1;
-  if (cosine_normalize_rows(d_d, N, D, q_hi, q_lo, Dp, st)) return -1;
-  ConvDesc d;
-  d.B = 1; d.in_H = 1; d.in_W = S; d.Cin = Dp; d.in_pitch_H = 1; d.in_pitch_W = S; d.in_ld = Dp;
-  d.Cout = N; d.out_H = 1; d.out_W = S; d.ldc = Np;
-  ConvWeights w;
-  w.w_hi = q_hi; w.w_lo = split ? q_lo : nullptr; w.bias = d_bias; w.Cout_pad = Np; w.K = Dp;
-  ConvIO io;
-  io.in_hi = g_hi; io.in_lo = split ? g_lo : nullptr; io.out_f32 = d_dots;
-  cudaDeviceProp prop;
-  B2_CUDA(cudaGetDeviceProperties(&prop, device));
-  ConvPlan* plan = conv_tc_plan_create(d, w, io, split, prop.multiProcessorCount);
-  B2_CHECK(plan != nullptr, std::string("b2_cosine_cost: ") + last_error());
-  int rc = conv_tc_launch(plan, st);
-  if (!rc) rc = cosine_segmin(d_dots, Np, d_off, T, N, d_cost, st);
-  cudaError_t e = cudaMemcpy(cost, d_cost, sizeof(float) * T * N, cudaMemcpyDeviceToHost);
-  conv_tc_plan_destroy(plan);
-  cudaFree(d_g); cudaFree(d_d); cudaFree(d_dots); cudaFree(d_cost); cudaFree(d_bias); cudaFree(d_off);
-  cudaFree(g_hi); cudaFree(g_lo); cudaFree(q_hi); cudaFree(q_lo);
-  if (rc) return -1;
-  B2_CUDA(e);
-  return 0;
+  std::lock_guard<std::mutex> lock(g_dist_ws_mutex);
+  if (getenv("B2_NO_WS") != nullptr) {
+    DistWs w;
+    w.transient = true;
+    return cosine_cost_run(w, device, gallery, seg_offsets, T, dets, N, D, split, cost);
+  }
+  return cosine_cost_run(g_dist_ws[device], device, gallery, seg_offsets, T, dets, N, D, split, cost);
 }
 
 // ---- distance matrix (torchreid/distance.py:6-80) ------------------------------------------------
@@ -1582,59 +1564,16 @@ int b2_distance_matrix(int device, const float* a, int na, const float* b, int n
   B2_CHECK(a && b && out, "b2_distance_matrix: null argument");
   B2_CHECK(metric == 0 || metric == 1, "b2_distance_matrix: metric must be 0 (cosine) or 1 (squared euclidean)");
   if (na <= 0 || nb <= 0) return 0;
+  B2_CHECK(D > 0, "b2_distance_matrix: D must be positive");
   B2_CUDA(cudaSetDevice(device));
   const bool split = precision == 1;
-  if (getenv("B2_WS") != nullptr) return distance_matrix_ws(device, a, na, b, nb, D, metric, split, out);
-  const int Dp = (D + 63) / 64 * 64, Np = (nb + 15) / 16 * 16, Sp = (na + 127) / 128 * 128;
-  cudaStream_t st = nullptr;
-  float *d_a = nullptr, *d_b = nullptr, *d_dots = nullptr, *d_out = nullptr, *d_bias = nullptr, *d_na2 = nullptr,
-        *d_nb2 = nullptr;
-  __half *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
-  B2_CUDA(cudaMalloc(&d_a, sizeof(float) * na * D));
-  B2_CUDA(cudaMalloc(&d_b, sizeof(float) * nb * D));
-  B2_CUDA(cudaMalloc(&d_dots, sizeof(float) * Sp * Np));
-  B2_CUDA(cudaMalloc(&d_out, sizeof(float) * na * nb));
-  B2_CUDA(cudaMalloc(&d_bias, sizeof(float) * Np));
-  B2_CUDA(cudaMalloc(&d_na2, sizeof(float) * Sp));
-  B2_CUDA(cudaMalloc(&d_nb2, sizeof(float) * Np));
-  B2_CUDA(cudaMalloc(&a_hi, sizeof(__half) * Sp * Dp));
-  B2_CUDA(cudaMalloc(&a_lo, sizeof(__half) * Sp * Dp));
-  B2_CUDA(cudaMalloc(&b_hi, sizeof(__half) * Np * Dp));
-  B2_CUDA(cudaMalloc(&b_lo, sizeof(__half) * Np * Dp));
-  B2_CUDA(cudaMemset(a_hi, 0, sizeof(__half) * Sp * Dp));
-  B2_CUDA(cudaMemset(a_lo, 0, sizeof(__half) * Sp * Dp));
-  B2_CUDA(cudaMemset(b_hi, 0, sizeof(__half) * Np * Dp));
-  B2_CUDA(cudaMemset(b_lo, 0, sizeof(__half) * Np * Dp));
-  B2_CUDA(cudaMemset(d_bias, 0, sizeof(float) * Np));
-  B2_CUDA(cudaMemcpy(d_a, a, sizeof(float) * na * D, cudaMemcpyHostToDevice));
-  B2_CUDA(cudaMemcpy(d_b, b, sizeof(float) * nb * D, cudaMemcpyHostToDevice));
-  if (metric == 0) {
-    if (cosine_normalize_rows(d_a, na, D, a_hi, a_lo, Dp, st) || cosine_normalize_rows(d_b, nb, D, b_hi, b_lo, Dp, st))
-      return -1;
-  } else {
-    if (rows_to_planes(d_a, na, D, a_hi, a_lo, Dp, d_na2, st) || rows_to_planes(d_b, nb, D, b_hi, b_lo, Dp, d_nb2, st))
-      return -1;
+  std::lock_guard<std::mutex> lock(g_dist_ws_mutex);
+  if (getenv("B2_NO_WS") != nullptr) {
+    DistWs w;
+    w.transient = true;
+    return distance_matrix_run(w, device, a, na, b, nb, D, metric, split, out);
   }
-  ConvDesc d;
-  d.B = 1; d.in_H = 1; d.in_W = na; d.Cin = Dp; d.in_pitch_H = 1; d.in_pitch_W = na; d.in_ld = Dp;
-  d.Cout = nb; d.out_H = 1; d.out_W = na; d.ldc = Np;
-  ConvWeights w;
-  w.w_hi = b_hi; w.w_lo = split ? b_lo : nullptr; w.bias = d_bias; w.Cout_pad = Np; w.K = Dp;
-  ConvIO io;
-  io.in_hi = a_hi; io.in_lo = split ? a_lo : nullptr; io.out_f32 = d_dots;
-  cudaDeviceProp prop;
-  B2_CUDA(cudaGetDeviceProperties(&prop, device));
-  ConvPlan* plan = conv_tc_plan_create(d, w, io, split, prop.multiProcessorCount);
-  B2_CHECK(plan != nullptr, std::string("b2_distance_matrix: ") + last_error());
-  int rc = conv_tc_launch(plan, st);
-  if (!rc) rc = distance_finish(d_dots, Np, na, nb, metric, d_na2, d_nb2, d_out, st);
-  cudaError_t e = cudaMemcpy(out, d_out, sizeof(float) * na * nb, cudaMemcpyDeviceToHost);
-  conv_tc_plan_destroy(plan);
-  cudaFree(d_a); cudaFree(d_b); cudaFree(d_dots); cudaFree(d_out); cudaFree(d_bias); cudaFree(d_na2); cudaFree(d_nb2);
-  cudaFree(a_hi); cudaFree(a_lo); cudaFree(b_hi); cudaFree(b_lo);
-  if (rc) return -1;
-  B2_CUDA(e);
-  return 0;
+  return distance_matrix_run(g_dist_ws[device], device, a, na, b, nb, D, metric, split, out);
 }
 
 // ---- single conv op for kernel parity tests ---------------------------------------------------

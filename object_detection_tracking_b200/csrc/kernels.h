@@ -13,6 +13,9 @@ int planes_to_f32(const __half* hi, const __half* lo, float* dst, size_t n, cuda
 int resize_u8_launch(const uint8_t* src, int B, int sh, int sw, float* dst, int dh, int dw, cudaStream_t s);
 int stem_pack_launch(const void* img, int is_u8, int B, int H, int W, __half* out_hi, __half* out_lo, int Hu, int Wu,
                      int norm_mode, cudaStream_t s);
+// compact operand of the detector stem: [B][Hu][Wv = Wu + 3][16] (stem.cu)
+int stem_pack16_launch(const void* img, int is_u8, int B, int H, int W, __half* out_hi, __half* out_lo, int Hu, int Wv,
+                       cudaStream_t s);
 int maxpool_launch(const __half* in_hi, const __half* in_lo, int B, int H, int W, int C, __half* out_hi,
                    __half* out_lo, int Ho, int Wo, cudaStream_t s);
 

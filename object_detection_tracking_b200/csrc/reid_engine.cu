@@ -530,17 +530,19 @@ static int reid_enqueue(b2_reid* c) {
 }
 
 // crops: host [B,256,128,3] uint8 RGB (already resized); feats: host [B,512] float32
-int b2_reid_embed(b2_reid* c, const uint8_t* crops_host, int n, float* feats_host) {
-  B2_CHECK(c && crops_host && feats_host, "b2_reid_embed: null argument");
+// crops: host RGB uint8; the features go to `feats` (host, or device memory of the context's GPU when to_device)
+static int reid_embed_impl(b2_reid* c, const uint8_t* crops_host, int n, float* feats, bool to_device) {
+  B2_CHECK(c && crops_host && feats, "b2_reid_embed: null argument");
   B2_CHECK(n >= 1 && n <= c->B, "b2_reid_embed: batch larger than the context was created for");
   B2_CUDA(cudaSetDevice(c->device));
   B2_CHECK(c->loaded, "b2_reid_embed: weights not loaded");
   const size_t per = static_cast<size_t>(c->in_h) * c->in_w * 3;
+  const cudaMemcpyKind out_kind = to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   if (n < c->B) B2_CUDA(cudaMemsetAsync(c->crops + n * per, 0, (c->B - n) * per, c->stream));
   B2_CUDA(cudaMemcpyAsync(c->crops, crops_host, n * per, cudaMemcpyHostToDevice, c->stream));
   if (getenv("B2_REID_NO_GRAPH") != nullptr) {
     if (reid_enqueue(c)) return -1;
-    B2_CUDA(cudaMemcpyAsync(feats_host, c->feats, sizeof(float) * n * c->feat_dim, cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaMemcpyAsync(feats, c->feats, sizeof(float) * n * c->feat_dim, out_kind, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
   }
@@ -557,10 +559,22 @@ int b2_reid_embed(b2_reid* c, const uint8_t* crops_host, int n, float* feats_hos
     B2_CUDA(cudaGraphDestroy(g));
   }
   B2_CUDA(cudaGraphLaunch(c->graph, c->stream));
-  B2_CUDA(cudaMemcpyAsync(feats_host, c->feats, sizeof(float) * n * c->feat_dim, cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaMemcpyAsync(feats, c->feats, sizeof(float) * n * c->feat_dim, out_kind, c->stream));
   B2_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
+
+int b2_reid_embed(b2_reid* c, const uint8_t* crops_host, int n, float* feats_host) {
+  return reid_embed_impl(c, crops_host, n, feats_host, false);
+}
+
+// The features stay in HBM: `feats_dev` is device memory of the context's GPU (e.g. this camera's slice of the gallery
+// buffer that the NCCL all-gather / the peer-memory pair cost of config 5 reads), so a gallery never crosses PCIe.
+int b2_reid_embed_dev(b2_reid* c, const uint8_t* crops_host, int n, float* feats_dev) {
+  return reid_embed_impl(c, crops_host, n, feats_dev, true);
+}
+
+int b2_reid_feat_dim(b2_reid* c) { return c ? c->feat_dim : -1; }
 
 // Stage-addressable activation of the last pass as fp32 NHWC (names: "conv1", "maxpool", "conv2.0", "conv2.0.x1",
 // "conv2.0.s0".."s3", "conv2.0.x2", "conv2.1", "conv2", ..., "conv5").

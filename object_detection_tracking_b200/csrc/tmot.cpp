@@ -404,6 +404,12 @@ int b2_jde_reset(b2_jde* t) {   // multitracker.py:206-215 (also zeroes the shar
   return 0;
 }
 
+int b2_jde_reset_ids(b2_jde* t) {   // BaseTrack._count = 0 alone (multitracker.py:215), for a reset() of a group member without state
+  B2_CHECK(t, "b2_jde_reset_ids: null tracker");
+  *t->id_counter = 0;
+  return 0;
+}
+
 int b2_jde_update(b2_jde* t, const double* tlwh, const double* conf, const float* features, int n) {   // :217-358
   B2_CHECK(t && (n == 0 || (tlwh && conf && features)), "b2_jde_update: null argument");
   const int D = t->feat_dim;

@@ -60,6 +60,18 @@ class ReidEngine:
         _lib.check(self.lib.b2_reid_embed(self._ctx, _lib.ptr(crops_u8), n, _lib.ptr(out)), "b2_reid_embed")
         return out
 
+    def embed_dev(self, crops_u8: np.ndarray, out_dev) -> None:
+        """Same pass with the [n, feat_dim] features written into `out_dev` -- a float32 torch CUDA tensor (or a slice of
+        one: e.g. this camera's rows of the gallery buffer the NCCL all-gather sends) on this engine's GPU; nothing comes
+        back to the host (b2_reid_embed_dev)."""
+        crops_u8 = np.ascontiguousarray(crops_u8, dtype=np.uint8)
+        n = crops_u8.shape[0]
+        assert crops_u8.shape[1:] == self.image_size + (3,), crops_u8.shape
+        assert out_dev.is_cuda and out_dev.is_contiguous() and tuple(out_dev.shape) == (n, self.feat_dim), out_dev.shape
+        assert str(out_dev.dtype) == "torch.float32"
+        _lib.check(self.lib.b2_reid_embed_dev(self._ctx, _lib.ptr(crops_u8), n, c_void_p(out_dev.data_ptr())),
+                   "b2_reid_embed_dev")
+
     def get_activation(self, name: str) -> np.ndarray:
         """fp32 NHWC copy of a named intermediate of the last pass (parity tests)."""
         shape = (c_int64 * 4)()
@@ -159,6 +171,77 @@ def allgather_gallery(local_feats, group=None):
     bufs = [torch.zeros_like(padded) for _ in range(world)]
     dist.all_gather(bufs, padded, group=group)
     return torch.cat([b[:c] for b, c in zip(bufs, counts)], 0), counts
+
+
+def allgather_gallery_dev(local_gallery, rows_cap, group=None):
+    """Device-resident exchange step of config 5 (multi_video_reid.py:448-476): `local_gallery` is this camera's
+    [rows_cap, D] float32 CUDA tensor (rows beyond the real count are padding); ONE all_gather_into_tensor over NCCL /
+    NVLink fills [world, rows_cap, D] on every GPU.  The galleries never visit the host: b2_reid_embed_dev wrote them,
+    b2_track_pair_cost_dev reads them.  torch.distributed owns the NCCL communicator (plumbing); the C ABI works on the
+    device pointers."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    assert local_gallery.is_cuda and local_gallery.is_contiguous() and local_gallery.shape[0] == rows_cap
+    out = torch.empty((world,) + tuple(local_gallery.shape), dtype=local_gallery.dtype, device=local_gallery.device)
+    dist.all_gather_into_tensor(out, local_gallery, group=group)
+    return out
+
+
+def match_cameras_allgather(tracks_meta, local_gallery, rows_cap, device=0, group=None, frame_offsets=None, tol=50,
+                            cost_limit=998., precision="split", ignore_pairs=None, timing=None, object_group=None):
+    """Config 5 with the NCCL all-gather (the p2p form is match_cameras_p2p).  Every rank = one camera.
+    `tracks_meta` = {track_id: (trajectory rows [K,>=3], number of crop embeddings)} of this camera, whose embeddings sit
+    in `local_gallery[:sum(counts)]` (track-id order).  Returns {(i, j): [(id_i, id_j), ...]} for the pairs this rank owns.
+    `timing` (dict) receives the all-gather time in ms (CUDA events) and its payload bytes.  `group` carries the gallery
+    tensors (NCCL); `object_group` (default: the same) the small host-side metadata -- a gloo group keeps it off the GPU."""
+    import torch
+    import torch.distributed as dist
+    from .tmot import lapjv
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if object_group is None:
+        object_group = group
+    ids = sorted(tracks_meta.keys())
+    seg = np.zeros(len(ids) + 1, np.int32)
+    for k, t in enumerate(ids):
+        seg[k + 1] = seg[k] + int(tracks_meta[t][1])
+    assert seg[-1] <= rows_cap
+    meta = dict(ids=ids, seg=seg, traj={t: np.asarray(tracks_meta[t][0], dtype=np.float64) for t in ids})
+    metas = [None] * world
+    dist.all_gather_object(metas, meta, group=object_group)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    gathered = allgather_gallery_dev(local_gallery, rows_cap, group)
+    e1.record()
+    torch.cuda.synchronize()
+    if timing is not None:
+        timing["allgather_ms"] = e0.elapsed_time(e1)
+        timing["allgather_bytes_recv"] = int((world - 1) * local_gallery.numel() * 4)
+    dim = int(local_gallery.shape[1])
+    result = {}
+    for (i, j) in camera_pairs(world, rank, world):
+        mi, mj = metas[i], metas[j]
+        if not mi["ids"] or not mj["ids"]:
+            result[(i, j)] = []
+            continue
+        fr_i, pt_i, sg_i = _pack_traj({t: (mi["traj"][t], None) for t in mi["ids"]})
+        fr_j, pt_j, sg_j = _pack_traj({t: (mj["traj"][t], None) for t in mj["ids"]})
+        off = 0 if frame_offsets is None else frame_offsets.get((i, j), 0)
+        spatial = np.zeros((len(mi["ids"]), len(mj["ids"])), dtype=np.float64)
+        _lib.check(_lib.load().b2_track_spatial_dist(_lib.ptr(fr_i), _lib.ptr(pt_i), _lib.ptr(sg_i), len(mi["ids"]),
+                                                     _lib.ptr(fr_j), _lib.ptr(pt_j), _lib.ptr(sg_j), len(mj["ids"]),
+                                                     int(off), float(tol), _lib.ptr(spatial)), "b2_track_spatial_dist")
+        ign = (ignore_pairs or {}).get((i, j))
+        if ign:                                      # multi_video_reid.py:299-303
+            for a, t1 in enumerate(mi["ids"]):
+                for b, t2 in enumerate(mj["ids"]):
+                    if t1 in ign[0] and t2 in ign[1]:
+                        spatial[a, b] = 9999.
+        feat = pair_cost_device(c_void_p(gathered[i].data_ptr()), mi["seg"], c_void_p(gathered[j].data_ptr()), mj["seg"],
+                                dim, spatial, device, precision)
+        _, x, _ = lapjv(feat, extend_cost=True, cost_limit=cost_limit)
+        result[(i, j)] = [(mi["ids"][a], mj["ids"][int(b)]) for a, b in enumerate(x) if b >= 0]
+    return result
 
 
 # ---- multi-camera track matching (multi_video_reid.py:260-324, 486-534) -----------------------------------------------

@@ -108,9 +108,15 @@ class JDETracker(object):
             pass
 
     def reset(self):
+        """multitracker.py:206-215: clears this tracker's lists and ALWAYS zeroes the id counter of the whole process
+        (BaseTrack._count = 0) -- also when this tracker has not seen a detection yet and owns no native state."""
         self.frame_id = 0
         if self._h is not None:
             _lib.check(self._lib.b2_jde_reset(self._h), "b2_jde_reset")
+        else:
+            h = self._group.live_handle()
+            if h is not None:
+                _lib.check(self._lib.b2_jde_reset_ids(h), "b2_jde_reset_ids")
 
     def update(self, detections):
         n = len(detections)

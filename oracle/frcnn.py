@@ -21,8 +21,29 @@ from .anchors import get_all_anchors
 BN_EPS = 1e-5            # nn.py:1723
 
 
+# Arithmetic type of the conv / matmul stack.  float32 is the reference's (and the default).  `exact()` switches it to
+# float64: the same graph evaluated without fp32 rounding noise -- the centre any two float32 implementations (TF's Eigen
+# kernels, this torch port, the GPU path) scatter around.  Tests use it to split |GPU - oracle32| into the GPU's own
+# error and the oracle's.  Post-processing (decode, top-k, NMS, ROIAlign) stays float32 in both modes: the stack's
+# outputs are rounded once to float32 at the hand-over (`_np`).
+_DT = [torch.float32]
+
+
+class exact(object):
+    def __enter__(self):
+        _DT.append(torch.float64)
+
+    def __exit__(self, *a):
+        _DT.pop()
+
+
 def _t(a):
-    return torch.from_numpy(np.ascontiguousarray(a))
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return t.to(_DT[-1]) if t.is_floating_point() else t
+
+
+def _np(t):
+    return t.to(torch.float32).numpy()
 
 
 def _conv(x, w_hwio, stride=1, dilation=1, pad=(0, 0, 0, 0), bias=None):
@@ -50,8 +71,8 @@ def _bn(x, W, name):
 def preprocess(img_hwc_f32: np.ndarray) -> torch.Tensor:
     """models.py:337-357: /255, -mean[::-1], /std[::-1] (BGR), HWC->NCHW."""
     x = _t(np.asarray(img_hwc_f32, dtype=np.float32)).unsqueeze(0)
-    mean = torch.tensor([0.485, 0.456, 0.406][::-1], dtype=torch.float32)
-    std = torch.tensor([0.229, 0.224, 0.225][::-1], dtype=torch.float32)
+    mean = torch.tensor([0.485, 0.456, 0.406][::-1], dtype=torch.float32).to(_DT[-1])
+    std = torch.tensor([0.229, 0.224, 0.225][::-1], dtype=torch.float32).to(_DT[-1])
     x = x * (1.0 / 255)
     x = (x - mean) / std
     return x.permute(0, 3, 1, 2).contiguous()
@@ -125,8 +146,8 @@ def rpn_head(p, W, na):
     h = torch.relu(_conv(p, W["rpn/conv0/W"], pad=(1, 1, 1, 1), bias=W["rpn/conv0/b"]))
     cls = _conv(h, W["rpn/class/W"], bias=W["rpn/class/b"])
     box = _conv(h, W["rpn/box/W"], bias=W["rpn/box/b"])
-    cls = cls[0].permute(1, 2, 0).contiguous().numpy()
-    box = box[0].permute(1, 2, 0).contiguous().numpy()
+    cls = _np(cls[0].permute(1, 2, 0).contiguous())
+    box = _np(box[0].permute(1, 2, 0).contiguous())
     return cls, box.reshape(box.shape[0], box.shape[1], na, 4)
 
 
@@ -210,14 +231,14 @@ def fastrcnn_head(feat, W, cfg):
     x = _t(feat.reshape(feat.shape[0], -1))
     h = torch.relu(x @ _t(W["fastrcnn/fc6/W"]) + _t(W["fastrcnn/fc6/b"]))
     h = torch.relu(h @ _t(W["fastrcnn/fc7/W"]) + _t(W["fastrcnn/fc7/b"]))
-    cls = (h @ _t(W["fastrcnn/outputs/class/W"]) + _t(W["fastrcnn/outputs/class/b"])).numpy()
-    box = (h @ _t(W["fastrcnn/outputs/box/W"]) + _t(W["fastrcnn/outputs/box/b"])).numpy()
+    cls = _np(h @ _t(W["fastrcnn/outputs/class/W"]) + _t(W["fastrcnn/outputs/class/b"]))
+    box = _np(h @ _t(W["fastrcnn/outputs/box/W"]) + _t(W["fastrcnn/outputs/box/b"]))
     box = box.reshape(box.shape[0], -1, 4)
     if not cfg.use_frcnn_class_agnostic:
         box = box[:, 1:, :]
     else:
         box = np.tile(box, (1, cfg.num_class - 1, 1))     # models.py:799-802
-    return cls, np.ascontiguousarray(box), h.numpy()
+    return cls, np.ascontiguousarray(box), _np(h)
 
 
 def softmax(x):
@@ -261,7 +282,7 @@ def maskrcnn_head(feat, W, num_class):
         x = torch.relu(F.conv_transpose2d(x, wd, _t(W["maskrcnn/deconv/b"]), stride=2))
         x = _conv(x, W["maskrcnn/conv/W"], bias=W["maskrcnn/conv/b"])
     assert x.shape[1] == num_class - 1
-    return x.numpy()
+    return _np(x)
 
 
 def final_masks(cfg, W, feats, fboxes, flabels):
@@ -306,7 +327,7 @@ def forward(cfg, W, img_hwc_f32: np.ndarray, stages: bool = True) -> dict:
     pb = np.concatenate(all_b, 0); ps = np.concatenate(all_s, 0)
     ps, ti = tf_ops.top_k(ps, min(ps.shape[0], cfg.rpn_test_post_nms_topk))   # models.py:429-433
     pb = pb[ti]
-    feats = [p[0].numpy() for p in p23456[:4]]
+    feats = [_np(p[0]) for p in p23456[:4]]
     roi, roi_lvl = multilevel_roi_align(feats, pb, 7, cfg.anchor_strides)
     with torch.no_grad():
         cls_logits, box_logits, hidden = fastrcnn_head(roi, W, cfg)
@@ -328,7 +349,7 @@ def forward(cfg, W, img_hwc_f32: np.ndarray, stages: bool = True) -> dict:
     if getattr(cfg, "add_mask", False):
         out["final_masks"], out["mask_logits"] = final_masks(cfg, W, feats, fboxes.astype(np.float32), flabels)
     if stages:
-        out.update(c2345=[c[0].numpy() for c in c2345], p23456=[p[0].numpy() for p in p23456],
+        out.update(c2345=[_np(c[0]) for c in c2345], p23456=[_np(p[0]) for p in p23456],
                    rpn=rpn_out, level_proposals=lvl_props, proposal_boxes=pb, proposal_scores=ps,
                    roi_feat=roi, roi_level=roi_lvl, cls_logits=cls_logits, box_logits=box_logits,
                    hidden=hidden, decoded_boxes=dec, probs=probs, pred_indices=pred)
@@ -341,7 +362,7 @@ def forward_givenbox(cfg, W, img_hwc_f32: np.ndarray, boxes: np.ndarray) -> np.n
     x = preprocess(img_hwc_f32)
     with torch.no_grad():
         p23456 = fpn(backbone(x, W, cfg), W)
-    feats = [p[0].numpy() for p in p23456[:4]]
+    feats = [_np(p[0]) for p in p23456[:4]]
     boxes = np.asarray(boxes, dtype=np.float32).reshape(-1, 4)
     if not len(boxes):
         return np.zeros((0, feats[0].shape[0]), np.float32)
@@ -399,7 +420,7 @@ def forward_multi(cfg, W, imgs, stages=False):
         area = ((pb[:, 3] - pb[:, 1]) * (pb[:, 2] - pb[:, 0])).astype(np.float32)
         keep = area > 0                                                                    # models.py:2516-2520
         pb, ps = pb[keep], ps[keep]
-        fmaps = [p[0].numpy() for p in p23456[:4]]
+        fmaps = [_np(p[0]) for p in p23456[:4]]
         roi, _ = multilevel_roi_align(fmaps, pb, 7, cfg.anchor_strides)
         with torch.no_grad():
             cls_logits, box_logits, _ = fastrcnn_head(roi, W, cfg)

@@ -51,6 +51,24 @@ def test_jde_tracker_reproduces_reference_run(golden_dir):
         t.close()
 
 
+def test_reset_of_a_tracker_without_state_zeroes_the_shared_id_counter(golden_dir):
+    """multitracker.py:206-215: reset() of ANY JDETracker sets BaseTrack._count = 0 -- also of one that has not seen a
+    detection yet (the vehicle tracker of a video without vehicles); ids of the next video then restart at 1."""
+    from object_detection_tracking_b200.tmot import JDETracker, _IdGroup
+    g = np.load(os.path.join(golden_dir, "tmot_jde.npz"))
+    grp = _IdGroup()
+    person, vehicle = (JDETracker(0.5, cost_fn=cdist_cost, id_group=grp) for _ in range(2))
+    frames = [[(r[:4].astype(np.float64), float(r[4]), r[5:].copy()) for r in g["s0_f%d" % f]] for f in range(3)]
+    first = [t.track_id for f in frames for t in person.update(f)]
+    assert first and min(first) == 1
+    vehicle.reset()                                       # owns no native handle yet
+    person2 = JDETracker(0.5, cost_fn=cdist_cost, id_group=grp)
+    again = [t.track_id for f in frames for t in person2.update(f)]
+    assert again == first                                 # counter restarted: the same ids as the first video
+    for t in (person, vehicle, person2):
+        t.close()
+
+
 def test_matching_functions_match_reference(golden_dir):
     from object_detection_tracking_b200 import tmot
     g = np.load(os.path.join(golden_dir, "tmot_matching.npz"))

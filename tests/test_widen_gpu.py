@@ -246,8 +246,8 @@ def test_detect_then_track_loop_end_to_end():
 
 
 def test_distance_calls_from_the_persistent_workspace_equal_the_per_call_path():
-    """B2_WS=1 (grow-only workspace + cached GEMM plans for b2_cosine_cost / b2_distance_matrix) returns the same bits as the
-    allocate-per-call path, across growing and shrinking shapes and both metrics (each mode in its own process: the switch is
+    """The default grow-only workspace + cached GEMM plans behind b2_cosine_cost / b2_distance_matrix returns the same bits as
+    a private workspace per call (B2_NO_WS=1), across growing and shrinking shapes and both metrics (each mode in its own process: the switch is
     read from the environment)."""
     import subprocess
     import sys
@@ -267,7 +267,7 @@ def test_distance_calls_from_the_persistent_workspace_equal_the_per_call_path():
         "np.savez(sys.argv[1], **out)\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = []
     with tempfile.TemporaryDirectory() as tmp:
-        for i, env in enumerate([{}, {"B2_WS": "1"}]):
+        for i, env in enumerate([{"B2_NO_WS": "1"}, {}]):
             path = os.path.join(tmp, "o%d.npz" % i)
             subprocess.run([sys.executable, "-c", code, path], check=True, env=dict(os.environ, **env), timeout=300)
             res.append(dict(np.load(path)))

@@ -6,7 +6,7 @@
 #   gpurun --timeout 1500 -- 'bash tools/round2_experiments.sh'
 set -u
 cd "$(dirname "$0")/.."
-tools/ab_run.sh tests \
+tools/ab_run.sh \
   base: \
   shortk2:B2_ACC_KB_SHORTK=2 \
   bn64tail:B2_BN64_TAIL=1 \
@@ -19,7 +19,6 @@ tools/ab_run.sh tests \
 echo "=== accuracy of the short-K chunk variant (boxes vs the fp32 oracle on the 720x1280 frame)"
 B2_ACC_KB_SHORTK=2 timeout 600 python tools/gpu_pipeline_probe.py 720 1280 tcgen05 split > gpurun_out/pipe_shortk2.log 2>&1
 grep -E "c[45] rel|proposals gpu|final gpu" gpurun_out/pipe_shortk2.log
-timeout 300 python tools/ab_two_contexts.py 40 | tee gpurun_out/ab_two_contexts.jsonl
 echo "=== trackers with the persistent distance workspace (B2_WS=1) vs per-call allocation"
 timeout 200 python tools/gpu_tracker_probe.py > gpurun_out/tracker_nows.log 2>&1; tail -2 gpurun_out/tracker_nows.log
 B2_WS=1 timeout 200 python tools/gpu_tracker_probe.py > gpurun_out/tracker_ws.log 2>&1; tail -2 gpurun_out/tracker_ws.log
