@@ -29,11 +29,15 @@ CONV_GFLOP_PER_FRAME = 490.4      # conv stack 245.2 GMAC
 FC_GFLOP_PER_FRAME = 8.4
 
 
-def workload_config(n_gpus, precision):
+def workload_config(n_gpus, precision="split", input_dtype="float32"):
+    """The workload both arms (--impl b200 / --impl reference) run; identical keys and values in both lines.  `precision`
+    and `input_dtype` name the arithmetic of the GPU arm's operands at the boundary; the reference arm computes the same
+    graph in float32 on the host (its own line says so under "arith")."""
     return {"workload": "ResNet-101-FPN Faster-RCNN rpn300 1280x720 batch=8 per GPU, detection only "
-                        "(BASELINE configs[1]); one stream per GPU, no data-path collective",
+                        "(BASELINE configs[1], batch graph Mask_RCNN_FPN_multi); one stream per GPU, no data-path collective",
             "frame": [H, W, 3], "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "num_class": 15,
-            "rpn_topk": 300, "precision": precision, "weights": "seeded synthetic (synth.py, seed 1234)",
+            "rpn_topk": 300, "precision": precision, "input_dtype": input_dtype,
+            "weights": "seeded synthetic (synth.py, seed 1234)",
             "l2": "inputs rotate over distinct batches larger than the 126 MB L2 (4 x 88 MB float32 / 8 x 22 MB uint8) "
                   "and the per-step activation footprint (> 2 GB) exceeds L2",
             "parallelism": "replicas x%d" % n_gpus}
@@ -159,6 +163,66 @@ def cpu_oracle_fps(n_frames, threads):
     return n_frames / dt, dt
 
 
+def stream_record(cfg, device, precision, n_frames=48):
+    """BASELINE configs[0] / [3] shape of work: ONE video stream, batch 1, the per-frame loop of
+    obj_detect_tracking.py:597-696 -- Session.run (upload of the float32 frame, pass, download of boxes / probs / labels /
+    box features) -> create_obj_infos -> pre-tracker NMS -> Tracker.predict / update with the GPU appearance metric.
+    Every class is tracked (up to 100 objects per frame: the stress case).  Returns ms per stage and FPS per stream."""
+    from object_detection_tracking_b200.backend import Session, get_model
+    from object_detection_tracking_b200.synth import synth_frame, synth_weights
+    from object_detection_tracking_b200.tracking import (GpuNearestNeighborDistanceMetric, Tracker, create_obj_infos,
+                                                         non_max_suppression)
+    model = get_model(cfg, gpuid=device, precision=precision)
+    model.set_weights(synth_weights(cfg, 1234))
+    sess = Session()
+    id2class = {i: "class%d" % i for i in range(1, cfg.num_class)}
+    tracked = list(id2class.values())
+    tracker = Tracker(GpuNearestNeighborDistanceMetric("cosine", 0.5, 5, device=device, precision=precision),
+                      max_iou_distance=0.5, max_age=60, n_init=1, device=device, precision=precision)
+    # a video: the same scene drifting by a few pixels per frame (np.roll of a synthetic frame)
+    base = synth_frame(H, W, seed=321, n_rects=12).astype(np.float32)
+    frames = [np.roll(base, (2 * f, 3 * f), axis=(0, 1)) for f in range(8)]
+    t_det = t_glue = t_assoc = 0.0
+    n_obj = 0
+    kept = []                     # the tracker inputs of the timed frames (for the reference-loop leg of cpu_baseline)
+    fetches = [model.final_boxes, model.final_labels, model.final_probs, model.fpn_box_feat]
+    for f in range(n_frames + 4):
+        a = time.perf_counter()
+        boxes, labels, probs, feats = sess.run(fetches, feed_dict=model.get_feed_dict_forward(frames[f % 8]))
+        b = time.perf_counter()
+        dets = create_obj_infos(f, boxes, probs, labels, feats, id2class, tracked, 0.0, 0, 1.0)
+        if dets:
+            keep = non_max_suppression(np.array([d.tlwh for d in dets]), 0.85, np.array([d.confidence for d in dets]))
+            dets = [dets[i] for i in keep]
+        c = time.perf_counter()
+        tracker.predict()
+        tracker.update(dets)
+        live = [t for t in tracker.tracks if t.is_confirmed() and t.time_since_update <= 1]
+        d = time.perf_counter()
+        if f >= 4:                    # first frames: graph capture, workspace growth
+            t_det += b - a; t_glue += c - b; t_assoc += d - c; n_obj += len(dets)
+        kept.append([(x.tlwh.copy(), x.confidence, x.feature.copy()) for x in dets])
+    tracker.close()
+    total = t_det + t_glue + t_assoc
+    return {"what": "one stream, batch 1: Session.run -> create_obj_infos -> NMS -> Tracker.predict/update (GPU cosine metric)",
+            "frames": n_frames, "objects_per_frame": n_obj / n_frames, "detect_ms": t_det / n_frames * 1e3,
+            "glue_ms": t_glue / n_frames * 1e3, "associate_ms": t_assoc / n_frames * 1e3,
+            "fps_per_stream": n_frames / total, "live_tracks_last_frame": len(live),
+            "timing": "host clock around synchronous calls (each call ends with a device sync)", "_dets": kept}
+
+
+def reference_assoc_ms(dets_per_frame):
+    """The reference's own association loop (deep_sort/tracker.py:57-138 restated in oracle/deepsort.py, numpy metric) on the
+    detections the stream record fed to the native tracker: ms per frame on the host (part of cpu_baseline)."""
+    from oracle import deepsort, nn_matching
+    trk = deepsort.Tracker(nn_matching.NearestNeighborDistanceMetric("cosine", 0.5, 5))
+    t0 = time.perf_counter()
+    for dets in dets_per_frame:
+        trk.predict()
+        trk.update([deepsort.Detection(t, c, f) for t, c, f in dets])
+    return (time.perf_counter() - t0) / max(1, len(dets_per_frame)) * 1e3
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -182,7 +246,8 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.gpus, "fp32 (CPU)"),
+            "config": workload_config(args.gpus, args.precision, args.input_dtype),
+            "arith": "float32 on the host CPU (PyTorch port of the reference TF graph), 1 frame per step",
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                              "sample": "%d steps x 1 frame 720x1280 through the CPU oracle (PyTorch fp32 port of "
                                        "the reference TF graph; TensorFlow is not installable here)" % args.steps},
@@ -203,6 +268,9 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=5, help="frames in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default="", help="write the per-layer roofline table here")
+    ap.add_argument("--single-semantics", action="store_true", help="batch of 8 through the single-image graph semantics")
+    ap.add_argument("--sustained-seconds", type=float, default=5.0, help="length of the sustained replay record (0 = skip)")
+    ap.add_argument("--no-stream", action="store_true", help="skip the config-1 detect+track stream record")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -231,8 +299,9 @@ def main():
         torch.cuda.synchronize()
 
     cfg = make_config()
+    # configs[1] is the reference's batch graph (Mask_RCNN_FPN_multi: combined NMS, zero-padded level merge, models.py:2058-2409)
     det = Detector(cfg, BATCH, H, W, device=local_rank, input_dtype=args.input_dtype, precision=args.precision,
-                   use_cuda_graph=True)
+                   use_cuda_graph=True, multi_semantics=not args.single_semantics)
     det.load_weights(synth_weights(cfg, 1234))
     # 4 distinct batches of synthetic frames (seeded per rank), resident on device and in pinned host memory
     np_dt = np.float32 if args.input_dtype == "float32" else np.uint8
@@ -257,6 +326,26 @@ def main():
     barrier()
     sampler.stop.set()
     sampler.join(timeout=2)
+    # ---------------- sustained: the same graph replayed for >= 5 s (what the board settles at under its power cap) ----------------
+    sustained = None
+    if args.sustained_seconds > 0:
+        s2 = ClockSampler(local_rank)
+        s2.start()
+        barrier()
+        n_s, t_s = 0, time.perf_counter()
+        while True:
+            for _ in range(16):
+                det.detect_device(dev[n_s % nb], None, sync=False)
+                n_s += 1
+            det.detect_device(dev[n_s % nb], None, sync=True)
+            n_s += 1
+            if time.perf_counter() - t_s >= args.sustained_seconds:
+                break
+        torch.cuda.synchronize()
+        dt_s = time.perf_counter() - t_s
+        s2.stop.set()
+        s2.join(timeout=2)
+        sustained = {"seconds": dt_s, "steps": n_s, "clocks": s2.summary(), "dt": dt_s}
     # device-side time of one steady-state pass from CUDA events on the launching (context) stream
     det.run_phases(255)
     phase_ms = det.phase_times()
@@ -291,6 +380,11 @@ def main():
 
     from object_detection_tracking_b200 import replicas
     dt, dt_e2e, dt_sync = replicas.max_over_ranks([dt, dt_e2e, dt_sync], device="cuda")     # slowest rank bounds the job
+    if sustained is not None:
+        (dts,) = replicas.max_over_ranks([sustained["dt"] / sustained["steps"]], device="cuda")
+        sustained = {"value": replicas.aggregate_fps(BATCH, dts, world), "unit": "frames/s", "seconds": sustained["seconds"],
+                     "steps_rank0": sustained["steps"], "ms_per_step": dts * 1e3, "clocks": sustained["clocks"]}
+    stream = None if (args.no_stream or rank != 0) else stream_record(cfg, local_rank, args.precision)
     value = replicas.aggregate_fps(args.steps * BATCH, dt, world)
     e2e_value = replicas.aggregate_fps(args.steps * BATCH, dt_e2e, world)
     h2d = host[0].numel() * host[0].element_size()
@@ -326,19 +420,23 @@ def main():
             fps, secs = cpu_oracle_fps(args.cpu_frames, threads)
             cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                    "sample": "%d frames 720x1280 (batch 1) through the CPU oracle in %.1f s" % (args.cpu_frames, secs)}
+            if stream is not None:
+                cpu["associate_ms_per_frame_reference_loop"] = reference_assoc_ms(stream["_dets"])
+        if stream is not None:
+            stream.pop("_dets", None)
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16x2-split (fp32-equivalent products, fp32 accumulate)" if args.precision == "split"
                 else "f16 (fp32 accumulate)",
-                "data": "synthetic", "config": dict(workload_config(world, args.precision), input_dtype=args.input_dtype),
+                "data": "synthetic", "config": workload_config(world, args.precision, args.input_dtype),
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": dt_e2e / args.steps * 1e3,
                         "api": "b2_submit_host/b2_wait (2 slots, pinned %s frames in, all outputs out, every step)" % args.input_dtype,
                         "sync_call_value": replicas.aggregate_fps(args.steps * BATCH, dt_sync, world)},
                 "gpu_launches": det.kernel_launches() * args.steps,
                 "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
-                "phase_ms": phase_ms}
+                "phase_ms": phase_ms, "sustained": sustained, "stream_c1": stream}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -123,6 +123,11 @@ class Mask_RCNN_FPN:
             self._detectors[key] = det
         return det
 
+    def detector(self, batch, height, width) -> Detector:
+        """The engine context behind this model object for a (batch, H, W) plan: queue-fed drivers use its two-slot
+        streaming pair submit_host / wait instead of one synchronous sess.run per batch."""
+        return self._detector(int(batch), int(height), int(width))
+
     def _run(self, fetches, feed_dict):
         img = feed_dict[self.image]
         img = np.asarray(img)

@@ -32,22 +32,21 @@ namespace b2 {
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;                 // fp16 elements = one 128-byte swizzle row (p.bk: 64, or 32 = 64-byte rows)
-constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB at bk = 64
+constexpr int kBlockK = 64;                 // fp16 elements = one 128-byte swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr int kUmmaK = 16;
 constexpr int kEpiHalves = 2;               // column halves of a tile handled by separate epilogue warp quartets
 constexpr int kEpiWarps = 4 * kEpiHalves;   // warps 4..: TMEM lane quarter = warp & 3, column half = (warp - 4) >> 2
 constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kTmemCols = 512;
-constexpr int kMaxStages = 12;
+constexpr int kMaxStages = 8;
+constexpr int kTq = 4;                      // depth of the tile queue between the producer warp and the MMA / epilogue warps
 constexpr int kSmemBudget = 224 * 1024;     // pipeline stages + epilogue staging (alignment slack and barriers on top)
 
 struct ConvTcParams {
   int M, Ho, Wo, HoWo;
   int stride, dil, lower_h, lower_w;
   int S, cin_blocks, num_kb;
-  int bk;            // K elements per pipeline stage: 64 (128-byte swizzle rows) or 32 (64-byte rows, twice the stages)
-  uint32_t a_bytes;  // bytes of one A plane per stage = 128 * bk * 2
   int block_n, num_n_blocks, num_tiles;
   int a_mode;   // 0 = A is a plain [M][Cin] matrix (2D tiled TMA), 1 = im2col TMA
   uint32_t idesc;
@@ -66,7 +65,8 @@ struct ConvTcParams {
   int acc_ring;      // ACC: chunk accumulators in the TMEM ring (2 for 128-column tiles, 6 for 64-column tiles)
   int acc_stride;    // ACC: TMEM columns per accumulator (ring at 0.., the two correction accumulators after it)
   int dbg_nodrain;   // perf experiment only (wrong results): skip the TMEM reads of the ACC drain
-  int l2_prefetch;   // experiment: the producer prefetches the next tile's A operand (and residual tile) into L2
+  float acc_delta;   // ACC: relative compensation of the tensor-core accumulator's truncation (kAccDelta)
+  int* sched;        // dynamic tile scheduler: device counter of this plan (nullptr = static round-robin schedule)
   int epi_mode;      // 0 = direct global loads/stores per thread, 1 = TMA-staged (residual in, result out)
   int epi_grp;       // staged: 16-column chunks per fence / barrier / store group (1 or 2)
   int epi_slots;     // staged: group slots in each column half's staging ring (2, or 3 when a residual is prefetched)
@@ -85,18 +85,16 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 
 // 16 consecutive output channels of one pixel (v = accumulator value): bias, residual, activation, store
 // (fp16 hi/lo planes or fp32) straight to global memory.
-template <bool SPLIT, bool BIAS = true>
+template <bool SPLIT>
 __device__ __forceinline__ void epilogue_chunk16(const ConvTcParams& p, float (&v)[16], size_t opix, size_t rpix, int n) {
-  if (BIAS) {
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+  const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float4 b = __ldg(b4 + j);
-      v[4 * j + 0] += b.x;
-      v[4 * j + 1] += b.y;
-      v[4 * j + 2] += b.z;
-      v[4 * j + 3] += b.w;
-    }
+  for (int j = 0; j < 4; ++j) {
+    float4 b = __ldg(b4 + j);
+    v[4 * j + 0] += b.x;
+    v[4 * j + 1] += b.y;
+    v[4 * j + 2] += b.z;
+    v[4 * j + 3] += b.w;
   }
   if (p.res_hi != nullptr) {
     const uint4* r4 = reinterpret_cast<const uint4*>(p.res_hi + rpix * p.ldr + n);
@@ -131,7 +129,7 @@ __device__ __forceinline__ void epilogue_chunk16(const ConvTcParams& p, float (&
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
   } else if (p.relu == 2) {   // swish: x * sigmoid(x)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], 1.f / (1.f + expf(-v[j])));   // x * sigmoid(x) as the other kernels compute it (the MUFU-only form cost ~3 ulp per swish: D7 c5 off by 3e-5 at 1536^2)
+    for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], 1.f / (1.f + expf(-v[j])));   // x * sigmoid(x) as the other kernels compute it
   }
   if (p.out_f32 != nullptr) {
     float4* o = reinterpret_cast<float4*>(p.out_f32 + opix * p.ldc + n);
@@ -160,19 +158,17 @@ __device__ __forceinline__ void epilogue_chunk16(const ConvTcParams& p, float (&
 
 // Same math on a chunk whose residual sits in (and whose result goes back to) a swizzled shared-memory staging box:
 // hi0 / hi1 (lo0 / lo1 for the lo plane) point at this thread's two 16-byte cells (channels 0-7 and 8-15 of the chunk).
-template <bool SPLIT, bool BIAS = true>
+template <bool SPLIT>
 __device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, float (&v)[16], uint4* hi0, uint4* hi1,
                                                       uint4* lo0, uint4* lo1, int n, bool has_res, bool has_res_lo) {
-  if (BIAS) {
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+  const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float4 b = __ldg(b4 + j);
-      v[4 * j + 0] += b.x;
-      v[4 * j + 1] += b.y;
-      v[4 * j + 2] += b.z;
-      v[4 * j + 3] += b.w;
-    }
+  for (int j = 0; j < 4; ++j) {
+    float4 b = __ldg(b4 + j);
+    v[4 * j + 0] += b.x;
+    v[4 * j + 1] += b.y;
+    v[4 * j + 2] += b.z;
+    v[4 * j + 3] += b.w;
   }
   if (has_res) {
     uint4 r[2] = {*hi0, *hi1};
@@ -205,7 +201,7 @@ __device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, flo
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
   } else if (p.relu == 2) {   // swish: x * sigmoid(x)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], 1.f / (1.f + expf(-v[j])));   // x * sigmoid(x) as the other kernels compute it (the MUFU-only form cost ~3 ulp per swish: D7 c5 off by 3e-5 at 1536^2)
+    for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], 1.f / (1.f + expf(-v[j])));   // x * sigmoid(x) as the other kernels compute it
   }
   uint32_t hi[8];
 #pragma unroll
@@ -230,6 +226,18 @@ __device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, flo
 // buffers and the epilogue warps sum the chunk results in registers with round-to-nearest fp32 adds
 // (overlapped with the MMAs of the next chunk), which brings the result to CUDA-core fp32 accuracy.
 constexpr int kAccChunkKb = 1;   // default: restart every K-block (64 K-elements = 4 truncating accumulations)
+// The (three) truncating adds that remain inside a chunk of four tcgen05.mma shrink every chunk sum toward zero by a small
+// relative amount, i.e. the whole conv output by the same factor (sum_q t_q (1 - eta) = (1 - eta) sum_q t_q).  Measured on
+// the 720x1280 R101 pass against the float64 evaluation of the same graph: the magnitudes of c2..c5 come out 1.8e-7 ...
+// 9.2e-7 too small (the float32 CPU port: +5e-8 ... +1e-9), and that bias IS the error: max |c5 - exact| = 9.5e-7 relative.
+// fmaf(v, kAccDelta, v) (one FFMA per output) gives the loss back: for delta in [2^-24, 1.5 * 2^-24) = [5.96e-8, 8.94e-8)
+// the product is between half an ulp and one and a half ulps of v for every mantissa, so the result is v moved away from
+// zero by exactly one ulp (0.72 * 2^-23 = 8.6e-8 relative on average); smaller values act on part of the mantissa range,
+// values below 2.98e-8 are no-ops.  With it the magnitude bias of c2..c5 is +3e-8 ... +7e-8, c5 is 5.0e-7 ... 6.1e-7 from
+// the exact values (the float32 port: 5.0e-7 ... 5.8e-7) and the final boxes move from 6.1e-4 to 3.1e-4 ... 3.7e-4 px
+// from the exact ones (the float32 port: 2.4e-4 ... 4.9e-4).  Sweeps: profiles/r2_acc_delta_sweep.txt.
+constexpr float kAccDelta = 6.8e-8f;
+constexpr float kAccDelta2 = 1.7e-7f;   // chunks of two K-blocks (seven truncating adds): bias -1.6e-6 at c5 without it
 constexpr int kAccRingMax = 6;
 constexpr int kAccMaxChunks = 8 / kEpiHalves; // ACC tiles are at most 128 columns wide -> chunks of 16 per column half
 
@@ -286,7 +294,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* res_full = bars + 2 * kMaxStages + 4;                       // [2 halves][kEpiSlotsMax]
   uint64_t* c_full = bars + 2 * kMaxStages + 4 + 2 * kEpiSlotsMax;      // [kAccRingMax] ACC chunk accumulator ready
   uint64_t* c_empty = c_full + kAccRingMax;                             // [kAccRingMax] ACC chunk accumulator drained
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(c_empty + kAccRingMax);
+  uint64_t* tq_full = c_empty + kAccRingMax;                            // [kTq] tile index published by the producer warp
+  uint64_t* tq_empty = tq_full + kTq;                                   // [kTq] ... read by the MMA warp and every epilogue warp
+  volatile int* tq_tile = reinterpret_cast<volatile int*>(tq_empty + kTq);   // [kTq]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(const_cast<int*>(tq_tile) + kTq);
   uint8_t* epi = tiles + p.epi_off;
 
   // broadcast from lane 0 so that the compiler treats the warp index (and everything derived from it) as warp-uniform
@@ -315,6 +326,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_init(&c_full[i], 1);
       mbar_init(&c_empty[i], kEpiWarps);
     }
+    for (int i = 0; i < kTq; ++i) {
+      mbar_init(&tq_full[i], 1);
+      mbar_init(&tq_empty[i], 1 + kEpiWarps);
+    }
     fence_mbar_init();
     fence_proxy_async();
   }
@@ -336,8 +351,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const uint32_t tmem_base = *tmem_holder;
   if (tmem_base != 0) __trap();   // the MMA issuer addresses TMEM from column 0 / lane 0 (whole-TMEM allocation)
 
-  const uint32_t a_lo_off = p.a_bytes;
-  const uint32_t b_hi_off = SPLIT ? 2 * p.a_bytes : p.a_bytes;
+  const uint32_t a_lo_off = kABytes;
+  const uint32_t b_hi_off = SPLIT ? 2 * kABytes : kABytes;
   const uint32_t b_lo_off = b_hi_off + p.b_bytes;
   // accumulator stage s: acc0 at column s*256, acc1 (split) at s*256 + 128
   const uint32_t acc_stage_cols = 256;
@@ -353,7 +368,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      // Tile schedule.  The first tile of a CTA is blockIdx.x; every further one is claimed from the plan's device counter
+      // when the loads of the current tile have been issued (p.sched == nullptr: static round-robin).  A CTA that gets
+      // its SM late -- the half-batch chains of the forked pass start their CTAs as the other chain's retire -- then
+      // simply claims fewer tiles, and a partly filled last wave is shared by whoever is free.  The claimed index is
+      // handed to the MMA and epilogue warps through a small queue (tq_*); -1 ends them.
+      int tq_s = 0;
+      uint32_t tq_ph = 0;
+      int tile = blockIdx.x;
+      for (;;) {
+        mbar_wait(&tq_empty[tq_s], tq_ph ^ 1);
+        if (elect_one()) {
+          tq_tile[tq_s] = tile < p.num_tiles ? tile : -1;
+          mbar_arrive(&tq_full[tq_s]);
+        }
+        __syncwarp();
+        if (++tq_s == kTq) {
+          tq_s = 0;
+          tq_ph ^= 1;
+        }
+        if (tile >= p.num_tiles) break;
         const int m_blk = tile / p.num_n_blocks;
         const int n_blk = tile - m_blk * p.num_n_blocks;
         const int m0 = m_blk * kBlockM;
@@ -367,57 +401,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           ch = p.lower_h + pp * p.stride;
           cw = p.lower_w + qq * p.stride;
         }
-        if (p.l2_prefetch) {
-          // next tile of this CTA: pull its A operand (every K-block, both planes) and its residual tile into L2 while
-          // this tile is being processed, so that the stage loads later hit L2 instead of HBM
-          const int nt = tile + gridDim.x;
-          if (nt < p.num_tiles) {
-            const int nm_blk = nt / p.num_n_blocks;
-            const int nn0 = (nt - nm_blk * p.num_n_blocks) * p.block_n;
-            const int nm0 = nm_blk * kBlockM;
-            if (nm_blk != m_blk || p.l2_prefetch > 1) {
-              int nimg = 0, nch = 0, ncw = 0;
-              if (p.a_mode == 1) {
-                nimg = nm0 / p.HoWo;
-                const int rem = nm0 - nimg * p.HoWo;
-                const int pp = rem / p.Wo;
-                nch = p.lower_h + pp * p.stride;
-                ncw = p.lower_w + (rem - pp * p.Wo) * p.stride;
-              }
-              if (elect_one()) {
-                int ptap = 0, pcb = 0;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                  if (p.a_mode == 1) {
-                    const int r = ptap / p.S;
-                    const int s = ptap - r * p.S;
-                    tma_prefetch_im2col_4d(&tmA_hi, pcb * p.bk, ncw, nch, nimg, static_cast<uint16_t>(s * p.dil),
-                                           static_cast<uint16_t>(r * p.dil));
-                    if (SPLIT) tma_prefetch_im2col_4d(&tmA_lo, pcb * p.bk, ncw, nch, nimg, static_cast<uint16_t>(s * p.dil),
-                                                      static_cast<uint16_t>(r * p.dil));
-                  } else {
-                    tma_prefetch_2d(&tmA_hi, pcb * p.bk, nm0);
-                    if (SPLIT) tma_prefetch_2d(&tmA_lo, pcb * p.bk, nm0);
-                  }
-                  if (++pcb == p.cin_blocks) {
-                    pcb = 0;
-                    ++ptap;
-                  }
-                }
-              }
-              __syncwarp();
-            }
-            if (p.epi_mode == 1 && p.res_hi != nullptr) {
-              const int ebox = p.epi_wide ? 32 : 16;
-              if (elect_one()) {
-                for (int c = 0; c < p.block_n; c += ebox) {
-                  tma_prefetch_2d(&tmR_hi, nn0 + c, nm0);
-                  if (SPLIT && p.res_lo != nullptr) tma_prefetch_2d(&tmR_lo, nn0 + c, nm0);
-                }
-              }
-              __syncwarp();
-            }
-          }
-        }
         int tap = 0, cb = 0;   // K-block = (filter tap, 64-channel block)
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -429,14 +412,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               const int s = tap - r * p.S;
               const uint16_t ow = static_cast<uint16_t>(s * p.dil);
               const uint16_t oh = static_cast<uint16_t>(r * p.dil);
-              tma_load_im2col_4d(st, &tmA_hi, &full_bar[stage], cb * p.bk, cw, ch, img, ow, oh);
-              if (SPLIT) tma_load_im2col_4d(st + a_lo_off, &tmA_lo, &full_bar[stage], cb * p.bk, cw, ch, img, ow, oh);
+              tma_load_im2col_4d(st, &tmA_hi, &full_bar[stage], cb * kBlockK, cw, ch, img, ow, oh);
+              if (SPLIT) tma_load_im2col_4d(st + a_lo_off, &tmA_lo, &full_bar[stage], cb * kBlockK, cw, ch, img, ow, oh);
             } else {
-              tma_load_2d(st, &tmA_hi, &full_bar[stage], cb * p.bk, m0);
-              if (SPLIT) tma_load_2d(st + a_lo_off, &tmA_lo, &full_bar[stage], cb * p.bk, m0);
+              tma_load_2d(st, &tmA_hi, &full_bar[stage], cb * kBlockK, m0);
+              if (SPLIT) tma_load_2d(st + a_lo_off, &tmA_lo, &full_bar[stage], cb * kBlockK, m0);
             }
-            tma_load_2d(st + b_hi_off, &tmB_hi, &full_bar[stage], kb * p.bk, n0);
-            if (SPLIT) tma_load_2d(st + b_lo_off, &tmB_lo, &full_bar[stage], kb * p.bk, n0);
+            tma_load_2d(st + b_hi_off, &tmB_hi, &full_bar[stage], kb * kBlockK, n0);
+            if (SPLIT) tma_load_2d(st + b_lo_off, &tmB_lo, &full_bar[stage], kb * kBlockK, n0);
           }
           __syncwarp();
           if (++cb == p.cin_blocks) {
@@ -447,6 +430,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             stage = 0;
             phase ^= 1;
           }
+        }
+        if (p.sched != nullptr) {
+          int claimed = 0;
+          if (lane == 0) {
+            claimed = atomicAdd(p.sched, 1);
+            // the claims of one launch are exactly 0 .. num_tiles-1 (num_tiles - grid successful ones, one failing one per
+            // CTA): whoever draws the last value re-arms the counter for the next launch of this plan
+            if (claimed == p.num_tiles - 1) atomicExch(p.sched, 0);
+          }
+          tile = static_cast<int>(gridDim.x) + __shfl_sync(0xffffffffu, claimed, 0);
+        } else {
+          tile += gridDim.x;
         }
       }
     }
@@ -467,13 +462,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       // shared-memory matrix descriptor (K-major, 128-byte swizzle): low word = start address >> 4 (14 bits) | LBO 1 << 16,
       // high word = SBO 1024 >> 4 | descriptor version 1 << 14 | SWIZZLE_128B 2 << 29; offsets inside the stage and the
       // K advance (32 bytes per UMMA_K) add to the address field without carry (all of shared memory is < 2^18 bytes)
-      // (bk = 32: rows of 64 bytes, SBO 512, layout type 4 = SWIZZLE_64B; the K advance of 32 bytes per UMMA_K is the same)
-      const uint64_t kDescHi = static_cast<uint64_t>(p.bk == 64 ? ((1024u >> 4) | (1u << 14) | (2u << 29))
-                                                                 : ((512u >> 4) | (1u << 14) | (4u << 29))) << 32;
-      const int ksteps = p.bk / kUmmaK;
+      constexpr uint64_t kDescHi = static_cast<uint64_t>((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
       // this CTA owns the whole TMEM of its SM (512 columns, one CTA per SM): the allocation starts at column 0, lane 0
       // (checked after the allocation), so the accumulator addresses are plain constants here
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int tq_s = 0;
+      uint32_t tq_ph = 0;
+      for (;;) {
+        mbar_wait(&tq_full[tq_s], tq_ph);
+        const int tile = tq_tile[tq_s];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tq_empty[tq_s]);
+        if (++tq_s == kTq) {
+          tq_s = 0;
+          tq_ph ^= 1;
+        }
+        if (tile < 0) break;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         // plain: acc0 at as*256, acc1 at as*256+128.  ACC: acc0 chunk buffers at 0 / 128, acc1 at 256 + as*128.
@@ -497,8 +500,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              if (k >= ksteps) break;
-              const uint32_t ko = k * (kUmmaK * 2 >> 4);   // 32 bytes along K inside the swizzle row, in 16-byte units
+              const uint32_t ko = k * (kUmmaK * 2 >> 4);   // 32 bytes along K inside the 128B swizzle row, in 16-byte units
               const uint64_t a_hi = kDescHi | (d_a_hi + ko);
               const uint64_t b_hi = kDescHi | (d_b_hi + ko);
               const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
@@ -546,13 +548,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ring, own named barrier, own elected TMA thread); together they halve the time per tile of the epilogue, which
     // bounds the short-K layers and -- in ACC mode, where the same warps must keep draining chunk accumulators --
     // stalls the MMA issuer for as long as a tile's output stage takes.
-#ifdef B2_BIAS_INIT
-    // ACC: the running sums start from the bias (loaded while the first chunk is still being multiplied) instead of
-    // zero, which takes 4 dependent L1/L2 loads + 16 adds per chunk out of the output stage
-    constexpr bool kBiasInChunk = !ACC;
-#else
-    constexpr bool kBiasInChunk = true;
-#endif
     const int ew = warp & 3;
     const int hf = (warp - 4) >> 2;
     const int row = ew * 32 + lane;
@@ -585,41 +580,80 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int bar_id = 1 + hf;
     int slot = 0, la_slot = 0;
     uint32_t rph = 0;        // phase bits of rfull[]
-    int la_tile = blockIdx.x, la_c = 0;   // look-ahead cursor of the residual prefetch (elected thread only)
-    auto issue_res_group = [&]() {   // called by every thread of the half (the cursor is warp-uniform state)
-      if (la_tile >= p.num_tiles || my_n == 0) return;
+    // Look-ahead cursor of the residual prefetch (state of the issuing warp of this half only).  The tile sequence comes
+    // from the producer's queue; an entry beyond the tile this warp is working on may not be published yet (the producer
+    // publishes tile i+1 once the loads of tile i are out), so the cursor advances with a non-blocking test there and the
+    // issue is retried at the next opportunity; entries up to the current tile are always published.
+    int la_tile = blockIdx.x, la_c = 0;
+    uint32_t la_seq = 0, cur_seq = 0;          // queue sequence numbers of la_tile / of the tile being processed
+    bool la_need_adv = false, la_done = my_n == 0;
+    int la_issued = 0, la_want = 0, n_consumed = 0;   // residual groups issued / wanted by now / waited for
+    auto la_try_issue = [&]() -> bool {          // issuing warp only; false = the next tile is not known yet
+      if (la_done) return true;
+      if (la_need_adv) {
+        const uint32_t seq = la_seq + 1;
+        const int qs = static_cast<int>(seq % kTq);
+        const uint32_t ph = (seq / kTq) & 1u;
+        if (seq <= cur_seq) mbar_wait(&tq_full[qs], ph);   // already consumed by the main loop: published
+        else if (!mbar_try_wait(&tq_full[qs], ph)) return false;
+        la_tile = tq_tile[qs];
+        la_seq = seq;
+        la_need_adv = false;
+        if (la_tile < 0) {
+          la_done = true;
+          return true;
+        }
+      }
       const int m_blk = la_tile / p.num_n_blocks;
       const int n_blk = la_tile - m_blk * p.num_n_blocks;
       const int gn = (my_n - la_c) < grp ? (my_n - la_c) : grp;
       const int col = n_blk * p.block_n + (c_beg + la_c) * 16;
       uint8_t* b = ring + la_slot * slot_bytes;
       uint64_t* bar = &rfull[la_slot];
-      if (issuer) {
-        if (elect_one()) {
-          mbar_expect_tx(bar, gn * kEpiPlaneBytes * (res_lo ? 2 : 1));
-          if (p.epi_wide) {   // one 32-column box per plane (groups are always full in wide mode)
-            tma_load_2d(b, &tmR_hi, bar, col, m_blk * kBlockM);
-            if (res_lo) tma_load_2d(b + 2 * kEpiPlaneBytes, &tmR_lo, bar, col, m_blk * kBlockM);
-          } else {
-            for (int u = 0; u < gn; ++u) {
-              tma_load_2d(b + u * p.epi_chunk_bytes, &tmR_hi, bar, col + u * 16, m_blk * kBlockM);
-              if (res_lo) tma_load_2d(b + u * p.epi_chunk_bytes + kEpiPlaneBytes, &tmR_lo, bar, col + u * 16, m_blk * kBlockM);
-            }
+      if (elect_one()) {
+        mbar_expect_tx(bar, gn * kEpiPlaneBytes * (res_lo ? 2 : 1));
+        if (p.epi_wide) {   // one 32-column box per plane (groups are always full in wide mode)
+          tma_load_2d(b, &tmR_hi, bar, col, m_blk * kBlockM);
+          if (res_lo) tma_load_2d(b + 2 * kEpiPlaneBytes, &tmR_lo, bar, col, m_blk * kBlockM);
+        } else {
+          for (int u = 0; u < gn; ++u) {
+            tma_load_2d(b + u * p.epi_chunk_bytes, &tmR_hi, bar, col + u * 16, m_blk * kBlockM);
+            if (res_lo) tma_load_2d(b + u * p.epi_chunk_bytes + kEpiPlaneBytes, &tmR_lo, bar, col + u * 16, m_blk * kBlockM);
           }
         }
-        __syncwarp();
       }
+      __syncwarp();
       la_c += gn;
       if (la_c >= my_n) {
         la_c = 0;
-        la_tile += gridDim.x;
+        la_need_adv = true;
       }
       if (++la_slot == nslots) la_slot = 0;
+      ++la_issued;
+      return true;
+    };
+    // brings the prefetch up to the wanted look-ahead where the tile sequence is known
+    auto issue_res_group = [&]() {
+      if (!issuer) return;
+      ++la_want;
+      while (la_issued < la_want && !la_done)
+        if (!la_try_issue()) break;
     };
     if (staged && has_res)
       for (int i = 0; i < nslots - 1; ++i) issue_res_group();
 
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    int tq_s = 0;
+    uint32_t tq_ph = 0;
+    for (;;) {
+      mbar_wait(&tq_full[tq_s], tq_ph);
+      const int tile = tq_tile[tq_s];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tq_empty[tq_s]);
+      if (++tq_s == kTq) {
+        tq_s = 0;
+        tq_ph ^= 1;
+      }
+      if (tile < 0) break;
       const int m_blk = tile / p.num_n_blocks;
       const int n_blk = tile - m_blk * p.num_n_blocks;
       const int n0 = n_blk * p.block_n;
@@ -642,12 +676,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       auto chunk_out = [&](int c, float (&v)[16]) {
         const int n = n0 + (c_beg + c) * 16;
         if (!staged) {
-          if (valid) epilogue_chunk16<SPLIT, kBiasInChunk>(p, v, opix, rpix, n);
+          if (valid) epilogue_chunk16<SPLIT>(p, v, opix, rpix, n);
           return;
         }
         const int u = grp == 2 ? (c & 1) : 0;      // position inside the group
         uint8_t* sb = ring + slot * slot_bytes;
         if (u == 0 && has_res) {
+          if (issuer) {   // the load of this group may have been deferred (tile not yet known at its look-ahead point)
+            while (la_issued <= n_consumed && !la_done) la_try_issue();
+          }
+          ++n_consumed;
           mbar_wait(&rfull[slot], (rph >> slot) & 1u);
           rph ^= 1u << slot;
         }
@@ -669,7 +707,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             c1 = (1 ^ sw) << 4;
             lo_off = kEpiPlaneBytes;
           }
-          epilogue_chunk16_smem<SPLIT, kBiasInChunk>(p, v, reinterpret_cast<uint4*>(hp + c0), reinterpret_cast<uint4*>(hp + c1),
+          epilogue_chunk16_smem<SPLIT>(p, v, reinterpret_cast<uint4*>(hp + c0), reinterpret_cast<uint4*>(hp + c1),
                                        reinterpret_cast<uint4*>(hp + lo_off + c0), reinterpret_cast<uint4*>(hp + lo_off + c1), n,
                                        has_res, res_lo);
         }
@@ -707,28 +745,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
       if (ACC) {
         float sums[kAccMaxChunks * 16];
-        if (kBiasInChunk) {
 #pragma unroll
-          for (int i = 0; i < kAccMaxChunks * 16; ++i) sums[i] = 0.0f;
-        } else {
-#pragma unroll
-          for (int c = 0; c < kAccMaxChunks; ++c) {
-            if (c < my_n) {
-              const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + (c_beg + c) * 16);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 b = __ldg(b4 + j);
-                sums[c * 16 + 4 * j + 0] = b.x;
-                sums[c * 16 + 4 * j + 1] = b.y;
-                sums[c * 16 + 4 * j + 2] = b.z;
-                sums[c * 16 + 4 * j + 3] = b.w;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) sums[c * 16 + i] = 0.0f;
-            }
-          }
-        }
+        for (int i = 0; i < kAccMaxChunks * 16; ++i) sums[i] = 0.0f;
         const int nq = (p.num_kb + p.acc_kb - 1) / p.acc_kb;
         for (int q = 0; q < nq; ++q) {
           const int cbuf = ecbuf;
@@ -745,33 +763,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
         acc_fold<true>(sums, tmem_base + lane_off + (p.acc_ring + as) * p.acc_stride + c_beg * 16, my_n, &tmem_empty[as], lane);
-#ifdef B2_ROLL_OUT
-        // one copy of the output-stage body, executed my_n times: unrolled over the (statically indexed) running sums it
-        // is ~37 KB of straight-line code per tile, and ncu's stall sampling showed the epilogue warps waiting for
-        // instruction fetch (no_inst) for a third of the output stage
-#pragma unroll 1
-        for (int c = 0; c < my_n; ++c) {
-          float v[16];
-#pragma unroll
-          for (int k = 0; k < kAccMaxChunks; ++k) {
-            if (c == k) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = sums[(ACC ? k : 0) * 16 + i];
-            }
-          }
-          chunk_out(c, v);
-        }
-#else
 #pragma unroll
         for (int c = 0; c < kAccMaxChunks; ++c) {
           if (c < my_n) {
             float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = sums[(ACC ? c : 0) * 16 + i];
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(sums[(ACC ? c : 0) * 16 + i], p.acc_delta, sums[(ACC ? c : 0) * 16 + i]);
             chunk_out(c, v);
           }
         }
-#endif
       } else {
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
@@ -786,7 +786,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             v[i] = __uint_as_float(a0[i]);
-            if (SPLIT) v[i] = fmaf(__uint_as_float(a1[i]), kLoInv, v[i]);
+            if (SPLIT) {
+              v[i] = fmaf(v[i], p.acc_delta, v[i]);   // the same compensation for the single-chunk (K <= 64) split layers
+              v[i] = fmaf(__uint_as_float(a1[i]), kLoInv, v[i]);
+            }
           }
           chunk_out(c, v);
         }
@@ -798,6 +801,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         as = 0;
         aphase ^= 1;
       }
+      ++cur_seq;
     }
     if (staged && issuer) {   // the output must be globally written before the CTA retires
       if (elect_one()) bulk_wait_all();
@@ -856,6 +860,7 @@ struct ConvPlan {
   bool acc;
   int grid;
   size_t smem_bytes;
+  int* sched = nullptr;   // device counter of the dynamic tile scheduler (owned by the plan)
 };
 
 int conv_tc_init() {
@@ -888,13 +893,6 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
                       int num_sms, int force_a_mode) {
   B2_CHECK(conv_tc_init() == 0, "conv_tc_init failed");
   B2_CHECK(d.Cin % kBlockK == 0, "conv_tc: Cin must be a multiple of 64");
-  // experiment hook (round 2): half-size pipeline stages (32 K-elements, 64-byte swizzle rows) in split precision.  A
-  // split-precision stage of 64 K-elements is 64 KB, so only 2-3 stages fit beside the epilogue ring and the operand
-  // latency (TMA issue -> data: 1-2 us under load) is not covered; half stages keep the same bytes resident with twice
-  // the stages in flight (B2_BK32=1: every split layer, =2: only layers with a residual ring)
-  int bk = kBlockK;
-  if (const char* e = getenv("B2_BK32"))
-    if (split && (atoi(e) == 1 || (atoi(e) == 2 && io.res_hi != nullptr))) bk = 32;
   B2_CHECK(w.Cout_pad % 16 == 0, "conv_tc: Cout_pad must be a multiple of 16");
   B2_CHECK(w.K == d.R * d.S * d.Cin, "conv_tc: packed weight K mismatch");
   B2_CHECK(!split || (io.in_lo && w.w_lo), "conv_tc: split precision needs lo planes");
@@ -910,9 +908,7 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   p.lower_h = -d.pad_t;
   p.lower_w = -d.pad_l;
   p.S = d.S;
-  p.bk = bk;
-  p.a_bytes = static_cast<uint32_t>(kBlockM) * bk * 2;
-  p.cin_blocks = d.Cin / bk;
+  p.cin_blocks = d.Cin / kBlockK;
   p.num_kb = d.R * d.S * p.cin_blocks;
   p.block_n = pick_block_n(w.Cout_pad, split);
   // short-K layers in split precision (K <= 256: at most four accumulation chunks per tile) are bound by the output
@@ -932,8 +928,8 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   const int num_m_blocks = (p.M + kBlockM - 1) / kBlockM;
   p.num_tiles = num_m_blocks * p.num_n_blocks;
   p.idesc = make_idesc_f16(kBlockM, p.block_n);
-  p.b_bytes = static_cast<uint32_t>(p.block_n) * bk * 2;
-  p.stage_bytes = (p.a_bytes + p.b_bytes) * (split ? 2 : 1);
+  p.b_bytes = static_cast<uint32_t>(p.block_n) * kBlockK * 2;
+  p.stage_bytes = (kABytes + p.b_bytes) * (split ? 2 : 1);
   // TMA-staged epilogue: fp16 plane output with a 1:1 row mapping (no placement offset, no shifted residual)
   {
     const bool one_to_one = d.off_h == 0 && d.off_w == 0 && d.out_H == Ho && d.out_W == Wo;
@@ -992,20 +988,20 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   pl->split = split;
   // accurate accumulation: on by default in split precision when K spans more than one chunk
   p.dbg_nodrain = getenv("B2_ACC_NODRAIN") != nullptr;
-  p.l2_prefetch = getenv("B2_L2_PREFETCH") ? atoi(getenv("B2_L2_PREFETCH")) : 0;
+  p.acc_delta = getenv("B2_ACC_DELTA") ? static_cast<float>(atof(getenv("B2_ACC_DELTA"))) : kAccDelta;
+  const float acc_delta2 = getenv("B2_ACC_DELTA2") ? static_cast<float>(atof(getenv("B2_ACC_DELTA2"))) : kAccDelta2;
   p.acc_kb = d.acc_kb > 0 ? d.acc_kb : kAccChunkKb;
   if (const char* e = getenv("B2_ACC_KB")) p.acc_kb = atoi(e) > 0 ? atoi(e) : kAccChunkKb;   // experiment hook
-  const int kb_per_64 = kBlockK / bk;   // acc_kb counts 64-element K-blocks in the interface; the kernel counts stages
   // experiment hook (round 2): two K-blocks per chunk on the K <= 256 layers only.  A 4-K-block tile then has two
   // chunks = exactly the ring, so the MMA issuer can finish tile i+1 while the epilogue warps are still in the output
   // stage of tile i (with one K-block per chunk it stalls after two of four), and the drains per tile halve; costs
   // 8 instead of 4 truncating accumulation steps on those layers (all layers at 2: boxes 1.07e-3 px instead of 7.3e-4)
-  if (const char* e = getenv("B2_ACC_KB_SHORTK")) if (p.num_kb <= 4 * kb_per_64 && atoi(e) > 0) p.acc_kb = atoi(e);
-  p.acc_kb *= kb_per_64;
+  if (const char* e = getenv("B2_ACC_KB_SHORTK")) if (p.num_kb <= 4 && atoi(e) > 0) p.acc_kb = atoi(e);
   pl->acc = split && d.acc_kb >= 0 && p.num_kb > p.acc_kb && getenv("B2_NO_ACC") == nullptr;
+  if (p.acc_kb >= 2) p.acc_delta = acc_delta2;
   p.acc_stride = p.block_n == 64 ? 64 : 128;
   p.acc_ring = p.block_n == 64 ? kAccRingMax : 2;   // (ring + 2 correction accumulators) * stride <= 512 columns
-  if (const char* e = getenv("B2_ACC_MIN_KB")) pl->acc = pl->acc && p.num_kb > atoi(e) * kb_per_64;   // experiment hook
+  if (const char* e = getenv("B2_ACC_MIN_KB")) pl->acc = pl->acc && p.num_kb > atoi(e);   // experiment hook
   pl->grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   pl->smem_bytes = static_cast<size_t>(p.num_stages) * p.stage_bytes + epi_bytes + 1024 /*align*/ + 512 /*barriers*/;
   const int in_ld = d.in_ld > 0 ? d.in_ld : d.Cin;
@@ -1017,7 +1013,6 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
     p.a_mode = force_a_mode;
   }
   const size_t in_bytes = static_cast<size_t>(d.B) * d.in_pitch_H * d.in_pitch_W * in_ld * 2;
-  const CUtensorMapSwizzle op_swz = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   for (int plane = 0; plane < (split ? 2 : 1); ++plane) {
     CUtensorMap* mA = plane == 0 ? &pl->tmA_hi : &pl->tmA_lo;
     CUtensorMap* mB = plane == 0 ? &pl->tmB_hi : &pl->tmB_lo;
@@ -1025,7 +1020,7 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
     const __half* b = plane == 0 ? w.w_hi : w.w_lo;
     if (p.a_mode == 0) {
       if (encode_2d(mA, a, d.Cin, static_cast<uint64_t>(d.B) * d.in_H * d.in_W, static_cast<uint64_t>(in_ld) * 2,
-                    bk, kBlockM, op_swz))
+                    kBlockK, kBlockM))
         return -1;
     } else {
       cuuint64_t dims[4] = {static_cast<cuuint64_t>(d.Cin), static_cast<cuuint64_t>(d.in_W),
@@ -1038,8 +1033,8 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
       int upper[2] = {d.pad_r - (d.S - 1) * d.dil, d.pad_b - (d.R - 1) * d.dil};
       cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(d.stride), static_cast<cuuint32_t>(d.stride), 1};
       CUresult r = g_encode_im2col(mA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(a), dims, strides,
-                                   lower, upper, bk, kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                   op_swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   lower, upper, kBlockK, kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeIm2col failed: " + std::to_string(static_cast<int>(r)) + " (Cin=" +
@@ -1048,7 +1043,7 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
       }
       small_tensor_fixup(mA, in_bytes);
     }
-    if (encode_2d(mB, b, w.K, w.Cout_pad, static_cast<uint64_t>(w.K) * 2, bk, p.block_n, op_swz)) return -1;
+    if (encode_2d(mB, b, w.K, w.Cout_pad, static_cast<uint64_t>(w.K) * 2, kBlockK, p.block_n)) return -1;
   }
   if (!split) {
     pl->tmA_lo = pl->tmA_hi;
@@ -1084,10 +1079,24 @@ ConvPlan* conv_tc_plan_create(const ConvDesc& d, const ConvWeights& w, const Con
     delete pl;
     return nullptr;
   }
+  // dynamic tile schedule when the CTAs have more than one tile each (B2_STATIC_SCHED=1: round-robin, for A/B runs)
+  pl->p.sched = nullptr;
+  if (pl->p.num_tiles > pl->grid && getenv("B2_STATIC_SCHED") == nullptr) {
+    if (cudaMalloc(&pl->sched, sizeof(int)) != cudaSuccess || cudaMemset(pl->sched, 0, sizeof(int)) != cudaSuccess) {
+      set_error("conv_tc: cannot allocate the tile-scheduler counter");
+      if (pl->sched) cudaFree(pl->sched);
+      delete pl;
+      return nullptr;
+    }
+    pl->p.sched = pl->sched;
+  }
   return pl;
 }
 
-void conv_tc_plan_destroy(ConvPlan* p) { delete p; }
+void conv_tc_plan_destroy(ConvPlan* p) {
+  if (p && p->sched) cudaFree(p->sched);
+  delete p;
+}
 
 #ifdef B2_PDL
 template <typename K>

@@ -23,7 +23,14 @@ BN_EPS = 1e-3
 
 
 def _t(a):
-    return torch.from_numpy(np.ascontiguousarray(a))
+    """float32 by default; float64 inside `with oracle.frcnn.exact():` (the rounding-noise-free evaluation, see frcnn.py)."""
+    from .frcnn import _DT
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return t.to(_DT[-1]) if t.is_floating_point() else t
+
+
+def _np(t):
+    return t.to(torch.float32).numpy()
 
 
 def swish(x):
@@ -212,7 +219,7 @@ def box_features(fpn_feats, boxes, levels, cfg):
         ids = np.where(levels == l)[0]
         if len(ids):
             bf = (boxes[ids] * np.float32(1.0 / (2.0 ** l))).astype(np.float32)
-            r = frcnn.roi_align(fpn_feats[l][0].numpy(), bf, 7)          # [K,C,7,7]
+            r = frcnn.roi_align(_np(fpn_feats[l][0]), bf, 7)          # [K,C,7,7]
             out[ids] = r.mean(axis=(2, 3), dtype=np.float32)
     return out
 
@@ -223,11 +230,11 @@ def forward_from_features(cfg, W, features, image_scale=1.0, stages=False, parti
     fs = feat_sizes(cfg)
     with torch.no_grad():
         feats = build_feature_network({l: _t(features[l])[None] for l in (3, 4, 5)}, W, cfg, BIFPN_NODES, fs)
-        cls_out = {l: head_net(feats[l], W, l, cfg, "class")[0].permute(1, 2, 0).contiguous().numpy() for l in feats}
-        box_out = {l: head_net(feats[l], W, l, cfg, "box")[0].permute(1, 2, 0).contiguous().numpy() for l in feats}
+        cls_out = {l: _np(head_net(feats[l], W, l, cfg, "class")[0].permute(1, 2, 0).contiguous()) for l in feats}
+        box_out = {l: _np(head_net(feats[l], W, l, cfg, "box")[0].permute(1, 2, 0).contiguous()) for l in feats}
     boxes, scores, classes, levels = postprocess(cls_out, box_out, cfg, fs, image_scale, partial_class_idxs)
     res = dict(final_boxes=boxes, final_probs=scores, final_labels=classes, levels=levels,
                fpn_box_feat=box_features(feats, boxes, levels, cfg))
     if stages:
-        res.update(fpn={l: feats[l][0].numpy() for l in feats}, cls_out=cls_out, box_out=box_out)
+        res.update(fpn={l: _np(feats[l][0]) for l in feats}, cls_out=cls_out, box_out=box_out)
     return res

@@ -77,7 +77,14 @@ def endpoint_blocks(blocks):
 
 
 def _t(a):
-    return torch.from_numpy(np.ascontiguousarray(a))
+    """float32 by default; float64 inside `with oracle.frcnn.exact():` (the rounding-noise-free evaluation, see frcnn.py)."""
+    from .frcnn import _DT
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return t.to(_DT[-1]) if t.is_floating_point() else t
+
+
+def _np(t):
+    return t.to(torch.float32).numpy()
 
 
 def swish(x):
@@ -137,13 +144,13 @@ def forward(image_nhwc, W, name, stages=False):
     with torch.no_grad():
         x = _t(np.asarray(image_nhwc, np.float32)).permute(2, 0, 1)[None]
         x = swish(bn(conv(x, W, name + "/stem/conv2d", stride=2), W, name + "/stem/tpu_batch_normalization"))
-        every["stem"] = x[0].numpy()
+        every["stem"] = _np(x[0])
         for i, b in enumerate(blocks):
             x = mbconv(x, W, "%s/blocks_%d" % (name, i), b)
             if stages:
-                every["block_%d" % i] = x[0].numpy()
+                every["block_%d" % i] = _np(x[0])
             if i in red:
-                out[red.index(i) + 1] = x[0].numpy()
+                out[red.index(i) + 1] = _np(x[0])
     res = {l: out[l] for l in (3, 4, 5)}
     if stages:
         res["stages"] = every

@@ -34,6 +34,26 @@ def main():
     t = time.time(); det.run_phases(255); print("gpu pass %.1f ms" % ((time.time() - t) * 1e3), det.phase_times())
     for b in range(B):
         o = frcnn.forward(cfg, Wt, frames[b])
+        with frcnn.exact():
+            x = frcnn.forward(cfg, Wt, frames[b])
+        # summary against the float64 evaluation (the centre both float32 realisations scatter around)
+        def sd(a, bb):
+            d = np.abs(a[:, None, :].astype(np.float64) - bb[None, :, :].astype(np.float64)).max(-1)
+            return max(d.min(1).max(), d.min(0).max())
+        for i in range(4):
+            g = det.get_stage("c%d" % (i + 2))[b].transpose(2, 0, 1).astype(np.float64)
+            r = x["c2345"][i].astype(np.float64)
+            print("EXACT b%d c%d rel %.3e  magnitude bias (sum|gpu|-sum|ref|)/sum|ref| %+.3e   [oracle32: rel %.3e bias %+.3e]" % (
+                b, i + 2, np.abs(g - r).max() / np.abs(r).max(), (np.abs(g).sum() - np.abs(r).sum()) / np.abs(r).sum(),
+                np.abs(o["c2345"][i] - r).max() / np.abs(r).max(),
+                (np.abs(o["c2345"][i].astype(np.float64)).sum() - np.abs(r).sum()) / np.abs(r).sum()))
+        fcx = int(det.get_stage("final_count")[b].reshape(-1)[0])
+        fbx = det.get_stage("final_boxes")[b].reshape(-1, 4)[:fcx]
+        pcx = int(det.get_stage("proposal_count")[b].reshape(-1)[0])
+        pbx = det.get_stage("proposal_boxes")[b].reshape(-1, 4)[:pcx]
+        print("EXACT b%d proposals set-dist gpu %.3e oracle32 %.3e | final boxes set-dist gpu %.3e oracle32 %.3e (counts gpu %d exact %d)" % (
+            b, sd(pbx, x["proposal_boxes"]), sd(o["proposal_boxes"], x["proposal_boxes"]),
+            sd(fbx, x["final_boxes"]), sd(o["final_boxes"], x["final_boxes"]), fcx, len(x["final_boxes"])))
         for i in range(4):
             g = det.get_stage("c%d" % (i + 2))[b].transpose(2, 0, 1)
             e = (g.astype(np.float64) - o["c2345"][i]) / np.abs(o["c2345"][i]).max()
