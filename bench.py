@@ -122,7 +122,9 @@ def measured_peaks():
 def ncu_traffic(precision):
     """dram__bytes_read.sum + dram__bytes_write.sum per conv_tc_kernel launch (average over the launches of one
     pass) from the committed ncu capture of the same workload, or None when no capture is committed."""
-    p = os.path.join(ROOT, "profiles", "r1_conv_tc_dram_%s_b8.json" % precision)
+    p = os.path.join(ROOT, "profiles", "r2_conv_tc_dram_%s_b8.json" % precision)     # this round's capture first
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r1_conv_tc_dram_%s_b8.json" % precision)
     if not os.path.exists(p):
         return None
     d = json.load(open(p))
@@ -439,6 +441,7 @@ def main():
                 "phase_ms": phase_ms, "sustained": sustained, "stream_c1": stream}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()              # rank 0 is the only one with the stream / cpu_baseline legs: the others wait for it
         dist.destroy_process_group()
 
 

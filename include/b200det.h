@@ -292,7 +292,9 @@ int b2_track_pair_cost(int device, const float* a, const int32_t* seg_a, int N, 
  * share of the camera pairs against the other ranks' galleries in place).
  * b2_gallery_create uploads a gallery [rows, D] into a cudaMalloc'ed buffer and returns the 64-byte CUDA IPC handle other
  * ranks pass to b2_gallery_open (exchange the handles with any host-side channel, e.g. torch.distributed objects);
- * b2_gallery_close unmaps a peer gallery, b2_gallery_free releases an own one (after the peers have closed it). */
+ * b2_gallery_close unmaps a peer gallery, b2_gallery_free releases an own one (after the peers have closed it).
+ * The call runs on a private non-blocking stream and returns when `out` is complete: device inputs must be complete when it
+ * is entered (synchronise the stream / collective that produced them first). */
 int b2_track_pair_cost_dev(int device, const float* a_dev, const int32_t* seg_a, int N, const float* b_dev,
                            const int32_t* seg_b, int M, int D, const uint8_t* gate, float fill, int precision, float* out);
 int b2_gallery_create(int device, const float* feats_host, int rows, int D, float** dev_out, uint8_t handle_out[64]);

@@ -82,6 +82,9 @@ struct ConvIO {
   float* out_f32 = nullptr;       // when set, fp32 output instead of fp16 planes
   const __half* res_hi = nullptr;
   const __half* res_lo = nullptr;
+  // device word that the kernel ORs with 1 when an fp16-plane output leaves the representable range (|x| > 65504: the
+  // hi plane would hold inf and every later layer would silently compute on it); nullptr = not monitored
+  unsigned int* range_flag = nullptr;
 };
 
 // A fully prepared tensor-core conv launch (tensor maps encoded once, reused every frame).

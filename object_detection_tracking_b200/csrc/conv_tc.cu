@@ -40,7 +40,6 @@ constexpr int kEpiWarps = 4 * kEpiHalves;   // warps 4..: TMEM lane quarter = wa
 constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 8;
-constexpr int kTq = 4;                      // depth of the tile queue between the producer warp and the MMA / epilogue warps
 constexpr int kSmemBudget = 224 * 1024;     // pipeline stages + epilogue staging (alignment slack and barriers on top)
 
 struct ConvTcParams {
@@ -66,7 +65,7 @@ struct ConvTcParams {
   int acc_stride;    // ACC: TMEM columns per accumulator (ring at 0.., the two correction accumulators after it)
   int dbg_nodrain;   // perf experiment only (wrong results): skip the TMEM reads of the ACC drain
   float acc_delta;   // ACC: relative compensation of the tensor-core accumulator's truncation (kAccDelta)
-  int* sched;        // dynamic tile scheduler: device counter of this plan (nullptr = static round-robin schedule)
+  unsigned int* range_flag;   // ORed with 1 when a plane output exceeds the fp16 range (nullptr = not monitored)
   int epi_mode;      // 0 = direct global loads/stores per thread, 1 = TMA-staged (residual in, result out)
   int epi_grp;       // staged: 16-column chunks per fence / barrier / store group (1 or 2)
   int epi_slots;     // staged: group slots in each column half's staging ring (2, or 3 when a residual is prefetched)
@@ -85,8 +84,9 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 
 // 16 consecutive output channels of one pixel (v = accumulator value): bias, residual, activation, store
 // (fp16 hi/lo planes or fp32) straight to global memory.
-template <bool SPLIT>
-__device__ __forceinline__ void epilogue_chunk16(const ConvTcParams& p, float (&v)[16], size_t opix, size_t rpix, int n) {
+template <bool SPLIT, bool SWISH>
+__device__ __forceinline__ void epilogue_chunk16(const ConvTcParams& p, float (&v)[16], size_t opix, size_t rpix, int n,
+                                                 float& amax) {
   const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -127,7 +127,8 @@ __device__ __forceinline__ void epilogue_chunk16(const ConvTcParams& p, float (&
   if (p.relu == 1) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
-  } else if (p.relu == 2) {   // swish: x * sigmoid(x)
+  } else if (SWISH && p.relu == 2) {   // swish: x * sigmoid(x) -- only in the SWISH instantiations (EfficientDet): the
+    // accurate expf + division are ~30 instructions per element, 2000 per kernel once inlined into every chunk copy
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], 1.f / (1.f + expf(-v[j])));   // x * sigmoid(x) as the other kernels compute it
   }
@@ -137,6 +138,10 @@ __device__ __forceinline__ void epilogue_chunk16(const ConvTcParams& p, float (&
     for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     return;
   }
+#ifndef B2_NO_RANGE   // build variant for A/B runs: without the range monitor
+#pragma unroll
+  for (int j = 0; j < 16; ++j) amax = fmaxf(amax, fabsf(v[j]));
+#endif
   uint32_t hi[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) hi[j] = pack_half2(v[2 * j], v[2 * j + 1]);
@@ -158,9 +163,10 @@ __device__ __forceinline__ void epilogue_chunk16(const ConvTcParams& p, float (&
 
 // Same math on a chunk whose residual sits in (and whose result goes back to) a swizzled shared-memory staging box:
 // hi0 / hi1 (lo0 / lo1 for the lo plane) point at this thread's two 16-byte cells (channels 0-7 and 8-15 of the chunk).
-template <bool SPLIT>
+template <bool SPLIT, bool SWISH>
 __device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, float (&v)[16], uint4* hi0, uint4* hi1,
-                                                      uint4* lo0, uint4* lo1, int n, bool has_res, bool has_res_lo) {
+                                                      uint4* lo0, uint4* lo1, int n, bool has_res, bool has_res_lo,
+                                                      float& amax) {
   const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -199,10 +205,15 @@ __device__ __forceinline__ void epilogue_chunk16_smem(const ConvTcParams& p, flo
   if (p.relu == 1) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
-  } else if (p.relu == 2) {   // swish: x * sigmoid(x)
+  } else if (SWISH && p.relu == 2) {   // swish: x * sigmoid(x) -- only in the SWISH instantiations (EfficientDet): the
+    // accurate expf + division are ~30 instructions per element, 2000 per kernel once inlined into every chunk copy
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], 1.f / (1.f + expf(-v[j])));   // x * sigmoid(x) as the other kernels compute it
   }
+#ifndef B2_NO_RANGE   // build variant for A/B runs: without the range monitor
+#pragma unroll
+  for (int j = 0; j < 16; ++j) amax = fmaxf(amax, fabsf(v[j]));
+#endif
   uint32_t hi[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) hi[j] = pack_half2(v[2 * j], v[2 * j + 1]);
@@ -273,7 +284,7 @@ __device__ __forceinline__ void acc_fold(float (&sums)[kAccMaxChunks * 16], uint
   }
 }
 
-template <bool SPLIT, bool ACC>
+template <bool SPLIT, bool ACC, bool SWISH>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -294,10 +305,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* res_full = bars + 2 * kMaxStages + 4;                       // [2 halves][kEpiSlotsMax]
   uint64_t* c_full = bars + 2 * kMaxStages + 4 + 2 * kEpiSlotsMax;      // [kAccRingMax] ACC chunk accumulator ready
   uint64_t* c_empty = c_full + kAccRingMax;                             // [kAccRingMax] ACC chunk accumulator drained
-  uint64_t* tq_full = c_empty + kAccRingMax;                            // [kTq] tile index published by the producer warp
-  uint64_t* tq_empty = tq_full + kTq;                                   // [kTq] ... read by the MMA warp and every epilogue warp
-  volatile int* tq_tile = reinterpret_cast<volatile int*>(tq_empty + kTq);   // [kTq]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(const_cast<int*>(tq_tile) + kTq);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(c_empty + kAccRingMax);
   uint8_t* epi = tiles + p.epi_off;
 
   // broadcast from lane 0 so that the compiler treats the warp index (and everything derived from it) as warp-uniform
@@ -325,10 +333,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     for (int i = 0; i < kAccRingMax; ++i) {
       mbar_init(&c_full[i], 1);
       mbar_init(&c_empty[i], kEpiWarps);
-    }
-    for (int i = 0; i < kTq; ++i) {
-      mbar_init(&tq_full[i], 1);
-      mbar_init(&tq_empty[i], 1 + kEpiWarps);
     }
     fence_mbar_init();
     fence_proxy_async();
@@ -368,26 +372,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     {
       int stage = 0;
       uint32_t phase = 0;
-      // Tile schedule.  The first tile of a CTA is blockIdx.x; every further one is claimed from the plan's device counter
-      // when the loads of the current tile have been issued (p.sched == nullptr: static round-robin).  A CTA that gets
-      // its SM late -- the half-batch chains of the forked pass start their CTAs as the other chain's retire -- then
-      // simply claims fewer tiles, and a partly filled last wave is shared by whoever is free.  The claimed index is
-      // handed to the MMA and epilogue warps through a small queue (tq_*); -1 ends them.
-      int tq_s = 0;
-      uint32_t tq_ph = 0;
-      int tile = blockIdx.x;
-      for (;;) {
-        mbar_wait(&tq_empty[tq_s], tq_ph ^ 1);
-        if (elect_one()) {
-          tq_tile[tq_s] = tile < p.num_tiles ? tile : -1;
-          mbar_arrive(&tq_full[tq_s]);
-        }
-        __syncwarp();
-        if (++tq_s == kTq) {
-          tq_s = 0;
-          tq_ph ^= 1;
-        }
-        if (tile >= p.num_tiles) break;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int m_blk = tile / p.num_n_blocks;
         const int n_blk = tile - m_blk * p.num_n_blocks;
         const int m0 = m_blk * kBlockM;
@@ -431,18 +416,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             phase ^= 1;
           }
         }
-        if (p.sched != nullptr) {
-          int claimed = 0;
-          if (lane == 0) {
-            claimed = atomicAdd(p.sched, 1);
-            // the claims of one launch are exactly 0 .. num_tiles-1 (num_tiles - grid successful ones, one failing one per
-            // CTA): whoever draws the last value re-arms the counter for the next launch of this plan
-            if (claimed == p.num_tiles - 1) atomicExch(p.sched, 0);
-          }
-          tile = static_cast<int>(gridDim.x) + __shfl_sync(0xffffffffu, claimed, 0);
-        } else {
-          tile += gridDim.x;
-        }
       }
     }
   } else if (warp == 1) {
@@ -465,18 +438,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       constexpr uint64_t kDescHi = static_cast<uint64_t>((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
       // this CTA owns the whole TMEM of its SM (512 columns, one CTA per SM): the allocation starts at column 0, lane 0
       // (checked after the allocation), so the accumulator addresses are plain constants here
-      int tq_s = 0;
-      uint32_t tq_ph = 0;
-      for (;;) {
-        mbar_wait(&tq_full[tq_s], tq_ph);
-        const int tile = tq_tile[tq_s];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tq_empty[tq_s]);
-        if (++tq_s == kTq) {
-          tq_s = 0;
-          tq_ph ^= 1;
-        }
-        if (tile < 0) break;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         // plain: acc0 at as*256, acc1 at as*256+128.  ACC: acc0 chunk buffers at 0 / 128, acc1 at 256 + as*128.
@@ -580,80 +542,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int bar_id = 1 + hf;
     int slot = 0, la_slot = 0;
     uint32_t rph = 0;        // phase bits of rfull[]
-    // Look-ahead cursor of the residual prefetch (state of the issuing warp of this half only).  The tile sequence comes
-    // from the producer's queue; an entry beyond the tile this warp is working on may not be published yet (the producer
-    // publishes tile i+1 once the loads of tile i are out), so the cursor advances with a non-blocking test there and the
-    // issue is retried at the next opportunity; entries up to the current tile are always published.
-    int la_tile = blockIdx.x, la_c = 0;
-    uint32_t la_seq = 0, cur_seq = 0;          // queue sequence numbers of la_tile / of the tile being processed
-    bool la_need_adv = false, la_done = my_n == 0;
-    int la_issued = 0, la_want = 0, n_consumed = 0;   // residual groups issued / wanted by now / waited for
-    auto la_try_issue = [&]() -> bool {          // issuing warp only; false = the next tile is not known yet
-      if (la_done) return true;
-      if (la_need_adv) {
-        const uint32_t seq = la_seq + 1;
-        const int qs = static_cast<int>(seq % kTq);
-        const uint32_t ph = (seq / kTq) & 1u;
-        if (seq <= cur_seq) mbar_wait(&tq_full[qs], ph);   // already consumed by the main loop: published
-        else if (!mbar_try_wait(&tq_full[qs], ph)) return false;
-        la_tile = tq_tile[qs];
-        la_seq = seq;
-        la_need_adv = false;
-        if (la_tile < 0) {
-          la_done = true;
-          return true;
-        }
-      }
+    int la_tile = blockIdx.x, la_c = 0;   // look-ahead cursor of the residual prefetch (elected thread only)
+    auto issue_res_group = [&]() {   // called by every thread of the half (the cursor is warp-uniform state)
+      if (la_tile >= p.num_tiles || my_n == 0) return;
       const int m_blk = la_tile / p.num_n_blocks;
       const int n_blk = la_tile - m_blk * p.num_n_blocks;
       const int gn = (my_n - la_c) < grp ? (my_n - la_c) : grp;
       const int col = n_blk * p.block_n + (c_beg + la_c) * 16;
       uint8_t* b = ring + la_slot * slot_bytes;
       uint64_t* bar = &rfull[la_slot];
-      if (elect_one()) {
-        mbar_expect_tx(bar, gn * kEpiPlaneBytes * (res_lo ? 2 : 1));
-        if (p.epi_wide) {   // one 32-column box per plane (groups are always full in wide mode)
-          tma_load_2d(b, &tmR_hi, bar, col, m_blk * kBlockM);
-          if (res_lo) tma_load_2d(b + 2 * kEpiPlaneBytes, &tmR_lo, bar, col, m_blk * kBlockM);
-        } else {
-          for (int u = 0; u < gn; ++u) {
-            tma_load_2d(b + u * p.epi_chunk_bytes, &tmR_hi, bar, col + u * 16, m_blk * kBlockM);
-            if (res_lo) tma_load_2d(b + u * p.epi_chunk_bytes + kEpiPlaneBytes, &tmR_lo, bar, col + u * 16, m_blk * kBlockM);
+      if (issuer) {
+        if (elect_one()) {
+          mbar_expect_tx(bar, gn * kEpiPlaneBytes * (res_lo ? 2 : 1));
+          if (p.epi_wide) {   // one 32-column box per plane (groups are always full in wide mode)
+            tma_load_2d(b, &tmR_hi, bar, col, m_blk * kBlockM);
+            if (res_lo) tma_load_2d(b + 2 * kEpiPlaneBytes, &tmR_lo, bar, col, m_blk * kBlockM);
+          } else {
+            for (int u = 0; u < gn; ++u) {
+              tma_load_2d(b + u * p.epi_chunk_bytes, &tmR_hi, bar, col + u * 16, m_blk * kBlockM);
+              if (res_lo) tma_load_2d(b + u * p.epi_chunk_bytes + kEpiPlaneBytes, &tmR_lo, bar, col + u * 16, m_blk * kBlockM);
+            }
           }
         }
+        __syncwarp();
       }
-      __syncwarp();
       la_c += gn;
       if (la_c >= my_n) {
         la_c = 0;
-        la_need_adv = true;
+        la_tile += gridDim.x;
       }
       if (++la_slot == nslots) la_slot = 0;
-      ++la_issued;
-      return true;
-    };
-    // brings the prefetch up to the wanted look-ahead where the tile sequence is known
-    auto issue_res_group = [&]() {
-      if (!issuer) return;
-      ++la_want;
-      while (la_issued < la_want && !la_done)
-        if (!la_try_issue()) break;
     };
     if (staged && has_res)
       for (int i = 0; i < nslots - 1; ++i) issue_res_group();
 
-    int tq_s = 0;
-    uint32_t tq_ph = 0;
-    for (;;) {
-      mbar_wait(&tq_full[tq_s], tq_ph);
-      const int tile = tq_tile[tq_s];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tq_empty[tq_s]);
-      if (++tq_s == kTq) {
-        tq_s = 0;
-        tq_ph ^= 1;
-      }
-      if (tile < 0) break;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.num_n_blocks;
       const int n_blk = tile - m_blk * p.num_n_blocks;
       const int n0 = n_blk * p.block_n;
@@ -672,20 +595,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           rpix = (static_cast<size_t>(img) * p.res_H + (pp >> p.res_shift)) * p.res_W + (qq >> p.res_shift);
         }
       }
+      float amax = 0.f;   // largest |output| this thread writes in this tile (range monitor)
       // one finished chunk (relative index c in this half): bias / residual / activation, then out
       auto chunk_out = [&](int c, float (&v)[16]) {
         const int n = n0 + (c_beg + c) * 16;
         if (!staged) {
-          if (valid) epilogue_chunk16<SPLIT>(p, v, opix, rpix, n);
+          if (valid) epilogue_chunk16<SPLIT, SWISH>(p, v, opix, rpix, n, amax);
           return;
         }
         const int u = grp == 2 ? (c & 1) : 0;      // position inside the group
         uint8_t* sb = ring + slot * slot_bytes;
         if (u == 0 && has_res) {
-          if (issuer) {   // the load of this group may have been deferred (tile not yet known at its look-ahead point)
-            while (la_issued <= n_consumed && !la_done) la_try_issue();
-          }
-          ++n_consumed;
           mbar_wait(&rfull[slot], (rph >> slot) & 1u);
           rph ^= 1u << slot;
         }
@@ -707,9 +627,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             c1 = (1 ^ sw) << 4;
             lo_off = kEpiPlaneBytes;
           }
-          epilogue_chunk16_smem<SPLIT>(p, v, reinterpret_cast<uint4*>(hp + c0), reinterpret_cast<uint4*>(hp + c1),
+          epilogue_chunk16_smem<SPLIT, SWISH>(p, v, reinterpret_cast<uint4*>(hp + c0), reinterpret_cast<uint4*>(hp + c1),
                                        reinterpret_cast<uint4*>(hp + lo_off + c0), reinterpret_cast<uint4*>(hp + lo_off + c1), n,
-                                       has_res, res_lo);
+                                       has_res, res_lo, amax);
         }
         if (u == grp - 1 || c == my_n - 1) {
           fence_proxy_async();
@@ -801,7 +721,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         as = 0;
         aphase ^= 1;
       }
-      ++cur_seq;
+      // inf included; a NaN can only follow an inf, which an earlier launch has flagged
+      if (p.range_flag != nullptr && amax > 65504.f) atomicOr(p.range_flag, 1u);
     }
     if (staged && issuer) {   // the output must be globally written before the CTA retires
       if (elect_one()) bulk_wait_all();
@@ -860,7 +781,6 @@ struct ConvPlan {
   bool acc;
   int grid;
   size_t smem_bytes;
-  int* sched = nullptr;   // device counter of the dynamic tile scheduler (owned by the plan)
 };
 
 int conv_tc_init() {
@@ -875,9 +795,12 @@ int conv_tc_init() {
   B2_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q));
   B2_CHECK(fn != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeIm2col not available");
   g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
-  B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   return 0;
 }
 
@@ -990,6 +913,7 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   p.dbg_nodrain = getenv("B2_ACC_NODRAIN") != nullptr;
   p.acc_delta = getenv("B2_ACC_DELTA") ? static_cast<float>(atof(getenv("B2_ACC_DELTA"))) : kAccDelta;
   const float acc_delta2 = getenv("B2_ACC_DELTA2") ? static_cast<float>(atof(getenv("B2_ACC_DELTA2"))) : kAccDelta2;
+  p.range_flag = io.range_flag;
   p.acc_kb = d.acc_kb > 0 ? d.acc_kb : kAccChunkKb;
   if (const char* e = getenv("B2_ACC_KB")) p.acc_kb = atoi(e) > 0 ? atoi(e) : kAccChunkKb;   // experiment hook
   // experiment hook (round 2): two K-blocks per chunk on the K <= 256 layers only.  A 4-K-block tile then has two
@@ -1079,24 +1003,10 @@ ConvPlan* conv_tc_plan_create(const ConvDesc& d, const ConvWeights& w, const Con
     delete pl;
     return nullptr;
   }
-  // dynamic tile schedule when the CTAs have more than one tile each (B2_STATIC_SCHED=1: round-robin, for A/B runs)
-  pl->p.sched = nullptr;
-  if (pl->p.num_tiles > pl->grid && getenv("B2_STATIC_SCHED") == nullptr) {
-    if (cudaMalloc(&pl->sched, sizeof(int)) != cudaSuccess || cudaMemset(pl->sched, 0, sizeof(int)) != cudaSuccess) {
-      set_error("conv_tc: cannot allocate the tile-scheduler counter");
-      if (pl->sched) cudaFree(pl->sched);
-      delete pl;
-      return nullptr;
-    }
-    pl->p.sched = pl->sched;
-  }
   return pl;
 }
 
-void conv_tc_plan_destroy(ConvPlan* p) {
-  if (p && p->sched) cudaFree(p->sched);
-  delete p;
-}
+void conv_tc_plan_destroy(ConvPlan* p) { delete p; }
 
 #ifdef B2_PDL
 template <typename K>
@@ -1117,23 +1027,29 @@ static cudaError_t launch_pdl(K kernel, const ConvPlan* pl, cudaStream_t stream)
 #endif
 
 int conv_tc_launch(const ConvPlan* pl, cudaStream_t stream) {
+  const bool sw = pl->p.relu == 2;
+#define B2_CONV_LAUNCH(S, A, W)                                                                                          \
+  conv_tc_kernel<S, A, W><<<pl->grid, kThreads, pl->smem_bytes, stream>>>(pl->tmA_hi, pl->tmA_lo, pl->tmB_hi, pl->tmB_lo, \
+                                                                          pl->tmO_hi, pl->tmO_lo, pl->tmR_hi, pl->tmR_lo, pl->p)
 #ifdef B2_PDL
   if (getenv("B2_PDL_OFF") == nullptr) {
-    if (pl->split && pl->acc) B2_CUDA(launch_pdl(conv_tc_kernel<true, true>, pl, stream));
-    else if (pl->split) B2_CUDA(launch_pdl(conv_tc_kernel<true, false>, pl, stream));
-    else B2_CUDA(launch_pdl(conv_tc_kernel<false, false>, pl, stream));
+    if (pl->split && pl->acc) B2_CUDA(sw ? launch_pdl(conv_tc_kernel<true, true, true>, pl, stream) : launch_pdl(conv_tc_kernel<true, true, false>, pl, stream));
+    else if (pl->split) B2_CUDA(sw ? launch_pdl(conv_tc_kernel<true, false, true>, pl, stream) : launch_pdl(conv_tc_kernel<true, false, false>, pl, stream));
+    else B2_CUDA(sw ? launch_pdl(conv_tc_kernel<false, false, true>, pl, stream) : launch_pdl(conv_tc_kernel<false, false, false>, pl, stream));
     return 0;
   }
 #endif
-  if (pl->split && pl->acc)
-    conv_tc_kernel<true, true><<<pl->grid, kThreads, pl->smem_bytes, stream>>>(
-        pl->tmA_hi, pl->tmA_lo, pl->tmB_hi, pl->tmB_lo, pl->tmO_hi, pl->tmO_lo, pl->tmR_hi, pl->tmR_lo, pl->p);
-  else if (pl->split)
-    conv_tc_kernel<true, false><<<pl->grid, kThreads, pl->smem_bytes, stream>>>(
-        pl->tmA_hi, pl->tmA_lo, pl->tmB_hi, pl->tmB_lo, pl->tmO_hi, pl->tmO_lo, pl->tmR_hi, pl->tmR_lo, pl->p);
-  else
-    conv_tc_kernel<false, false><<<pl->grid, kThreads, pl->smem_bytes, stream>>>(
-        pl->tmA_hi, pl->tmA_lo, pl->tmB_hi, pl->tmB_lo, pl->tmO_hi, pl->tmO_lo, pl->tmR_hi, pl->tmR_lo, pl->p);
+  if (pl->split && pl->acc) {
+    if (sw) B2_CONV_LAUNCH(true, true, true);
+    else B2_CONV_LAUNCH(true, true, false);
+  } else if (pl->split) {
+    if (sw) B2_CONV_LAUNCH(true, false, true);
+    else B2_CONV_LAUNCH(true, false, false);
+  } else {
+    if (sw) B2_CONV_LAUNCH(false, false, true);
+    else B2_CONV_LAUNCH(false, false, false);
+  }
+#undef B2_CONV_LAUNCH
   B2_CUDA(cudaGetLastError());
   return 0;
 }

@@ -152,6 +152,10 @@ struct b2_ctx {
   cudaEvent_t pass_done[2] = {nullptr, nullptr};
   cudaEvent_t h2d_done[2] = {nullptr, nullptr}, staged_free[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
   bool slot_busy[2] = {false, false};
+  // range monitor: conv_tc_kernel ORs the device word when an fp16-plane output exceeds +-65504 (or is NaN); the word is
+  // read back with every host-facing result (h_range: [0], [1] = submit slots, [2] = synchronous calls)
+  unsigned int* range_flag = nullptr;
+  unsigned int* h_range = nullptr;
   Planes stem_u, c1, pool, cfeat[4], lat[4], pfeat[5], rpn_h[5];
   float* rpn_out[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   RpnParams rpn;
@@ -259,6 +263,7 @@ Layer* add_conv(b2_ctx* c, int phase, const std::string& name, const Planes& in,
   L->io.in_hi = in.hi; L->io.in_lo = in.lo;
   L->io.out_hi = out.hi; L->io.out_lo = out.lo; L->io.out_f32 = out_f32;
   if (res) { L->io.res_hi = res->hi; L->io.res_lo = res->lo; }
+  L->io.range_flag = c->range_flag;
   Layer* raw = L.get();
   c->layers.push_back(std::move(L));
   c->steps.push_back({phase, 0, raw});
@@ -321,6 +326,10 @@ int build_plan(b2_ctx* c) {
   // ---- input + stem + pool (phase 0) ----
   c->img_bytes = static_cast<size_t>(B) * H * W * 3 * (cfg.input_dtype == 1 ? 1 : 4);
   c->img = c->alloc<uint8_t>(c->img_bytes);
+  c->range_flag = c->alloc<unsigned int>(1);
+  B2_CHECK(c->range_flag != nullptr, "out of device memory (range flag)");
+  B2_CUDA(cudaMallocHost(&c->h_range, 3 * sizeof(unsigned int)));
+  c->h_range[0] = c->h_range[1] = c->h_range[2] = 0;
   // compact stem operand [B][c1h + 3][c1w + 3][16]; conv0 reads 64-channel pixels out of it with a pixel stride of 16 (stem.cu)
   B2_CHECK(c->alloc_planes(c->stem_u, B, c->c1h + 3, c->c1w + 3, 16), "alloc stem operand");
   B2_CHECK(c->alloc_planes(c->c1, B, c->c1h, c->c1w, 64), "alloc c1");
@@ -778,6 +787,19 @@ int bn_fold(const WeightSet& ws, const std::string& scope, int C, std::vector<do
 
 int upload_layer(b2_ctx* c, Layer* L, const std::vector<float>& packed, const std::vector<float>& bias) {
   const size_t n = packed.size();
+  // the (hi, lo) operand planes are fp16: a folded weight beyond +-65504 (or a non-finite one) would become inf here and
+  // NaN inside the MMA (inf * 0) -- refuse it at load time; activations are watched by the kernel's range monitor
+  for (size_t i = 0; i < n; ++i)
+    if (!(fabsf(packed[i]) <= 65504.f)) {
+      set_error("weight of layer '" + L->name + "' outside the fp16-plane range (|w| > 65504 after BatchNorm folding, or not "
+                "finite): this checkpoint is not representable in the (hi, lo) fp16 operand format");
+      return -1;
+    }
+  for (size_t i = 0; i < bias.size(); ++i)
+    if (!std::isfinite(bias[i])) {
+      set_error("bias / folded BatchNorm shift of layer '" + L->name + "' is not finite");
+      return -1;
+    }
   float* tmp = nullptr;
   B2_CUDA(cudaMalloc(&tmp, n * sizeof(float)));
   B2_CUDA(cudaMemcpyAsync(tmp, packed.data(), n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
@@ -932,6 +954,7 @@ void b2_destroy(b2_ctx* c) {
     if (c->side_stream[h]) cudaStreamDestroy(c->side_stream[h]);
   }
   if (c->raw_frames) cudaFree(c->raw_frames);
+  if (c->h_range) cudaFreeHost(c->h_range);
   for (void* p : c->allocs) cudaFree(p);
   for (int i = 0; i <= NPHASE; ++i)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -959,12 +982,16 @@ int b2_load_weights(b2_ctx* c, const char* const* names, const float* const* dat
   return 0;
 }
 
+static int range_failed(b2_ctx* c, int idx);
+
 int b2_run_phases(b2_ctx* c, int mask) {
   B2_CHECK(c, "b2_run_phases: null ctx");
   B2_CUDA(cudaSetDevice(c->device));
   B2_CHECK(c->weights_loaded, "b2_run_phases: weights not loaded");
   if (enqueue(c, mask, true)) return -1;
+  B2_CUDA(cudaMemcpyAsync(&c->h_range[2], c->range_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
   B2_CUDA(cudaStreamSynchronize(c->stream));
+  if (range_failed(c, 2)) return -1;
   int last = -1;
   for (int ph = 0; ph < NPHASE; ++ph) {
     c->phase_ms[ph] = 0.f;
@@ -1074,6 +1101,17 @@ static int run_all(b2_ctx* c) {
   return enqueue(c, B2_PHASE_ALL, false);
 }
 
+// The pass left the representable range of the fp16 activation planes somewhere (the kernel flags |x| > 65504 or NaN at the
+// store): the results of this call are not trustworthy.  The flag is cleared so that the next pass is judged on its own.
+static int range_failed(b2_ctx* c, int idx) {
+  if (c->h_range[idx] == 0) return 0;
+  c->h_range[idx] = 0;
+  cudaMemsetAsync(c->range_flag, 0, sizeof(unsigned int), c->stream);
+  set_error("activation outside the fp16-plane range (|x| > 65504 or NaN) in a convolution output: the weights / input are "
+            "not conditioned for the (hi, lo) fp16 representation (DESIGN.md section 3)");
+  return -1;
+}
+
 static int copy_outputs(b2_ctx* c, float* boxes, float* probs, int32_t* labels, int32_t* valid, float* box_feat,
                         int feat_mode, cudaMemcpyKind kind) {
   const int B = c->cfg.batch, R = c->cfg.result_per_im, C = c->cfg.fpn_num_channel;
@@ -1111,7 +1149,11 @@ int b2_detect(b2_ctx* c, const void* frames_dev, float* boxes, float* probs, int
     B2_CUDA(cudaMemcpyAsync(c->img, frames_dev, c->img_bytes, cudaMemcpyDeviceToDevice, c->stream));
   if (run_all(c)) return -1;
   if (copy_outputs(c, boxes, probs, labels, valid, box_feat, feat_mode, cudaMemcpyDeviceToDevice)) return -1;
-  if (sync) B2_CUDA(cudaStreamSynchronize(c->stream));
+  if (sync) {
+    B2_CUDA(cudaMemcpyAsync(&c->h_range[2], c->range_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return range_failed(c, 2);
+  }
   return 0;
 }
 
@@ -1123,8 +1165,9 @@ int b2_detect_host(b2_ctx* c, const void* frames_host, float* boxes, float* prob
   B2_CUDA(cudaMemcpyAsync(c->img, frames_host, c->img_bytes, cudaMemcpyHostToDevice, c->stream));
   if (run_all(c)) return -1;
   if (copy_outputs(c, boxes, probs, labels, valid, box_feat, feat_mode, cudaMemcpyDeviceToHost)) return -1;
+  B2_CUDA(cudaMemcpyAsync(&c->h_range[2], c->range_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
   B2_CUDA(cudaStreamSynchronize(c->stream));
-  return 0;
+  return range_failed(c, 2);
 }
 
 // Frame ingest with the resize on the device (reference host path: frame.astype("float32") ->
@@ -1153,8 +1196,9 @@ int b2_detect_host_resize(b2_ctx* c, const uint8_t* frames_u8, int src_h, int sr
                        c->stream)) return -1;
   if (run_all(c)) return -1;
   if (copy_outputs(c, boxes, probs, labels, valid, box_feat, feat_mode, cudaMemcpyDeviceToHost)) return -1;
+  B2_CUDA(cudaMemcpyAsync(&c->h_range[2], c->range_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
   B2_CUDA(cudaStreamSynchronize(c->stream));
-  return 0;
+  return range_failed(c, 2);
 }
 
 // The resize alone (parity tests): host uint8 [n, src_h, src_w, 3] -> host float32 [n, dst_h, dst_w, 3].
@@ -1237,6 +1281,7 @@ static int submit_impl(b2_ctx* c, const void* frames_host, int src_h, int src_w,
   if (copy_outputs(c, boxes ? reinterpret_cast<float*>(d_boxes) : nullptr, probs ? reinterpret_cast<float*>(d_probs) : nullptr,
                    labels ? reinterpret_cast<int32_t*>(d_labels) : nullptr, valid ? reinterpret_cast<int32_t*>(d_valid) : nullptr,
                    box_feat ? reinterpret_cast<float*>(d_feat) : nullptr, feat_mode, cudaMemcpyDeviceToDevice)) return -1;
+  B2_CUDA(cudaMemcpyAsync(&c->h_range[slot], c->range_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
   B2_CUDA(cudaEventRecord(c->pass_done[slot], c->stream));
   cudaStream_t ds = c->down_stream;
   B2_CUDA(cudaStreamWaitEvent(ds, c->pass_done[slot], 0));
@@ -1272,7 +1317,7 @@ int b2_wait(b2_ctx* c, int slot) {
   B2_CHECK(c->slot_busy[slot], "b2_wait: nothing was submitted on this slot");
   B2_CUDA(cudaEventSynchronize(c->out_done[slot]));
   c->slot_busy[slot] = false;
-  return 0;
+  return range_failed(c, slot);
 }
 
 // RCNN_FPN_givenbox (models.py:1816-1967; get_model_feat :121-131): features of GIVEN boxes on one frame -- backbone + FPN,

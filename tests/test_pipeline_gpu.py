@@ -252,3 +252,34 @@ def test_batch_graph_semantics_match_oracle_multi():
     single = frcnn.forward(cfg, Wt, frames[0], stages=True)
     assert len(single["proposal_scores"]) >= len(ref["per_image"][0]["proposal_scores"])
     det.close()
+
+
+def test_out_of_range_activations_fail_loudly():
+    """Activations are stored as fp16 (hi, lo) planes: |x| > 65504 would put inf into the hi plane and every later layer
+    would silently compute on it.  conv_tc_kernel flags such a store and every host-facing call
+    returns an error; the flag does not stick to the next pass."""
+    from object_detection_tracking_b200.config import make_config
+    from object_detection_tracking_b200.engine import Detector
+    from object_detection_tracking_b200.synth import synth_frame, synth_weights
+    H, W = 192, 256
+    cfg = make_config(resnet_num_block=(1, 1, 1, 1), max_size=W, short_edge_size=H)
+    Wt = synth_weights(cfg, 5)
+    frame = synth_frame(H, W, 2).astype(np.float32)[None]
+    bad = dict(Wt)
+    bad["group1/block0/conv2/W"] = Wt["group1/block0/conv2/W"] * np.float32(1.5e5)    # weights still inside the fp16 range
+    det = Detector(cfg, 1, H, W, precision="split", use_cuda_graph=True)
+    worse = dict(Wt)
+    worse["group1/block0/conv2/W"] = Wt["group1/block0/conv2/W"] * np.float32(1e9)    # the operand planes themselves overflow
+    with pytest.raises(RuntimeError, match="outside the fp16-plane range"):
+        det.load_weights(worse)
+    det.load_weights(bad)
+    with pytest.raises(RuntimeError, match="fp16-plane range"):
+        det.detect_host(frame)
+    outs = det.alloc_outputs()
+    det.submit_host(frame, outs, 0)
+    with pytest.raises(RuntimeError, match="fp16-plane range"):
+        det.wait(0)
+    det.load_weights(Wt)                      # same context, conditioned weights: clean again
+    out = det.detect_host(frame)
+    assert int(out["valid"][0]) > 0 and np.isfinite(out["boxes"]).all()
+    det.close()

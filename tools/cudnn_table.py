@@ -39,7 +39,10 @@ def main():
             hit = [v for kk, v in t.items() if kk[2] == ci and kk[3] == k and kk[5] == s and kk[6] == dl and kk[7] == co
                    and abs(kk[0] - H) <= 4 and abs(kk[1] - W) <= 4]
             if hit:
-                ms, fl, n = hit[0]
+                keys = [kk for kk in t if kk[2] == ci and kk[3] == k and kk[5] == s and kk[6] == dl and kk[7] == co
+                        and abs(kk[0] - H) <= 4 and abs(kk[1] - W) <= 4]
+                best = min(range(len(hit)), key=lambda i: abs(keys[i][0] - H) + abs(keys[i][1] - W))
+                ms, fl, n = hit[best]
                 n_l = n
                 cells.append("%.4f (%.0f)" % (ms / n, fl / (ms * 1e-3) / 1e12))
             else:
