@@ -159,7 +159,8 @@ EConv* add_pw(b2_effdet* c, const std::string& wname, const std::string& biasnam
   // a threshold for throughput experiments.
   {
     static const int min_k = getenv("B2_EFFDET_ACC_MIN_K") ? atoi(getenv("B2_EFFDET_ACC_MIN_K")) : 0;
-    d.acc_kb = in.C <= min_k ? -1 : 0;
+    static const int chunk = getenv("B2_EFFDET_ACC_KB") ? atoi(getenv("B2_EFFDET_ACC_KB")) : 0;   // 0 = the kernel's default (1)
+    d.acc_kb = in.C <= min_k ? -1 : chunk;
   }
   d.out_H = in.H; d.out_W = in.W; d.ldc = out_f32 ? ldc32 : out.C;
   L->w.Cout_pad = pad16(cout_real);
