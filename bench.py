@@ -157,10 +157,11 @@ def cpu_oracle_fps(n_frames, threads):
     from oracle import frcnn      # cpu_baseline / reference arm: the one place bench.py executes oracle/
     cfg = make_config()
     Wt = synth_weights(cfg, 1234)
-    frcnn.forward(cfg, Wt, synth_frame(H, W, 99).astype(np.float32), stages=False)     # warm-up
+    # the batch graph (Mask_RCNN_FPN_multi semantics, the workload both arms name), one frame per call
+    frcnn.forward_multi(cfg, Wt, [synth_frame(H, W, 99).astype(np.float32)])           # warm-up
     t0 = time.perf_counter()
     for i in range(n_frames):
-        frcnn.forward(cfg, Wt, synth_frame(H, W, i).astype(np.float32), stages=False)
+        frcnn.forward_multi(cfg, Wt, [synth_frame(H, W, i).astype(np.float32)])
     dt = time.perf_counter() - t0
     return n_frames / dt, dt
 
@@ -239,10 +240,10 @@ def run_reference(args, rank, world):
     Wt = synth_weights(cfg, 1234)
     frames = [synth_frame(H, W, i).astype(np.float32) for i in range(4)]
     for i in range(args.warmup):
-        frcnn.forward(cfg, Wt, frames[i % 4], stages=False)
+        frcnn.forward_multi(cfg, Wt, [frames[i % 4]])        # the batch graph's semantics, one frame per step
     t0 = time.perf_counter()
     for i in range(args.steps):
-        frcnn.forward(cfg, Wt, frames[i % 4], stages=False)
+        frcnn.forward_multi(cfg, Wt, [frames[i % 4]])
     dt = time.perf_counter() - t0
     fps = args.steps * frames_per_step / dt
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
