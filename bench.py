@@ -166,16 +166,20 @@ def cpu_oracle_fps(n_frames, threads):
     return n_frames / dt, dt
 
 
-def stream_record(cfg, device, precision, n_frames=48):
+def stream_record(cfg, device, precision, n_frames=48, opt_in=False):
     """BASELINE configs[0] / [3] shape of work: ONE video stream, batch 1, the per-frame loop of
     obj_detect_tracking.py:597-696 -- Session.run (upload of the float32 frame, pass, download of boxes / probs / labels /
     box features) -> create_obj_infos -> pre-tracker NMS -> Tracker.predict / update with the GPU appearance metric.
-    Every class is tracked (up to 100 objects per frame: the stress case).  Returns ms per stage and FPS per stream."""
+    Every class is tracked (up to 100 objects per frame: the stress case).  Returns ms per stage and FPS per stream.
+    opt_in=True: the two boundary extensions of INTEGRATION.md 2d / 2e -- the frame crosses PCIe as uint8 (what the decoder
+    produces; the reference casts to float32 on the host first) and `fpn_box_feat` comes back mean-pooled over the 7x7 grid
+    ([R,256], feat_mode 1: the mean create_obj_infos would take on the host)."""
     from object_detection_tracking_b200.backend import Session, get_model
     from object_detection_tracking_b200.synth import synth_frame, synth_weights
     from object_detection_tracking_b200.tracking import (GpuNearestNeighborDistanceMetric, Tracker, create_obj_infos,
                                                          non_max_suppression)
-    model = get_model(cfg, gpuid=device, precision=precision)
+    model = get_model(cfg, gpuid=device, precision=precision, input_dtype="uint8" if opt_in else "float32",
+                      feat_mode=1 if opt_in else 0)
     model.set_weights(synth_weights(cfg, 1234))
     sess = Session()
     id2class = {i: "class%d" % i for i in range(1, cfg.num_class)}
@@ -183,8 +187,8 @@ def stream_record(cfg, device, precision, n_frames=48):
     tracker = Tracker(GpuNearestNeighborDistanceMetric("cosine", 0.5, 5, device=device, precision=precision),
                       max_iou_distance=0.5, max_age=60, n_init=1, device=device, precision=precision)
     # a video: the same scene drifting by a few pixels per frame (np.roll of a synthetic frame)
-    base = synth_frame(H, W, seed=321, n_rects=12).astype(np.float32)
-    frames = [np.roll(base, (2 * f, 3 * f), axis=(0, 1)) for f in range(8)]
+    base = synth_frame(H, W, seed=321, n_rects=12).astype(np.uint8 if opt_in else np.float32)
+    frames = [np.ascontiguousarray(np.roll(base, (2 * f, 3 * f), axis=(0, 1))) for f in range(8)]
     t_det = t_glue = t_assoc = 0.0
     n_obj = 0
     kept = []                     # the tracker inputs of the timed frames (for the reference-loop leg of cpu_baseline)
@@ -207,7 +211,8 @@ def stream_record(cfg, device, precision, n_frames=48):
         kept.append([(x.tlwh.copy(), x.confidence, x.feature.copy()) for x in dets])
     tracker.close()
     total = t_det + t_glue + t_assoc
-    return {"what": "one stream, batch 1: Session.run -> create_obj_infos -> NMS -> Tracker.predict/update (GPU cosine metric)",
+    return {"what": "one stream, batch 1: Session.run -> create_obj_infos -> NMS -> Tracker.predict/update (GPU cosine metric)"
+                    + ("; uint8 frame in, pooled [R,256] features out" if opt_in else "; float32 frame in, [R,256,7,7] features out (reference semantics)"),
             "frames": n_frames, "objects_per_frame": n_obj / n_frames, "detect_ms": t_det / n_frames * 1e3,
             "glue_ms": t_glue / n_frames * 1e3, "associate_ms": t_assoc / n_frames * 1e3,
             "fps_per_stream": n_frames / total, "live_tracks_last_frame": len(live),
@@ -387,7 +392,11 @@ def main():
         (dts,) = replicas.max_over_ranks([sustained["dt"] / sustained["steps"]], device="cuda")
         sustained = {"value": replicas.aggregate_fps(BATCH, dts, world), "unit": "frames/s", "seconds": sustained["seconds"],
                      "steps_rank0": sustained["steps"], "ms_per_step": dts * 1e3, "clocks": sustained["clocks"]}
-    stream = None if (args.no_stream or rank != 0) else stream_record(cfg, local_rank, args.precision)
+    stream = stream_opt = None
+    if not args.no_stream and rank == 0:
+        stream = stream_record(cfg, local_rank, args.precision)
+        stream_opt = stream_record(cfg, local_rank, args.precision, opt_in=True)
+        stream_opt.pop("_dets", None)
     value = replicas.aggregate_fps(args.steps * BATCH, dt, world)
     e2e_value = replicas.aggregate_fps(args.steps * BATCH, dt_e2e, world)
     h2d = host[0].numel() * host[0].element_size()
@@ -439,7 +448,7 @@ def main():
                         "sync_call_value": replicas.aggregate_fps(args.steps * BATCH, dt_sync, world)},
                 "gpu_launches": det.kernel_launches() * args.steps,
                 "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
-                "phase_ms": phase_ms, "sustained": sustained, "stream_c1": stream}
+                "phase_ms": phase_ms, "sustained": sustained, "stream_c1": stream, "stream_c1_uint8_pooled": stream_opt}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()              # rank 0 is the only one with the stream / cpu_baseline legs: the others wait for it

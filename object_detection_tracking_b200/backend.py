@@ -66,11 +66,15 @@ class Mask_RCNN_FPN:
 
     is_multi = False
 
-    def __init__(self, config, gpuid=0, precision="split", input_dtype="float32"):
+    def __init__(self, config, gpuid=0, precision="split", input_dtype="float32", feat_mode=0):
         self.config = normalize_config(config)
         self.gpuid = gpuid
         self.precision = precision
         self.input_dtype = input_dtype
+        # what `fpn_box_feat` returns: 0 = the reference's [R,256,7,7]; 1 / 2 / 3 = the drivers' emb_agg_method avg / max /
+        # spatial computed on the GPU ([R,256] / [R,256] / [R,49], obj_detect_tracking_multi_queuer.py:482-495): 49x fewer
+        # bytes over PCIe, and create_obj_infos / preprocess_detections take the pooled form as it is
+        self.feat_mode = int(feat_mode)
         self.num_class = self.config.num_class
         self.image = TensorHandle(self, "image:0")
         self.final_boxes = TensorHandle(self, "final_boxes:0")          # exported names: models.py:138-146
@@ -136,7 +140,7 @@ class Mask_RCNN_FPN:
         B, H, W, _ = frames.shape
         det = self._detector(B, H, W)
         want_feat = any(f is self.fpn_box_feat for f in fetches)
-        out = det.detect_host(frames, want_feat=want_feat)
+        out = det.detect_host(frames, feat_mode=self.feat_mode, want_feat=want_feat)
         valid = out["valid"]
         res = []
         for f in fetches:

@@ -324,8 +324,8 @@ def create_obj_infos(cur_frame, final_boxes, final_probs, final_labels, box_feat
     """Drop-in for deep_sort.utils.create_obj_infos (deep_sort/utils.py:5-44) -> list of Detection."""
     xywh, confs, f = _select_detections(final_boxes, final_probs, final_labels, box_feats, targetid2class, tracking_objs,
                                         min_confidence, scale, is_coco_model, coco_to_actev_mapping)
-    return [Detection(xywh[k].tolist(), confs[k], f[k].tolist()) for k in range(len(confs))
-            if not xywh[k, 3] < min_detection_height]
+    # (the reference builds Python lists here; Detection converts to float64 / float32 arrays either way)
+    return [Detection(xywh[k], confs[k], f[k]) for k in range(len(confs)) if not xywh[k, 3] < min_detection_height]
 
 
 def preprocess_detections(final_boxes, final_probs, final_labels, box_feats, targetid2class, tracking_objs, min_confidence,
