@@ -305,7 +305,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* res_full = bars + 2 * kMaxStages + 4;                       // [2 halves][kEpiSlotsMax]
   uint64_t* c_full = bars + 2 * kMaxStages + 4 + 2 * kEpiSlotsMax;      // [kAccRingMax] ACC chunk accumulator ready
   uint64_t* c_empty = c_full + kAccRingMax;                             // [kAccRingMax] ACC chunk accumulator drained
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(c_empty + kAccRingMax);
+  uint64_t* grp_ready = c_empty + kAccRingMax;                          // [2 halves][kEpiSlotsMax] staged group written by its four warps
+  uint64_t* slot_free = grp_ready + kEpiHalves * kEpiSlotsMax;          // [2 halves][kEpiSlotsMax] store of the slot has read it (no-residual layers)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(slot_free + kEpiHalves * kEpiSlotsMax);
   uint8_t* epi = tiles + p.epi_off;
 
   // broadcast from lane 0 so that the compiler treats the warp index (and everything derived from it) as warp-uniform
@@ -333,6 +335,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     for (int i = 0; i < kAccRingMax; ++i) {
       mbar_init(&c_full[i], 1);
       mbar_init(&c_empty[i], kEpiWarps);
+    }
+    for (int i = 0; i < kEpiHalves * kEpiSlotsMax; ++i) {
+      mbar_init(&grp_ready[i], 4);     // one arrive per epilogue warp of the half
+      mbar_init(&slot_free[i], 1);
     }
     fence_mbar_init();
     fence_proxy_async();
@@ -501,6 +507,97 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
       }
     }
+   } else if (p.epi_mode == 1) {
+    // ===================== output TMA warps (warp 2: column half 0, warp 3: column half 1) =====================
+    // Staged output: the four epilogue warps of a half only compute -- they take a staging slot when its residual has
+    // landed (or, without a residual, when the slot's previous store has read it), write the finished group into it and
+    // arrive on grp_ready.  This warp does everything asynchronous for the half: it waits for the group, issues the TMA
+    // store, and keeps the residual prefetch nslots-1 groups ahead (also across tile boundaries).  Until round 2 the first
+    // epilogue warp of the half did this on top of its share of the math, behind a 128-thread named barrier per group: ncu's
+    // stall sampling showed `barrier` as the top stall of the epilogue warps in the K <= 256 residual layers.
+    const int hf = warp - 2;
+    const int nch = p.block_n >> 4;
+    const int h0 = (nch + 1) >> 1;
+    const int c_beg = hf ? h0 : 0;
+    const int my_n = hf ? nch - h0 : h0;
+    const bool has_res = p.res_hi != nullptr;
+    const bool res_lo = SPLIT && p.res_lo != nullptr;
+    const int grp = p.epi_grp;
+    const int nslots = p.epi_slots;
+    uint8_t* ring = tiles + p.epi_off + hf * ring_bytes;
+    uint64_t* rfull = res_full + hf * kEpiSlotsMax;
+    uint64_t* gready = grp_ready + hf * kEpiSlotsMax;
+    uint64_t* sfree = slot_free + hf * kEpiSlotsMax;
+    int la_tile = blockIdx.x, la_c = 0, la_slot = 0;   // look-ahead cursor of the residual prefetch
+    auto issue_res_group = [&]() {
+      if (la_tile >= p.num_tiles) return;
+      const int m_blk = la_tile / p.num_n_blocks;
+      const int n_blk = la_tile - m_blk * p.num_n_blocks;
+      const int gn = (my_n - la_c) < grp ? (my_n - la_c) : grp;
+      const int col = n_blk * p.block_n + (c_beg + la_c) * 16;
+      uint8_t* b = ring + la_slot * slot_bytes;
+      uint64_t* bar = &rfull[la_slot];
+      if (elect_one()) {
+        mbar_expect_tx(bar, gn * kEpiPlaneBytes * (res_lo ? 2 : 1));
+        if (p.epi_wide) {   // one 32-column box per plane (groups are always full in wide mode)
+          tma_load_2d(b, &tmR_hi, bar, col, m_blk * kBlockM);
+          if (res_lo) tma_load_2d(b + 2 * kEpiPlaneBytes, &tmR_lo, bar, col, m_blk * kBlockM);
+        } else {
+          for (int u = 0; u < gn; ++u) {
+            tma_load_2d(b + u * p.epi_chunk_bytes, &tmR_hi, bar, col + u * 16, m_blk * kBlockM);
+            if (res_lo) tma_load_2d(b + u * p.epi_chunk_bytes + kEpiPlaneBytes, &tmR_lo, bar, col + u * 16, m_blk * kBlockM);
+          }
+        }
+      }
+      __syncwarp();
+      la_c += gn;
+      if (la_c >= my_n) {
+        la_c = 0;
+        la_tile += gridDim.x;
+      }
+      if (++la_slot == nslots) la_slot = 0;
+    };
+    if (my_n > 0) {
+      if (has_res)
+        for (int i = 0; i < nslots - 1; ++i) issue_res_group();
+      int slot = 0, prev_slot = -1;
+      uint32_t gph = 0;        // phase bits of gready[]
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_blocks;
+        const int n_blk = tile - m_blk * p.num_n_blocks;
+        const int n0 = n_blk * p.block_n;
+        for (int c = 0; c < my_n; c += grp) {
+          const int gn = (my_n - c) < grp ? (my_n - c) : grp;
+          const int nb = n0 + (c_beg + c) * 16;
+          uint8_t* sb = ring + slot * slot_bytes;
+          mbar_wait(&gready[slot], (gph >> slot) & 1u);
+          gph ^= 1u << slot;
+          if (elect_one()) {
+            // every earlier store must be done reading its slot before the look-ahead load below refills the slot of
+            // the previous group (residual ring) or before that slot is handed back to the epilogue warps (two slots)
+            bulk_wait_read<0>();
+            if (p.epi_wide) {
+              tma_store_2d(&tmO_hi, sb, nb, m_blk * kBlockM);
+              if (SPLIT && p.out_lo != nullptr) tma_store_2d(&tmO_lo, sb + 2 * kEpiPlaneBytes, nb, m_blk * kBlockM);
+            } else {
+              for (int t = 0; t < gn; ++t) {
+                tma_store_2d(&tmO_hi, sb + t * p.epi_chunk_bytes, nb + t * 16, m_blk * kBlockM);
+                if (SPLIT && p.out_lo != nullptr)
+                  tma_store_2d(&tmO_lo, sb + t * p.epi_chunk_bytes + kEpiPlaneBytes, nb + t * 16, m_blk * kBlockM);
+              }
+            }
+            bulk_commit();
+            if (!has_res && prev_slot >= 0) mbar_arrive(&sfree[prev_slot]);   // its store was among those waited for above
+          }
+          __syncwarp();
+          if (has_res) issue_res_group();
+          prev_slot = slot;
+          if (++slot == nslots) slot = 0;
+        }
+      }
+      if (elect_one()) bulk_wait_all();   // the output must be globally written before the CTA retires
+      __syncwarp();
+    }
    }
   } else if (warp < 4 + kEpiWarps) {
     if (ACC) setmaxnreg_inc<224>();
@@ -528,53 +625,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const bool staged = p.epi_mode == 1;
     const bool has_res = p.res_hi != nullptr;
     const bool res_lo = SPLIT && p.res_lo != nullptr;
-    // TMA traffic of this half is issued by its first warp, converged, through one elected lane: coordinates, staging
-    // addresses and barriers are then warp-uniform values (issued by a lone thread, every bulk-tensor instruction was
-    // wrapped in an elect / broadcast / compare waterfall of ~15 instructions, ~300 per group on the group's critical path)
-    const bool issuer = ew == 0;
+    // the TMA stores and the residual prefetch of this half are issued by its output TMA warp (warp 2 + hf, see above)
     const int grp = p.epi_grp;
     const int nslots = p.epi_slots;
-    // before group k+1 may overwrite its slot, the store of group k+1-nslots must be done reading it; with a residual
-    // the look-ahead load issued right after store k refills the slot of group k-1
-    const bool wait_all_reads = has_res || nslots == 2;
     uint8_t* ring = epi + hf * ring_bytes;
     uint64_t* rfull = res_full + hf * kEpiSlotsMax;
-    const int bar_id = 1 + hf;
-    int slot = 0, la_slot = 0;
-    uint32_t rph = 0;        // phase bits of rfull[]
-    int la_tile = blockIdx.x, la_c = 0;   // look-ahead cursor of the residual prefetch (elected thread only)
-    auto issue_res_group = [&]() {   // called by every thread of the half (the cursor is warp-uniform state)
-      if (la_tile >= p.num_tiles || my_n == 0) return;
-      const int m_blk = la_tile / p.num_n_blocks;
-      const int n_blk = la_tile - m_blk * p.num_n_blocks;
-      const int gn = (my_n - la_c) < grp ? (my_n - la_c) : grp;
-      const int col = n_blk * p.block_n + (c_beg + la_c) * 16;
-      uint8_t* b = ring + la_slot * slot_bytes;
-      uint64_t* bar = &rfull[la_slot];
-      if (issuer) {
-        if (elect_one()) {
-          mbar_expect_tx(bar, gn * kEpiPlaneBytes * (res_lo ? 2 : 1));
-          if (p.epi_wide) {   // one 32-column box per plane (groups are always full in wide mode)
-            tma_load_2d(b, &tmR_hi, bar, col, m_blk * kBlockM);
-            if (res_lo) tma_load_2d(b + 2 * kEpiPlaneBytes, &tmR_lo, bar, col, m_blk * kBlockM);
-          } else {
-            for (int u = 0; u < gn; ++u) {
-              tma_load_2d(b + u * p.epi_chunk_bytes, &tmR_hi, bar, col + u * 16, m_blk * kBlockM);
-              if (res_lo) tma_load_2d(b + u * p.epi_chunk_bytes + kEpiPlaneBytes, &tmR_lo, bar, col + u * 16, m_blk * kBlockM);
-            }
-          }
-        }
-        __syncwarp();
-      }
-      la_c += gn;
-      if (la_c >= my_n) {
-        la_c = 0;
-        la_tile += gridDim.x;
-      }
-      if (++la_slot == nslots) la_slot = 0;
-    };
-    if (staged && has_res)
-      for (int i = 0; i < nslots - 1; ++i) issue_res_group();
+    uint64_t* gready = grp_ready + hf * kEpiSlotsMax;
+    uint64_t* sfree = slot_free + hf * kEpiSlotsMax;
+    int slot = 0;
+    uint32_t rph = 0;        // phase bits of rfull[] (residual landed) / of sfree[] (previous store has read the slot)
 
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.num_n_blocks;
@@ -605,8 +664,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         const int u = grp == 2 ? (c & 1) : 0;      // position inside the group
         uint8_t* sb = ring + slot * slot_bytes;
-        if (u == 0 && has_res) {
-          mbar_wait(&rfull[slot], (rph >> slot) & 1u);
+        if (u == 0) {   // first chunk of a group: take the slot
+          if (has_res) mbar_wait(&rfull[slot], (rph >> slot) & 1u);            // its residual has landed
+          else mbar_wait(&sfree[slot], ((rph >> slot) & 1u) ^ 1u);             // its previous store has read it (first use: free)
           rph ^= 1u << slot;
         }
         {
@@ -631,34 +691,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                                        reinterpret_cast<uint4*>(hp + lo_off + c0), reinterpret_cast<uint4*>(hp + lo_off + c1), n,
                                        has_res, res_lo, amax);
         }
-        if (u == grp - 1 || c == my_n - 1) {
+        if (u == grp - 1 || c == my_n - 1) {   // group complete: hand it to the output TMA warp
           fence_proxy_async();
-          if (issuer) {
-            if (elect_one()) {
-              if (wait_all_reads) bulk_wait_read<0>();
-              else bulk_wait_read<1>();
-            }
-            __syncwarp();
-          }
-          named_bar_sync(bar_id, 128);
-          if (issuer) {
-            if (elect_one()) {
-              const int nb = n - u * 16;
-              if (p.epi_wide) {
-                tma_store_2d(&tmO_hi, sb, nb, m_blk * kBlockM);
-                if (SPLIT && p.out_lo != nullptr) tma_store_2d(&tmO_lo, sb + 2 * kEpiPlaneBytes, nb, m_blk * kBlockM);
-              } else {
-                for (int t = 0; t <= u; ++t) {
-                  tma_store_2d(&tmO_hi, sb + t * p.epi_chunk_bytes, nb + t * 16, m_blk * kBlockM);
-                  if (SPLIT && p.out_lo != nullptr)
-                    tma_store_2d(&tmO_lo, sb + t * p.epi_chunk_bytes + kEpiPlaneBytes, nb + t * 16, m_blk * kBlockM);
-                }
-              }
-              bulk_commit();
-            }
-            __syncwarp();
-          }
-          if (has_res) issue_res_group();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&gready[slot]);
           if (++slot == nslots) slot = 0;
         }
       };
@@ -723,10 +759,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
       // inf included; a NaN can only follow an inf, which an earlier launch has flagged
       if (p.range_flag != nullptr && amax > 65504.f) atomicOr(p.range_flag, 1u);
-    }
-    if (staged && issuer) {   // the output must be globally written before the CTA retires
-      if (elect_one()) bulk_wait_all();
-      __syncwarp();
     }
   }
   tc_fence_before();
