@@ -309,6 +309,10 @@ int b2_op_conv2d(int device, const float* x, const float* w, const float* bias, 
                  int Cin, int R, int S, int Cout, int stride, int dil, int pad_t, int pad_b, int pad_l, int pad_r,
                  int relu, int res_shift, int impl, int split, int a_mode, float* out);
 
+/* Number of conv launches of this process that ran on CTA pairs (tcgen05 cta_group::2; opt-in through the environment
+ * variable B2_PAIR=<min K-blocks>): lets the tests assert that the hook is live. */
+long long b2_conv_pair_launches(void);
+
 #ifdef __cplusplus
 }
 #endif

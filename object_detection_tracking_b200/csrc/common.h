@@ -92,6 +92,7 @@ struct ConvPlan;
 ConvPlan* conv_tc_plan_create(const ConvDesc& d, const ConvWeights& w, const ConvIO& io, bool split, int num_sms);
 void conv_tc_plan_destroy(ConvPlan*);
 int conv_tc_launch(const ConvPlan*, cudaStream_t);
+long long conv_tc_pair_launches();   // conv launches of this process that used CTA pairs (B2_PAIR)
 int conv_tc_init();   // resolves the driver entry point for cuTensorMapEncode*
 
 // CUDA-core reference implementation of exactly the same contract (validation + odd shapes).

@@ -72,6 +72,8 @@ struct ConvTcParams {
   int epi_wide;      // staged, epi_grp == 2: a group is one [128 rows][32 fp16] box per plane (64-byte swizzle, one TMA op)
   uint32_t epi_chunk_bytes;   // staged: bytes of one chunk buffer (4 KB hi plane, + 4 KB lo plane in split precision)
   uint32_t epi_off;  // byte offset of the epilogue staging buffers inside the tile area
+  int num_pair_tiles;   // PAIR: tiles of 256 rows (two m-blocks, one per CTA of the pair) x block_n columns
+  int pair_bswap;       // PAIR, test hook: the CTAs load each other's half of the B tile
 };
 
 constexpr int kEpiSlotsMax = 3;
@@ -252,16 +254,50 @@ constexpr float kAccDelta2 = 1.7e-7f;   // chunks of two K-blocks (seven truncat
 constexpr int kAccRingMax = 6;
 constexpr int kAccMaxChunks = 8 / kEpiHalves; // ACC tiles are at most 128 columns wide -> chunks of 16 per column half
 
+// mbarrier wait of the PAIR kernel.  Build variant -DB2_PAIR_DIAG (bring-up of the two-CTA barrier protocol without a
+// local GPU): a wait that lasts longer than ~0.5 s records who waited for what (role << 28 | CTA rank << 27 | tile << 8 |
+// K-block) in g_pair_diag and every wait of the grid (and of later launches) returns at once, so a protocol error ends as a
+// report on the host (conv_tc_launch) instead of a hung box.
+#ifdef B2_PAIR_DIAG
+__device__ unsigned int g_pair_diag[2];
+#endif
+template <bool PAIR>
+__device__ __forceinline__ void mbar_wait_r(uint64_t* bar, uint32_t parity, uint32_t role, uint32_t crank, int tile, int kb) {
+#ifdef B2_PAIR_DIAG
+  if (PAIR) {
+    if (*reinterpret_cast<volatile unsigned int*>(&g_pair_diag[0]) != 0u) return;
+    const long long t0 = clock64();
+    for (uint32_t spin = 0;; ++spin) {
+      if (mbar_try_wait(bar, parity)) return;
+      if ((spin & 1023u) == 1023u) {
+        if (*reinterpret_cast<volatile unsigned int*>(&g_pair_diag[0]) != 0u) return;
+        if (clock64() - t0 > 1000000000LL) {
+          atomicCAS(&g_pair_diag[0], 0u, (role << 28) | (crank << 27) | ((static_cast<uint32_t>(tile) & 0x7FFFFu) << 8) |
+                                             (static_cast<uint32_t>(kb) & 0xFFu));
+          return;
+        }
+      }
+    }
+  }
+#endif
+  mbar_wait(bar, parity);
+}
+
 // ACC drain: fold this thread's share (my_n chunks of 16 columns of its row) of one chunk accumulator into the
 // running sums with round-to-nearest adds.  All tcgen05.ld are in flight before the single wait; the accumulator is
 // handed back to the MMA issuer as soon as the values sit in registers, before the adds.
-template <bool FMA_LO>
+// PAIR: the accumulator belongs to the pair's MMA issuer, which runs in the even CTA and waits on ITS barrier for the
+// epilogue warps of both CTAs.
+template <bool FMA_LO, bool PAIR>
 __device__ __forceinline__ void acc_fold(float (&sums)[kAccMaxChunks * 16], uint32_t tsrc, int my_n, uint64_t* release_bar,
                                          int lane) {
   auto release = [&]() {
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(release_bar);
+    if (lane == 0) {
+      if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(release_bar), 0));
+      else mbar_arrive(release_bar);
+    }
   };
   auto add = [&](int u, const uint32_t (&t)[16]) {
 #pragma unroll
@@ -284,7 +320,14 @@ __device__ __forceinline__ void acc_fold(float (&sums)[kAccMaxChunks * 16], uint
   }
 }
 
-template <bool SPLIT, bool ACC, bool SWISH>
+// PAIR (split + ACC only): the grid is launched in clusters of two CTAs that share 256-row tiles through
+// tcgen05.mma.cta_group::2 -- CTA r of a pair loads the A rows of m-block 2*mp + r and HALF of the tile's B rows, the even
+// CTA's MMA warp issues for both, each CTA finds its own 128 x block_n accumulators in its own TMEM, so everything after
+// the MMA (chunk drains, output stage) is the single-CTA code.  Barrier plumbing of the pair: all operand loads count on
+// the leader's full barrier (it expects both CTAs' bytes); tcgen05.commit multicasts every completion (stage free, chunk
+// ready, tile ready) to the same barrier in both CTAs; the "accumulator drained" barriers live in the leader and collect
+// the epilogue warps of both CTAs.
+template <bool SPLIT, bool ACC, bool SWISH, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -329,12 +372,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kEpiWarps);   // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], PAIR ? 2 * kEpiWarps : kEpiWarps);   // one arrive per epilogue warp (of both CTAs)
     }
     for (int i = 0; i < 2 * kEpiSlotsMax; ++i) mbar_init(&res_full[i], 1);
     for (int i = 0; i < kAccRingMax; ++i) {
       mbar_init(&c_full[i], 1);
-      mbar_init(&c_empty[i], kEpiWarps);
+      mbar_init(&c_empty[i], PAIR ? 2 * kEpiWarps : kEpiWarps);
     }
     for (int i = 0; i < kEpiHalves * kEpiSlotsMax; ++i) {
       mbar_init(&grp_ready[i], 4);     // one arrive per epilogue warp of the half
@@ -344,11 +387,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     fence_proxy_async();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_holder, kTmemCols);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_pair(tmem_holder, kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_holder, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync();   // the peer's barriers are initialised before anything of this CTA signals them
   tc_fence_after();
 #ifdef B2_PDL
   // Build variant (tools/build_variant.sh pdl -DB2_PDL=1), round-2 experiment: programmatic dependent launch.  The next
@@ -360,6 +409,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #endif
   const uint32_t tmem_base = *tmem_holder;
   if (tmem_base != 0) __trap();   // the MMA issuer addresses TMEM from column 0 / lane 0 (whole-TMEM allocation)
+  // tile schedule: static round robin over CTAs (over CTA pairs in PAIR mode: pair tile = (m-block pair, n-block))
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const int tile_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int tile_count = PAIR ? p.num_pair_tiles : p.num_tiles;
 
   const uint32_t a_lo_off = kABytes;
   const uint32_t b_hi_off = SPLIT ? 2 * kABytes : kABytes;
@@ -378,11 +432,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.num_n_blocks;
-        const int n_blk = tile - m_blk * p.num_n_blocks;
-        const int m0 = m_blk * kBlockM;
-        const int n0 = n_blk * p.block_n;
+      for (int tile = tile_first; tile < tile_count; tile += tile_step) {
+        const int m_row = tile / p.num_n_blocks;
+        const int n_blk = tile - m_row * p.num_n_blocks;
+        const int m_blk = PAIR ? 2 * m_row + static_cast<int>(crank) : m_row;   // an odd m-block count leaves the last
+        const int m0 = m_blk * kBlockM;                                           // pair a block past M: TMA zero-fills it
+        // PAIR: this CTA loads block_n/2 of the tile's B rows (the MMA reads the other half from the peer)
+        const int n0 = n_blk * p.block_n + (PAIR ? static_cast<int>(crank ^ static_cast<uint32_t>(p.pair_bswap)) * (p.block_n >> 1) : 0);
         int img = 0, ch = 0, cw = 0;
         if (p.a_mode == 1) {
           img = m0 / p.HoWo;
@@ -394,9 +450,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         int tap = 0, cb = 0;   // K-block = (filter tap, 64-channel block)
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_r<PAIR>(&empty_bar[stage], phase ^ 1, 1, crank, tile, kb);
           uint8_t* st = tiles + static_cast<size_t>(stage) * p.stage_bytes;
-          if (elect_one()) {
+          if (PAIR) {
+            // both CTAs' loads count on the LEADER's full barrier, which expects the bytes of both
+            const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (elect_one()) {
+              if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * p.stage_bytes);
+              if (p.a_mode == 1) {
+                const int r = tap / p.S;
+                const int s = tap - r * p.S;
+                const uint16_t ow = static_cast<uint16_t>(s * p.dil);
+                const uint16_t oh = static_cast<uint16_t>(r * p.dil);
+                tma_load_im2col_4d_pair(st, &tmA_hi, fb, cb * kBlockK, cw, ch, img, ow, oh);
+                tma_load_im2col_4d_pair(st + a_lo_off, &tmA_lo, fb, cb * kBlockK, cw, ch, img, ow, oh);
+              } else {
+                tma_load_2d_pair(st, &tmA_hi, fb, cb * kBlockK, m0);
+                tma_load_2d_pair(st + a_lo_off, &tmA_lo, fb, cb * kBlockK, m0);
+              }
+              tma_load_2d_pair(st + b_hi_off, &tmB_hi, fb, kb * kBlockK, n0);
+              tma_load_2d_pair(st + b_lo_off, &tmB_lo, fb, kb * kBlockK, n0);
+            }
+          } else if (elect_one()) {
             mbar_expect_tx(&full_bar[stage], p.stage_bytes);
             if (p.a_mode == 1) {
               const int r = tap / p.S;
@@ -425,12 +500,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer (PAIR: the even CTA's, for both; the odd CTA's warp 1 idles) =====================
     // The whole warp runs the loop converged and one elected lane issues: every MMA operand (descriptors, TMEM
     // address, instruction descriptor) is then computed by warp-uniform code and lives in uniform registers.  (Run by
     // lane 0 alone, each tcgen05.mma was wrapped in an elect / broadcast / compare waterfall -- 276 instructions per
     // K-block, which bounded the MMA-bound layers: ncu showed this warp never waiting, only issuing.)
-    {
+    if (!PAIR || crank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -444,8 +519,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       constexpr uint64_t kDescHi = static_cast<uint64_t>((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
       // this CTA owns the whole TMEM of its SM (512 columns, one CTA per SM): the allocation starts at column 0, lane 0
       // (checked after the allocation), so the accumulator addresses are plain constants here
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[as], aphase ^ 1);
+      for (int tile = tile_first; tile < tile_count; tile += tile_step) {
+        mbar_wait_r<PAIR>(&tmem_empty[as], aphase ^ 1, 4, crank, tile, 0);
         tc_fence_after();
         // plain: acc0 at as*256, acc1 at as*256+128.  ACC: acc0 chunk buffers at 0 / 128, acc1 at 256 + as*128.
         uint32_t acc0 = as * acc_stage_cols;
@@ -453,11 +528,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         int kq = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           if (ACC && kq == 0) {
-            mbar_wait(&c_empty[cbuf], cphase ^ 1);
+            mbar_wait_r<PAIR>(&c_empty[cbuf], cphase ^ 1, 3, crank, tile, kb);
             tc_fence_after();
             acc0 = cbuf * p.acc_stride;
           }
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_r<PAIR>(&full_bar[stage], phase, 2, crank, tile, kb);
           tc_fence_after();
           const uint32_t st = tiles_u32 + static_cast<uint32_t>(stage) * p.stage_bytes;
           const uint32_t d_a_hi = ((st >> 4) & 0x3FFFu) | 0x10000u;
@@ -472,17 +547,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               const uint64_t a_hi = kDescHi | (d_a_hi + ko);
               const uint64_t b_hi = kDescHi | (d_b_hi + ko);
               const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
-              umma_f16(acc0, a_hi, b_hi, p.idesc, ACC ? ((kq > 0 || k > 0) ? 1u : 0u) : first);
-              if (SPLIT) {
+              if (PAIR) {
                 const uint64_t a_lo = kDescHi | (d_a_lo + ko);
                 const uint64_t b_lo = kDescHi | (d_b_lo + ko);
-                umma_f16(acc1, a_hi, b_lo, p.idesc, first);
-                umma_f16(acc1, a_lo, b_hi, p.idesc, 1u);
+                umma_f16_pair(acc0, a_hi, b_hi, p.idesc, (kq > 0 || k > 0) ? 1u : 0u);
+                umma_f16_pair(acc1, a_hi, b_lo, p.idesc, first);
+                umma_f16_pair(acc1, a_lo, b_hi, p.idesc, 1u);
+              } else {
+                umma_f16(acc0, a_hi, b_hi, p.idesc, ACC ? ((kq > 0 || k > 0) ? 1u : 0u) : first);
+                if (SPLIT) {
+                  const uint64_t a_lo = kDescHi | (d_a_lo + ko);
+                  const uint64_t b_lo = kDescHi | (d_b_lo + ko);
+                  umma_f16(acc1, a_hi, b_lo, p.idesc, first);
+                  umma_f16(acc1, a_lo, b_hi, p.idesc, 1u);
+                }
               }
             }
-            umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
-            if (chunk_end) umma_commit(&c_full[cbuf]);   // chunk accumulator complete -> epilogue sums it
-            if (kb == p.num_kb - 1) umma_commit(&tmem_full[as]);        // accumulator complete -> epilogue
+            if (PAIR) {   // every completion goes to the same barrier in both CTAs
+              umma_commit_pair(&empty_bar[stage]);
+              if (chunk_end) umma_commit_pair(&c_full[cbuf]);
+              if (kb == p.num_kb - 1) umma_commit_pair(&tmem_full[as]);
+            } else {
+              umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
+              if (chunk_end) umma_commit(&c_full[cbuf]);   // chunk accumulator complete -> epilogue sums it
+              if (kb == p.num_kb - 1) umma_commit(&tmem_full[as]);        // accumulator complete -> epilogue
+            }
           }
           __syncwarp();
           if (ACC) {
@@ -528,11 +617,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint64_t* rfull = res_full + hf * kEpiSlotsMax;
     uint64_t* gready = grp_ready + hf * kEpiSlotsMax;
     uint64_t* sfree = slot_free + hf * kEpiSlotsMax;
-    int la_tile = blockIdx.x, la_c = 0, la_slot = 0;   // look-ahead cursor of the residual prefetch
+    int la_tile = tile_first, la_c = 0, la_slot = 0;   // look-ahead cursor of the residual prefetch
     auto issue_res_group = [&]() {
-      if (la_tile >= p.num_tiles) return;
-      const int m_blk = la_tile / p.num_n_blocks;
-      const int n_blk = la_tile - m_blk * p.num_n_blocks;
+      if (la_tile >= tile_count) return;
+      const int m_row = la_tile / p.num_n_blocks;
+      const int n_blk = la_tile - m_row * p.num_n_blocks;
+      const int m_blk = PAIR ? 2 * m_row + static_cast<int>(crank) : m_row;
       const int gn = (my_n - la_c) < grp ? (my_n - la_c) : grp;
       const int col = n_blk * p.block_n + (c_beg + la_c) * 16;
       uint8_t* b = ring + la_slot * slot_bytes;
@@ -553,7 +643,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       la_c += gn;
       if (la_c >= my_n) {
         la_c = 0;
-        la_tile += gridDim.x;
+        la_tile += tile_step;
       }
       if (++la_slot == nslots) la_slot = 0;
     };
@@ -562,15 +652,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int i = 0; i < nslots - 1; ++i) issue_res_group();
       int slot = 0, prev_slot = -1;
       uint32_t gph = 0;        // phase bits of gready[]
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.num_n_blocks;
-        const int n_blk = tile - m_blk * p.num_n_blocks;
+      for (int tile = tile_first; tile < tile_count; tile += tile_step) {
+        const int m_row = tile / p.num_n_blocks;
+        const int n_blk = tile - m_row * p.num_n_blocks;
+        const int m_blk = PAIR ? 2 * m_row + static_cast<int>(crank) : m_row;
         const int n0 = n_blk * p.block_n;
         for (int c = 0; c < my_n; c += grp) {
           const int gn = (my_n - c) < grp ? (my_n - c) : grp;
           const int nb = n0 + (c_beg + c) * 16;
           uint8_t* sb = ring + slot * slot_bytes;
-          mbar_wait(&gready[slot], (gph >> slot) & 1u);
+          mbar_wait_r<PAIR>(&gready[slot], (gph >> slot) & 1u, 9, crank, tile, c);
           gph ^= 1u << slot;
           if (elect_one()) {
             // every earlier store must be done reading its slot before the look-ahead load below refills the slot of
@@ -635,9 +726,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     int slot = 0;
     uint32_t rph = 0;        // phase bits of rfull[] (residual landed) / of sfree[] (previous store has read the slot)
 
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.num_n_blocks;
-      const int n_blk = tile - m_blk * p.num_n_blocks;
+    for (int tile = tile_first; tile < tile_count; tile += tile_step) {
+      const int m_row = tile / p.num_n_blocks;
+      const int n_blk = tile - m_row * p.num_n_blocks;
+      const int m_blk = PAIR ? 2 * m_row + static_cast<int>(crank) : m_row;
       const int n0 = n_blk * p.block_n;
       // direct mode: this thread's output / residual pixel
       size_t opix = 0, rpix = 0;
@@ -665,8 +757,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int u = grp == 2 ? (c & 1) : 0;      // position inside the group
         uint8_t* sb = ring + slot * slot_bytes;
         if (u == 0) {   // first chunk of a group: take the slot
-          if (has_res) mbar_wait(&rfull[slot], (rph >> slot) & 1u);            // its residual has landed
-          else mbar_wait(&sfree[slot], ((rph >> slot) & 1u) ^ 1u);             // its previous store has read it (first use: free)
+          if (has_res) mbar_wait_r<PAIR>(&rfull[slot], (rph >> slot) & 1u, 7, crank, tile, c);   // its residual has landed
+          else mbar_wait_r<PAIR>(&sfree[slot], ((rph >> slot) & 1u) ^ 1u, 8, crank, tile, c);   // its previous store has read it (first use: free)
           rph ^= 1u << slot;
         }
         {
@@ -706,19 +798,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int nq = (p.num_kb + p.acc_kb - 1) / p.acc_kb;
         for (int q = 0; q < nq; ++q) {
           const int cbuf = ecbuf;
-          mbar_wait(&c_full[cbuf], ecphase);
+          mbar_wait_r<PAIR>(&c_full[cbuf], ecphase, 5, crank, tile, q);
           if (++ecbuf == p.acc_ring) {
             ecbuf = 0;
             ecphase ^= 1;
           }
           tc_fence_after();
-          acc_fold<false>(sums, tmem_base + lane_off + cbuf * p.acc_stride + c_beg * 16, p.dbg_nodrain ? 0 : my_n, &c_empty[cbuf], lane);
+          acc_fold<false, PAIR>(sums, tmem_base + lane_off + cbuf * p.acc_stride + c_beg * 16, p.dbg_nodrain ? 0 : my_n, &c_empty[cbuf], lane);
         }
         // the correction accumulator (hi*lo + lo*hi) is folded into the sums right away, which hands the tile's TMEM
         // stage back before the output stage starts
-        mbar_wait(&tmem_full[as], aphase);
+        mbar_wait_r<PAIR>(&tmem_full[as], aphase, 6, crank, tile, 0);
         tc_fence_after();
-        acc_fold<true>(sums, tmem_base + lane_off + (p.acc_ring + as) * p.acc_stride + c_beg * 16, my_n, &tmem_empty[as], lane);
+        acc_fold<true, PAIR>(sums, tmem_base + lane_off + (p.acc_ring + as) * p.acc_stride + c_beg * 16, my_n, &tmem_empty[as], lane);
 #pragma unroll
         for (int c = 0; c < kAccMaxChunks; ++c) {
           if (c < my_n) {
@@ -763,9 +855,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync();   // neither CTA retires (shared memory, TMEM, barriers) while its peer may still signal it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -811,6 +905,7 @@ struct ConvPlan {
   ConvTcParams p;
   bool split;
   bool acc;
+  bool pair;   // CTA pairs (cta_group::2): clusters of two CTAs share 256-row tiles
   int grid;
   size_t smem_bytes;
 };
@@ -833,6 +928,7 @@ int conv_tc_init() {
   B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   return 0;
 }
 
@@ -882,8 +978,20 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   B2_CHECK(p.num_n_blocks * p.block_n == w.Cout_pad, "conv_tc: Cout_pad not divisible by block_n");
   const int num_m_blocks = (p.M + kBlockM - 1) / kBlockM;
   p.num_tiles = num_m_blocks * p.num_n_blocks;
-  p.idesc = make_idesc_f16(kBlockM, p.block_n);
-  p.b_bytes = static_cast<uint32_t>(p.block_n) * kBlockK * 2;
+  // CTA pairs: an SM takes operands in at ~51 B/clk (tools/l2_fill_probe.cu), a 128x128 split tile needs 85 B/clk at full
+  // tensor-pipe rate; sharing the B tile between the two CTAs of a pair brings that to 64.  Layers with at least
+  // B2_PAIR K-blocks (the operand-bound ones), split + ACC, ReLU / linear epilogue.
+  pl->pair = false;
+  if (const char* e = getenv("B2_PAIR")) {
+    const int acc_kb_plan = d.acc_kb > 0 ? d.acc_kb : kAccChunkKb;
+    const bool acc_plan = split && d.acc_kb >= 0 && p.num_kb > acc_kb_plan && getenv("B2_NO_ACC") == nullptr;
+    pl->pair = acc_plan && atoi(e) > 0 && p.num_kb >= atoi(e) && p.block_n == 128 && d.relu != 2 && num_m_blocks >= 2 &&
+               num_sms >= 2;
+  }
+  p.num_pair_tiles = ((num_m_blocks + 1) / 2) * p.num_n_blocks;
+  p.pair_bswap = getenv("B2_PAIR_BSWAP") != nullptr ? 1 : 0;
+  p.idesc = make_idesc_f16(pl->pair ? 2 * kBlockM : kBlockM, p.block_n);
+  p.b_bytes = static_cast<uint32_t>(pl->pair ? p.block_n / 2 : p.block_n) * kBlockK * 2;   // per CTA
   p.stage_bytes = (kABytes + p.b_bytes) * (split ? 2 : 1);
   // TMA-staged epilogue: fp16 plane output with a 1:1 row mapping (no placement offset, no shifted residual)
   {
@@ -953,12 +1061,20 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
   // stage of tile i (with one K-block per chunk it stalls after two of four), and the drains per tile halve; costs
   // 8 instead of 4 truncating accumulation steps on those layers (all layers at 2: boxes 1.07e-3 px instead of 7.3e-4)
   if (const char* e = getenv("B2_ACC_KB_SHORTK")) if (p.num_kb <= 4 && atoi(e) > 0) p.acc_kb = atoi(e);
+  // experiment hook (round 2): longer chunks on the CTA-pair layers only -- every chunk hand-off of a pair crosses the two
+  // SMs twice (commit multicast out, "drained" arrive back), which a two-deep ring of one-K-block chunks does not cover
+  if (const char* e = getenv("B2_PAIR_ACC_KB")) if (pl->pair && atoi(e) > 0 && p.num_kb > atoi(e)) p.acc_kb = atoi(e);
   pl->acc = split && d.acc_kb >= 0 && p.num_kb > p.acc_kb && getenv("B2_NO_ACC") == nullptr;
   if (p.acc_kb >= 2) p.acc_delta = acc_delta2;
   p.acc_stride = p.block_n == 64 ? 64 : 128;
   p.acc_ring = p.block_n == 64 ? kAccRingMax : 2;   // (ring + 2 correction accumulators) * stride <= 512 columns
   if (const char* e = getenv("B2_ACC_MIN_KB")) pl->acc = pl->acc && p.num_kb > atoi(e);   // experiment hook
   pl->grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  if (pl->pair) {
+    B2_CHECK(pl->acc && p.acc_ring == 2, "conv_tc: CTA pairs need the ACC scheme on 128-column tiles");
+    const int pairs = num_sms / 2;
+    pl->grid = 2 * (p.num_pair_tiles < pairs ? p.num_pair_tiles : pairs);
+  }
   pl->smem_bytes = static_cast<size_t>(p.num_stages) * p.stage_bytes + epi_bytes + 1024 /*align*/ + 512 /*barriers*/;
   const int in_ld = d.in_ld > 0 ? d.in_ld : d.Cin;
   const bool plain = (d.R == 1 && d.S == 1 && d.stride == 1 && d.pad_t == 0 && d.pad_b == 0 && d.pad_l == 0 &&
@@ -999,7 +1115,8 @@ static int plan_build(ConvPlan* pl, const ConvDesc& d, const ConvWeights& w, con
       }
       small_tensor_fixup(mA, in_bytes);
     }
-    if (encode_2d(mB, b, w.K, w.Cout_pad, static_cast<uint64_t>(w.K) * 2, kBlockK, p.block_n)) return -1;
+    if (encode_2d(mB, b, w.K, w.Cout_pad, static_cast<uint64_t>(w.K) * 2, kBlockK, pl->pair ? p.block_n / 2 : p.block_n))
+      return -1;
   }
   if (!split) {
     pl->tmA_lo = pl->tmA_hi;
@@ -1040,6 +1157,9 @@ ConvPlan* conv_tc_plan_create(const ConvDesc& d, const ConvWeights& w, const Con
 
 void conv_tc_plan_destroy(ConvPlan* p) { delete p; }
 
+static long long g_pair_launches = 0;   // launches that took the CTA-pair path (tests check that the opt-in hook is live)
+long long conv_tc_pair_launches() { return g_pair_launches; }
+
 #ifdef B2_PDL
 template <typename K>
 static cudaError_t launch_pdl(K kernel, const ConvPlan* pl, cudaStream_t stream) {
@@ -1071,7 +1191,39 @@ int conv_tc_launch(const ConvPlan* pl, cudaStream_t stream) {
     return 0;
   }
 #endif
-  if (pl->split && pl->acc) {
+  if (pl->pair) {
+    ++g_pair_launches;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pl->grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = pl->smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B2_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true, false, true>, pl->tmA_hi, pl->tmA_lo, pl->tmB_hi, pl->tmB_lo,
+                               pl->tmO_hi, pl->tmO_lo, pl->tmR_hi, pl->tmR_lo, pl->p));
+#ifdef B2_PAIR_DIAG
+    {   // bring-up variant only (never inside a graph capture): report a wait that timed out
+      B2_CUDA(cudaStreamSynchronize(stream));
+      unsigned int diag[2] = {0, 0};
+      B2_CUDA(cudaMemcpyFromSymbol(diag, g_pair_diag, sizeof(diag)));
+      if (diag[0] != 0) {
+        fprintf(stderr, "conv_tc PAIR: wait timed out: role %u rank %u tile %u kb %u (grid %d, pair tiles %d, kb %d, stages %d, epi_mode %d)\n",
+                diag[0] >> 28, (diag[0] >> 27) & 1u, (diag[0] >> 8) & 0x7FFFFu, diag[0] & 0xFFu, pl->grid, pl->p.num_pair_tiles,
+                pl->p.num_kb, pl->p.num_stages, pl->p.epi_mode);
+        unsigned int zero[2] = {0, 0};
+        B2_CUDA(cudaMemcpyToSymbol(g_pair_diag, zero, sizeof(zero)));
+        set_error("conv_tc PAIR: barrier wait timed out");
+        return -1;
+      }
+    }
+#endif
+  } else if (pl->split && pl->acc) {
     if (sw) B2_CONV_LAUNCH(true, true, true);
     else B2_CONV_LAUNCH(true, true, false);
   } else if (pl->split) {

@@ -1622,6 +1622,8 @@ int b2_distance_matrix(int device, const float* a, int na, const float* b, int n
 }
 
 // ---- single conv op for kernel parity tests ---------------------------------------------------
+long long b2_conv_pair_launches(void) { return b2::conv_tc_pair_launches(); }
+
 int b2_op_conv2d(int device, const float* x, const float* w, const float* bias, const float* res, int B, int H, int W,
                  int Cin, int R, int S, int Cout, int stride, int dil, int pad_t, int pad_b, int pad_l, int pad_r,
                  int relu, int res_shift, int impl, int split, int a_mode, float* out) {

@@ -112,3 +112,26 @@ def test_direct_epilogue_path_equals_tma_staged_epilogue():
         subprocess.run([sys.executable, "-c", code, path], check=True, env=dict(os.environ, **env), timeout=300)
         outs.append(np.load(path))
     np.testing.assert_array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("name", ["1x1_bias_relu_res", "3x3_bigK_N256", "1x1_N1024", "3x3_dil2"])
+def test_cta_pair_path_is_bit_identical(name):
+    """The opt-in CTA-pair path (B2_PAIR: cta_group::2, two CTAs share 256-row tiles and the B operand) does the same
+    arithmetic in the same order as the single-CTA kernel: identical bits, including the odd m-block count of the first
+    case (the last pair's second block lies past M) and residual / ragged tiles."""
+    import os
+    from object_detection_tracking_b200 import engine
+    spec = CASES[name]
+    x, w, bias, res, _ = reference(spec, seed=11)
+    kw = dict(stride=spec[6], dil=spec[7], pad=spec[8], relu=bool(spec[10]), res_shift=spec[12], impl="tcgen05", split=True)
+    from object_detection_tracking_b200 import _lib
+    lib = _lib.load()
+    base = engine.op_conv2d(x, w, bias, res, **kw)
+    n0 = lib.b2_conv_pair_launches()
+    os.environ["B2_PAIR"] = "1"
+    try:
+        pair = engine.op_conv2d(x, w, bias, res, **kw)
+    finally:
+        os.environ.pop("B2_PAIR", None)
+    assert lib.b2_conv_pair_launches() == n0 + 1      # the pair kernel really ran
+    np.testing.assert_array_equal(base, pair)
